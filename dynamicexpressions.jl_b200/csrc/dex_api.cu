@@ -1,0 +1,631 @@
+// dex_api.cu — the C ABI of libdexb200.so (include/dexb200.h): contexts, operator
+// tables, packed populations and the evaluation entry points.  Everything above this
+// file (Julia shim, Python mirror) sees only `extern "C"` functions with raw pointers.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstring>
+#include <map>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/dexb200.h"
+#include "dex_kernels.h"
+#include "dex_tape.h"
+
+using namespace dex;
+
+// ---- opaque types ------------------------------------------------------------------
+struct dex_optable {
+    OpTable t;
+};
+
+struct dex_ctx {
+    int device = -1;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    int sm_count = 148;
+    std::string last_error;
+    // scratch owned by the context
+    void* scratch = nullptr;
+    size_t scratch_bytes = 0;
+    void* pinned = nullptr;
+    size_t pinned_bytes = 0;
+    void* dev_io = nullptr;  // device staging for the *_host entry points
+    size_t dev_io_bytes = 0;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    int64_t launches = 0;    // kernels launched through this context
+};
+
+struct dex_population {
+    PackedPopulation h;  // host image
+    int device = -1;
+    Instr* d_tape = nullptr;
+    int64_t* d_tape_off = nullptr;
+    GInstr* d_gtape = nullptr;
+    int64_t* d_gtape_off = nullptr;
+    int64_t* d_const_off = nullptr;
+    int64_t* d_const_pos = nullptr;
+    int64_t* d_gconst_pos = nullptr;
+    std::map<int32_t, int32_t*> chunk_tables;  // n_chunks -> device table
+    std::map<std::string, int64_t*> grad_off_tables;
+};
+
+namespace {
+
+int set_err(dex_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->last_error = msg;
+    return code;
+}
+int cuda_err(dex_ctx* ctx, cudaError_t e, const char* what) {
+    return set_err(ctx, DEX_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CU(ctx, call)                                              \
+    do {                                                           \
+        cudaError_t e__ = (call);                                  \
+        if (e__ != cudaSuccess) return cuda_err(ctx, e__, #call);  \
+    } while (0)
+
+struct OpInfo { int code; int degree; const char* sym; const char* name; const char* aliases; };
+const OpInfo kOps[] = {
+#define DEX_OP(SYM, code, degree, name, aliases) {code, degree, #SYM, name, aliases},
+#include "../../include/dex_ops.def"
+#undef DEX_OP
+};
+
+const OpInfo* find_op(int code) {
+    for (const OpInfo& o : kOps)
+        if (o.code == code) return &o;
+    return nullptr;
+}
+
+bool alias_match(const char* aliases, const char* name) {
+    const size_t n = std::strlen(name);
+    const char* p = aliases;
+    while (*p) {
+        const char* q = std::strchr(p, '|');
+        size_t len = q ? (size_t)(q - p) : std::strlen(p);
+        if (len == n && std::strncmp(p, name, n) == 0) return true;
+        if (!q) break;
+        p = q + 1;
+    }
+    return false;
+}
+
+int ensure_device(dex_ctx* ctx) {
+    if (!ctx) return DEX_ERR_INVALID;
+    if (ctx->device < 0) return set_err(ctx, DEX_ERR_CUDA, "host-only context: no CUDA device bound (libdexb200 has no CPU fallback)");
+    CU(ctx, cudaSetDevice(ctx->device));
+    return DEX_OK;
+}
+
+int ensure_scratch(dex_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->scratch_bytes) return DEX_OK;
+    if (ctx->scratch) { CU(ctx, cudaStreamSynchronize(ctx->stream)); CU(ctx, cudaFree(ctx->scratch)); ctx->scratch = nullptr; ctx->scratch_bytes = 0; }
+    CU(ctx, cudaMalloc(&ctx->scratch, bytes));
+    ctx->scratch_bytes = bytes;
+    return DEX_OK;
+}
+int ensure_dev_io(dex_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->dev_io_bytes) return DEX_OK;
+    if (ctx->dev_io) { CU(ctx, cudaStreamSynchronize(ctx->stream)); CU(ctx, cudaFree(ctx->dev_io)); ctx->dev_io = nullptr; ctx->dev_io_bytes = 0; }
+    CU(ctx, cudaMalloc(&ctx->dev_io, bytes));
+    ctx->dev_io_bytes = bytes;
+    return DEX_OK;
+}
+int ensure_pinned(dex_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->pinned_bytes) return DEX_OK;
+    if (ctx->pinned) { CU(ctx, cudaStreamSynchronize(ctx->stream)); CU(ctx, cudaFreeHost(ctx->pinned)); ctx->pinned = nullptr; ctx->pinned_bytes = 0; }
+    CU(ctx, cudaMallocHost(&ctx->pinned, bytes));
+    ctx->pinned_bytes = bytes;
+    return DEX_OK;
+}
+
+template <typename U>
+int upload(dex_ctx* ctx, U** dptr, const std::vector<U>& v) {
+    *dptr = nullptr;
+    const size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(U);
+    CU(ctx, cudaMalloc(reinterpret_cast<void**>(dptr), bytes));
+    if (!v.empty()) CU(ctx, cudaMemcpyAsync(*dptr, v.data(), v.size() * sizeof(U), cudaMemcpyHostToDevice, ctx->stream));
+    return DEX_OK;
+}
+
+// tree-index ranges with balanced tape length
+int chunk_table(dex_ctx* ctx, dex_population* pop, int32_t n_chunks, const int32_t** out, bool grad = false) {
+    const int32_t key = grad ? -n_chunks : n_chunks;
+    auto it = pop->chunk_tables.find(key);
+    if (it != pop->chunk_tables.end()) { *out = it->second; return DEX_OK; }
+    const PackedPopulation& h = pop->h;
+    std::vector<int32_t> tab((size_t)n_chunks + 1, 0);
+    // cost of trees [0, t) = tape instructions + a fixed per-tree cost of one
+    const std::vector<int64_t>& toff = grad ? h.gtape_off : h.tape_off;
+    auto cum = [&](int64_t t) { return toff[(size_t)t] + t; };
+    const int64_t total = cum(h.n_trees);
+    int64_t t = 0;
+    for (int32_t c = 1; c < n_chunks; ++c) {
+        const int64_t target = (total * c) / n_chunks;
+        while (t < h.n_trees && cum(t) < target) ++t;
+        tab[c] = (int32_t)t;
+    }
+    tab[n_chunks] = (int32_t)h.n_trees;
+    int32_t* d = nullptr;
+    CU(ctx, cudaMalloc(reinterpret_cast<void**>(&d), tab.size() * sizeof(int32_t)));
+    CU(ctx, cudaMemcpyAsync(d, tab.data(), tab.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));  // tab is a stack temporary
+    pop->chunk_tables[key] = d;
+    *out = d;
+    return DEX_OK;
+}
+
+int check_eval_args(dex_ctx* ctx, const dex_population* pop, const void* X, int32_t F, int64_t N,
+                    int64_t ldx, const void* out, int64_t ldo, const uint8_t* ok) {
+    if (!pop) return set_err(ctx, DEX_ERR_INVALID, "null population");
+    if (pop->device != ctx->device) return set_err(ctx, DEX_ERR_INVALID, "population was packed on another device");
+    if (F < 0 || N < 0) return set_err(ctx, DEX_ERR_INVALID, "negative size");
+    if (N > 0 && (!X && F > 0)) return set_err(ctx, DEX_ERR_INVALID, "null X");
+    if (ldx < F) return set_err(ctx, DEX_ERR_INVALID, "ldx < nfeatures");
+    if (out && ldo < N) return set_err(ctx, DEX_ERR_INVALID, "ldo < nsamples");
+    if (!ok) return set_err(ctx, DEX_ERR_INVALID, "null ok");
+    if (pop->h.max_feature >= F)
+        return set_err(ctx, DEX_ERR_RANGE,
+                       "population uses feature " + std::to_string(pop->h.max_feature + 1) +
+                           " (1-based) but X has only " + std::to_string(F) + " rows");
+    return DEX_OK;
+}
+
+int run_eval(dex_ctx* ctx, const dex_population* cpop, const void* X, int32_t F, int64_t N,
+             int64_t ldx, void* out, int64_t ldo, uint8_t* ok, int eval_flags, const void* params,
+             int32_t n_params, int32_t n_classes, const int32_t* classes, const void* y,
+             const void* w, double* loss_partial, int64_t* n_tiles_out) {
+    dex_population* pop = const_cast<dex_population*>(cpop);
+    const PackedPopulation& h = pop->h;
+    if (h.n_trees == 0 || N == 0) return DEX_OK;
+    int threads;
+    size_t smem;
+    const int64_t n_tiles = eval_num_tiles(h.dtype, F, h.max_stack, N, &threads, &smem);
+    if (n_tiles_out) *n_tiles_out = n_tiles;
+    if (smem > 227 * 1024)
+        return set_err(ctx, DEX_ERR_UNSUPPORTED,
+                       "nfeatures + stack rows = " + std::to_string(F + h.max_stack) +
+                           " do not fit in shared memory");
+    // enough CTAs for ~4 waves of 8 resident CTAs per SM, never more chunks than trees
+    const int64_t want = (int64_t)ctx->sm_count * 8 * 4;
+    int64_t n_chunks = std::max<int64_t>(1, (want + n_tiles - 1) / n_tiles);
+    n_chunks = std::min<int64_t>(n_chunks, std::min<int64_t>(h.n_trees, 65535));
+    EvalArgs a{};
+    a.dtype = h.dtype;
+    a.tape = pop->d_tape;
+    a.tape_off = pop->d_tape_off;
+    a.n_trees = h.n_trees;
+    int rc = chunk_table(ctx, pop, (int32_t)n_chunks, &a.chunk_start);
+    if (rc) return rc;
+    a.n_chunks = (int32_t)n_chunks;
+    a.max_stack = h.max_stack;
+    a.X = X; a.F = F; a.N = N; a.ldx = ldx;
+    a.out = out; a.ldo = ldo; a.ok = ok;
+    a.early_exit = (eval_flags & DEX_EVAL_EARLY_EXIT) ? 1 : 0;
+    a.params = params; a.n_params = n_params; a.n_classes = n_classes; a.classes = classes;
+    a.y = y; a.w = w; a.loss_partial = loss_partial;
+    int launches = 0;
+    cudaError_t e = launch_eval(a, ctx->stream, ctx->sm_count, &launches);
+    ctx->launches += launches;
+    if (e != cudaSuccess) return cuda_err(ctx, e, "eval kernel launch");
+    return DEX_OK;
+}
+
+}  // namespace
+
+// ---- library -------------------------------------------------------------------------
+extern "C" {
+
+int dex_abi_version(void) { return DEXB200_ABI_VERSION; }
+
+const char* dex_strerror(int code) {
+    switch (code) {
+        case DEX_OK: return "ok";
+        case DEX_ERR_INVALID: return "invalid argument or malformed tree";
+        case DEX_ERR_NOMEM: return "out of memory";
+        case DEX_ERR_CUDA: return "CUDA failure or no device";
+        case DEX_ERR_UNSUPPORTED: return "unsupported (operator without device implementation, tree too deep, ...)";
+        case DEX_ERR_RANGE: return "feature / parameter / class index out of range";
+        default: return "unknown error";
+    }
+}
+
+int dex_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int dex_opcode_from_name(const char* name, int degree) {
+    if (!name) return -1;
+    for (const OpInfo& o : kOps)
+        if (o.degree == degree && std::strcmp(o.name, name) == 0) return o.code;
+    for (const OpInfo& o : kOps)
+        if (o.degree == degree && alias_match(o.aliases, name)) return o.code;
+    return -1;
+}
+const char* dex_opcode_name(int opcode) {
+    const OpInfo* o = find_op(opcode);
+    return o ? o->name : nullptr;
+}
+int dex_opcode_degree(int opcode) {
+    const OpInfo* o = find_op(opcode);
+    return o ? o->degree : 0;
+}
+
+// ---- context ---------------------------------------------------------------------------
+int dex_ctx_create(int device, dex_ctx** out) {
+    if (!out) return DEX_ERR_INVALID;
+    *out = nullptr;
+    dex_ctx* ctx = new (std::nothrow) dex_ctx();
+    if (!ctx) return DEX_ERR_NOMEM;
+    ctx->device = device;
+    if (device >= 0) {
+        int n = dex_device_count();
+        if (device >= n) { delete ctx; return DEX_ERR_CUDA; }
+        if (cudaSetDevice(device) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ctx->ev[0], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ctx->ev[1], cudaEventDisableTiming) != cudaSuccess) {
+            cudaGetLastError();
+            delete ctx;
+            return DEX_ERR_CUDA;
+        }
+        ctx->stream = ctx->own_stream;
+        cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    }
+    *out = ctx;
+    return DEX_OK;
+}
+
+int dex_ctx_destroy(dex_ctx* ctx) {
+    if (!ctx) return DEX_OK;
+    if (ctx->device >= 0) {
+        cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+        if (ctx->scratch) cudaFree(ctx->scratch);
+        if (ctx->dev_io) cudaFree(ctx->dev_io);
+        if (ctx->pinned) cudaFreeHost(ctx->pinned);
+        for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
+        if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+        if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    }
+    delete ctx;
+    return DEX_OK;
+}
+
+int dex_ctx_set_stream(dex_ctx* ctx, void* stream) {
+    if (!ctx) return DEX_ERR_INVALID;
+    ctx->stream = stream ? static_cast<cudaStream_t>(stream) : ctx->own_stream;
+    return DEX_OK;
+}
+
+int dex_ctx_synchronize(dex_ctx* ctx) {
+    int rc = ensure_device(ctx);
+    if (rc) return rc;
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return DEX_OK;
+}
+
+const char* dex_last_error(const dex_ctx* ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
+
+int64_t dex_ctx_launch_count(const dex_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ---- operators -------------------------------------------------------------------------
+int dex_optable_create(const int32_t* opcodes, const int32_t* degree_offsets, int max_degree,
+                       dex_optable** out) {
+    if (!out || !degree_offsets || max_degree < 0 || max_degree > DEX_MAX_DEGREE) return DEX_ERR_INVALID;
+    dex_optable* t = new (std::nothrow) dex_optable();
+    if (!t) return DEX_ERR_NOMEM;
+    for (int d = 0; d < max_degree; ++d) {
+        for (int32_t i = degree_offsets[d]; i < degree_offsets[d + 1]; ++i) {
+            const OpInfo* o = opcodes ? find_op(opcodes[i]) : nullptr;
+            if (!o || o->degree != d + 1) { delete t; return DEX_ERR_UNSUPPORTED; }
+            t->t.ops[d].push_back(opcodes[i]);
+        }
+        if (t->t.ops[d].size() > 256) { delete t; return DEX_ERR_INVALID; }
+    }
+    *out = t;
+    return DEX_OK;
+}
+int dex_optable_destroy(dex_optable* t) {
+    delete t;
+    return DEX_OK;
+}
+
+// ---- populations -----------------------------------------------------------------------
+int dex_population_pack(dex_ctx* ctx, const dex_optable* ops, const dex_node* nodes,
+                        const int64_t* offsets, int64_t n_trees, int dtype, int pack_flags,
+                        dex_population** out) {
+    if (!ctx || !out) return DEX_ERR_INVALID;
+    *out = nullptr;
+    if (!ops || !offsets || n_trees < 0 || (n_trees > 0 && !nodes)) return set_err(ctx, DEX_ERR_INVALID, "null argument");
+    if (dtype != DEX_F32 && dtype != DEX_F64) return set_err(ctx, DEX_ERR_INVALID, "dtype must be DEX_F32 or DEX_F64");
+    dex_population* pop = new (std::nothrow) dex_population();
+    if (!pop) return set_err(ctx, DEX_ERR_NOMEM, "out of host memory");
+    std::string err;
+    int rc = flatten_population(ops->t, nodes, offsets, n_trees, dtype, pack_flags, pop->h, err);
+    if (rc) { delete pop; return set_err(ctx, rc, err); }
+    pop->device = ctx->device;
+    if (ctx->device >= 0) {
+        rc = ensure_device(ctx);
+        if (!rc) rc = upload(ctx, &pop->d_tape, pop->h.tape);
+        if (!rc) rc = upload(ctx, &pop->d_tape_off, pop->h.tape_off);
+        if (!rc) rc = upload(ctx, &pop->d_gtape, pop->h.gtape);
+        if (!rc) rc = upload(ctx, &pop->d_gtape_off, pop->h.gtape_off);
+        if (!rc) rc = upload(ctx, &pop->d_const_off, pop->h.const_off);
+        if (!rc) rc = upload(ctx, &pop->d_const_pos, pop->h.const_pos);
+        if (!rc) rc = upload(ctx, &pop->d_gconst_pos, pop->h.gconst_pos);
+        if (!rc && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = set_err(ctx, DEX_ERR_CUDA, "tape upload failed");
+        if (rc) { dex_population_destroy(pop); return rc; }
+    }
+    *out = pop;
+    return DEX_OK;
+}
+
+int dex_population_destroy(dex_population* pop) {
+    if (!pop) return DEX_OK;
+    if (pop->device >= 0) {
+        cudaSetDevice(pop->device);
+        cudaFree(pop->d_tape); cudaFree(pop->d_tape_off); cudaFree(pop->d_gtape);
+        cudaFree(pop->d_gtape_off); cudaFree(pop->d_const_off); cudaFree(pop->d_const_pos);
+        cudaFree(pop->d_gconst_pos);
+        for (auto& kv : pop->chunk_tables) cudaFree(kv.second);
+        for (auto& kv : pop->grad_off_tables) cudaFree(kv.second);
+    }
+    delete pop;
+    return DEX_OK;
+}
+
+int dex_population_get_info(const dex_population* pop, dex_population_info* info) {
+    if (!pop || !info) return DEX_ERR_INVALID;
+    info->n_trees = pop->h.n_trees;
+    info->n_nodes = pop->h.n_nodes;
+    info->n_instructions = (int64_t)pop->h.tape.size();
+    info->n_constants = pop->h.n_constants;
+    info->max_stack = pop->h.max_stack;
+    info->max_feature = pop->h.max_feature;
+    info->max_parameter = pop->h.max_parameter;
+    info->dtype = pop->h.dtype;
+    return DEX_OK;
+}
+
+int dex_population_constant_counts(const dex_population* pop, int32_t* counts) {
+    if (!pop || !counts) return DEX_ERR_INVALID;
+    std::copy(pop->h.n_const_tree.begin(), pop->h.n_const_tree.end(), counts);
+    return DEX_OK;
+}
+
+// debugging / tests: copy out the host image of the evaluation tape
+int64_t dex_population_copy_tape(const dex_population* pop, void* instrs, int64_t capacity,
+                                 int64_t* offsets /* n_trees+1 */) {
+    if (!pop) return DEX_ERR_INVALID;
+    const int64_t n = (int64_t)pop->h.tape.size();
+    if (instrs && capacity >= n) std::memcpy(instrs, pop->h.tape.data(), (size_t)n * sizeof(Instr));
+    if (offsets) std::copy(pop->h.tape_off.begin(), pop->h.tape_off.end(), offsets);
+    return n;
+}
+
+int dex_population_get_constants(dex_ctx* ctx, const dex_population* pop, void* values_host,
+                                 int64_t n_values) {
+    if (!ctx || !pop || (!values_host && n_values > 0)) return DEX_ERR_INVALID;
+    if (n_values != pop->h.n_constants) return set_err(ctx, DEX_ERR_INVALID, "constant count mismatch");
+    for (int64_t k = 0; k < n_values; ++k) {
+        const Instr& ins = pop->h.tape[(size_t)pop->h.const_pos[(size_t)k]];
+        if (pop->h.dtype == DEX_F32) std::memcpy(static_cast<float*>(values_host) + k, &ins.c_lo, 4);
+        else { uint64_t u = ((uint64_t)ins.c_hi << 32) | ins.c_lo; std::memcpy(static_cast<double*>(values_host) + k, &u, 8); }
+    }
+    return DEX_OK;
+}
+
+int dex_population_set_constants(dex_ctx* ctx, dex_population* pop, const void* values_host,
+                                 int64_t n_values) {
+    if (!ctx || !pop || (!values_host && n_values > 0)) return DEX_ERR_INVALID;
+    if (n_values != pop->h.n_constants) return set_err(ctx, DEX_ERR_INVALID, "constant count mismatch");
+    const size_t es = pop->h.dtype == DEX_F32 ? 4 : 8;
+    // host image
+    for (int64_t k = 0; k < n_values; ++k) {
+        Instr& ins = pop->h.tape[(size_t)pop->h.const_pos[(size_t)k]];
+        GInstr& g = pop->h.gtape[(size_t)pop->h.gconst_pos[(size_t)k]];
+        if (es == 4) { std::memcpy(&ins.c_lo, static_cast<const float*>(values_host) + k, 4); ins.c_hi = 0; }
+        else { uint64_t u; std::memcpy(&u, static_cast<const double*>(values_host) + k, 8); ins.c_lo = (uint32_t)u; ins.c_hi = (uint32_t)(u >> 32); }
+        g.c_lo = ins.c_lo; g.c_hi = ins.c_hi;
+    }
+    if (pop->device < 0 || n_values == 0) return DEX_OK;
+    int rc = ensure_device(ctx);
+    if (rc) return rc;
+    if ((rc = ensure_pinned(ctx, (size_t)n_values * es))) return rc;
+    if ((rc = ensure_dev_io(ctx, (size_t)n_values * es))) return rc;
+    std::memcpy(ctx->pinned, values_host, (size_t)n_values * es);
+    CU(ctx, cudaMemcpyAsync(ctx->dev_io, ctx->pinned, (size_t)n_values * es, cudaMemcpyHostToDevice, ctx->stream));
+    cudaError_t e = launch_scatter_constants(pop->h.dtype, pop->d_tape, pop->d_const_pos, pop->d_gtape,
+                                             pop->d_gconst_pos, ctx->dev_io, n_values, ctx->stream);
+    if (e != cudaSuccess) return cuda_err(ctx, e, "scatter constants");
+    ctx->launches += 1;
+    CU(ctx, cudaStreamSynchronize(ctx->stream));  // pinned staging is reused by later calls
+    return DEX_OK;
+}
+
+// ---- evaluation ------------------------------------------------------------------------
+int dex_eval(dex_ctx* ctx, const dex_population* pop, const void* X_dev, int32_t nfeatures,
+             int64_t nsamples, int64_t ldx, void* out_dev, int64_t ldo, uint8_t* ok_dev,
+             int eval_flags) {
+    int rc = ensure_device(ctx);
+    if (rc) return rc;
+    if ((rc = check_eval_args(ctx, pop, X_dev, nfeatures, nsamples, ldx, out_dev, ldo, ok_dev))) return rc;
+    if (!out_dev) return set_err(ctx, DEX_ERR_INVALID, "null out");
+    if (pop->h.max_parameter >= 0) return set_err(ctx, DEX_ERR_INVALID, "population has parameter leaves: use dex_eval_parametric");
+    return run_eval(ctx, pop, X_dev, nfeatures, nsamples, ldx, out_dev, ldo, ok_dev, eval_flags,
+                    nullptr, 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr);
+}
+
+int dex_eval_parametric(dex_ctx* ctx, const dex_population* pop, const void* X_dev,
+                        int32_t nfeatures, int64_t nsamples, int64_t ldx, const void* params_dev,
+                        int32_t n_params, int32_t n_classes, const int32_t* classes_dev,
+                        void* out_dev, int64_t ldo, uint8_t* ok_dev, int eval_flags) {
+    int rc = ensure_device(ctx);
+    if (rc) return rc;
+    if ((rc = check_eval_args(ctx, pop, X_dev, nfeatures, nsamples, ldx, out_dev, ldo, ok_dev))) return rc;
+    if (!out_dev) return set_err(ctx, DEX_ERR_INVALID, "null out");
+    if (n_params < 0 || n_classes < 1 || !classes_dev || (n_params > 0 && !params_dev))
+        return set_err(ctx, DEX_ERR_INVALID, "bad parameter arguments");
+    if (pop->h.max_parameter >= n_params)
+        return set_err(ctx, DEX_ERR_RANGE, "population uses parameter " + std::to_string(pop->h.max_parameter + 1) +
+                                               " (1-based) but only " + std::to_string(n_params) + " were passed");
+    // a dummy non-null params pointer keeps the parametric kernel selected when n_params == 0
+    return run_eval(ctx, pop, X_dev, nfeatures, nsamples, ldx, out_dev, ldo, ok_dev, eval_flags,
+                    params_dev ? params_dev : X_dev, n_params, n_classes, classes_dev, nullptr,
+                    nullptr, nullptr, nullptr);
+}
+
+int dex_eval_loss(dex_ctx* ctx, const dex_population* pop, const void* X_dev, int32_t nfeatures,
+                  int64_t nsamples, int64_t ldx, const void* y_dev, const void* weights_dev,
+                  double* loss_dev, uint8_t* ok_dev, int eval_flags) {
+    int rc = ensure_device(ctx);
+    if (rc) return rc;
+    if ((rc = check_eval_args(ctx, pop, X_dev, nfeatures, nsamples, ldx, nullptr, 0, ok_dev))) return rc;
+    if (!y_dev || !loss_dev) return set_err(ctx, DEX_ERR_INVALID, "null y / loss");
+    if (weights_dev) return set_err(ctx, DEX_ERR_UNSUPPORTED, "weighted loss: normalise weights on the caller side (not implemented)");
+    if (pop->h.max_parameter >= 0) return set_err(ctx, DEX_ERR_INVALID, "population has parameter leaves");
+    if (pop->h.n_trees == 0) return DEX_OK;
+    int threads; size_t smem;
+    const int64_t n_tiles = eval_num_tiles(pop->h.dtype, nfeatures, pop->h.max_stack, std::max<int64_t>(nsamples, 1), &threads, &smem);
+    if ((rc = ensure_scratch(ctx, (size_t)n_tiles * (size_t)pop->h.n_trees * sizeof(double)))) return rc;
+    double* partial = static_cast<double*>(ctx->scratch);
+    if ((rc = run_eval(ctx, pop, X_dev, nfeatures, nsamples, ldx, nullptr, 0, ok_dev, eval_flags, nullptr, 0,
+                       0, nullptr, y_dev, nullptr, partial, nullptr)))
+        return rc;
+    cudaError_t e = launch_loss_reduce(partial, nsamples > 0 ? n_tiles : 0, pop->h.n_trees,
+                                       nsamples > 0 ? 1.0 / (double)nsamples : 0.0, loss_dev, ctx->stream);
+    if (e != cudaSuccess) return cuda_err(ctx, e, "loss reduce");
+    ctx->launches += 1;
+    return DEX_OK;
+}
+
+int dex_grad_offsets(const dex_population* pop, int32_t nfeatures, int64_t nsamples, int mode,
+                     int64_t* offsets_host) {
+    if (!pop || !offsets_host || mode < 0 || mode > 2 || nfeatures < 0 || nsamples < 0) return DEX_ERR_INVALID;
+    int64_t acc = 0;
+    for (int64_t t = 0; t < pop->h.n_trees; ++t) {
+        offsets_host[t] = acc;
+        const int64_t nc = pop->h.n_const_tree[(size_t)t];
+        const int64_t G = mode == DEX_GRAD_FEATURES ? nfeatures : mode == DEX_GRAD_CONSTANTS ? nc : nfeatures + nc;
+        acc += G * nsamples;
+    }
+    offsets_host[pop->h.n_trees] = acc;
+    return DEX_OK;
+}
+
+static int run_grad(dex_ctx* ctx, const dex_population* cpop, const void* X, int32_t F, int64_t N,
+                    int64_t ldx, int mode, int32_t direction, void* out, int64_t ldo, void* grad,
+                    const int64_t* grad_offsets_host, uint8_t* ok) {
+    dex_population* pop = const_cast<dex_population*>(cpop);
+    const PackedPopulation& h = pop->h;
+    if (h.max_parameter >= 0) return set_err(ctx, DEX_ERR_UNSUPPORTED, "derivatives of parametric populations are not implemented");
+    if (h.n_trees == 0 || N == 0) return DEX_OK;
+    int Gmax = 1;
+    if (mode >= 0) {
+        int32_t ncmax = 0;
+        for (int32_t c : h.n_const_tree) ncmax = std::max(ncmax, c);
+        Gmax = mode == DEX_GRAD_FEATURES ? F : mode == DEX_GRAD_CONSTANTS ? ncmax : F + ncmax;
+    }
+    const int64_t n_tiles = grad_num_tiles(h.dtype, F, h.max_gstack, Gmax, N);
+    const int64_t want = (int64_t)ctx->sm_count * 8 * 4;
+    int64_t n_chunks = std::max<int64_t>(1, (want + n_tiles - 1) / n_tiles);
+    n_chunks = std::min<int64_t>(n_chunks, std::min<int64_t>(h.n_trees, 65535));
+    const int32_t* chunks = nullptr;
+    int rc = chunk_table(ctx, pop, (int32_t)n_chunks, &chunks, true);
+    if (rc) return rc;
+    GradArgs a{};
+    a.dtype = h.dtype;
+    a.gtape = pop->d_gtape; a.gtape_off = pop->d_gtape_off; a.const_off = pop->d_const_off;
+    a.n_trees = h.n_trees; a.max_gstack = h.max_gstack;
+    a.X = X; a.F = F; a.N = N; a.ldx = ldx; a.mode = mode; a.direction = direction;
+    a.out = out; a.ldo = ldo; a.grad = grad; a.ok = ok; a.grad_off = nullptr;
+    if (mode >= 0) {
+        const size_t bytes = (size_t)(h.n_trees + 1) * sizeof(int64_t);
+        if ((rc = ensure_scratch(ctx, bytes))) return rc;
+        // pageable -> device: the runtime stages the source before returning, so the
+        // caller's array may be reused immediately
+        CU(ctx, cudaMemcpyAsync(ctx->scratch, grad_offsets_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        a.grad_off = static_cast<const int64_t*>(ctx->scratch);
+    }
+    int launches = 0;
+    cudaError_t e = launch_grad_ex(a, chunks, (int)n_chunks, Gmax, ctx->stream, &launches);
+    ctx->launches += launches;
+    if (e != cudaSuccess) return cuda_err(ctx, e, "grad kernel launch");
+    return DEX_OK;
+}
+
+int dex_eval_grad(dex_ctx* ctx, const dex_population* pop, const void* X_dev, int32_t nfeatures,
+                  int64_t nsamples, int64_t ldx, int mode, void* out_dev, int64_t ldo,
+                  void* grad_dev, const int64_t* grad_offsets_host, uint8_t* ok_dev) {
+    int rc = ensure_device(ctx);
+    if (rc) return rc;
+    if ((rc = check_eval_args(ctx, pop, X_dev, nfeatures, nsamples, ldx, out_dev, ldo, ok_dev))) return rc;
+    if (mode < 0 || mode > 2) return set_err(ctx, DEX_ERR_INVALID, "mode must be DEX_GRAD_CONSTANTS/FEATURES/BOTH");
+    if (!out_dev || !grad_offsets_host) return set_err(ctx, DEX_ERR_INVALID, "null out / grad_offsets");
+    if (!grad_dev && grad_offsets_host[pop->h.n_trees] > 0) return set_err(ctx, DEX_ERR_INVALID, "null grad");
+    return run_grad(ctx, pop, X_dev, nfeatures, nsamples, ldx, mode, 0, out_dev, ldo, grad_dev, grad_offsets_host, ok_dev);
+}
+
+int dex_eval_diff(dex_ctx* ctx, const dex_population* pop, const void* X_dev, int32_t nfeatures,
+                  int64_t nsamples, int64_t ldx, int32_t direction, void* out_dev, void* dout_dev,
+                  int64_t ldo, uint8_t* ok_dev) {
+    int rc = ensure_device(ctx);
+    if (rc) return rc;
+    if ((rc = check_eval_args(ctx, pop, X_dev, nfeatures, nsamples, ldx, out_dev, ldo, ok_dev))) return rc;
+    if (!out_dev || !dout_dev) return set_err(ctx, DEX_ERR_INVALID, "null out / dout");
+    if (direction < 0) return set_err(ctx, DEX_ERR_RANGE, "direction must be a feature index");
+    return run_grad(ctx, pop, X_dev, nfeatures, nsamples, ldx, -1, direction, out_dev, ldo, dout_dev, nullptr, ok_dev);
+}
+
+int dex_eval_host(dex_ctx* ctx, const dex_population* pop, const void* X_host, int32_t nfeatures,
+                  int64_t nsamples, int64_t ldx, void* out_host, int64_t ldo, uint8_t* ok_host,
+                  int eval_flags) {
+    int rc = ensure_device(ctx);
+    if (rc) return rc;
+    if (!pop || !out_host || !ok_host || (!X_host && nfeatures > 0 && nsamples > 0)) return set_err(ctx, DEX_ERR_INVALID, "null argument");
+    const size_t es = pop->h.dtype == DEX_F32 ? 4 : 8;
+    const int64_t P = pop->h.n_trees, N = nsamples;
+    if (P == 0 || N == 0) return DEX_OK;
+    // device staging: X | out | ok
+    const size_t xb = (size_t)ldx * (size_t)N * es;
+    const size_t xoff = 0, ooff = (xb + 255) & ~(size_t)255;
+    const size_t ob = (size_t)P * (size_t)N * es;
+    const size_t koff = (ooff + ob + 255) & ~(size_t)255;
+    if ((rc = ensure_dev_io(ctx, koff + (size_t)P))) return rc;
+    char* base = static_cast<char*>(ctx->dev_io);
+    void* dX = base + xoff;
+    void* dO = base + ooff;
+    uint8_t* dK = reinterpret_cast<uint8_t*>(base + koff);
+    CU(ctx, cudaMemcpyAsync(dX, X_host, xb, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = check_eval_args(ctx, pop, dX, nfeatures, N, ldx, dO, N, dK))) return rc;
+    if (pop->h.max_parameter >= 0) return set_err(ctx, DEX_ERR_INVALID, "population has parameter leaves");
+    if ((rc = run_eval(ctx, pop, dX, nfeatures, N, ldx, dO, N, dK, eval_flags, nullptr, 0, 0, nullptr,
+                       nullptr, nullptr, nullptr, nullptr)))
+        return rc;
+    CU(ctx, cudaMemcpy2DAsync(out_host, (size_t)ldo * es, dO, (size_t)N * es, (size_t)N * es, (size_t)P,
+                              cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(ok_host, dK, (size_t)P, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return DEX_OK;
+}
+
+// pinned host buffers for callers of the *_host entry points
+int dex_host_alloc(void** out, int64_t bytes) {
+    if (!out || bytes < 0) return DEX_ERR_INVALID;
+    if (cudaMallocHost(out, (size_t)std::max<int64_t>(bytes, 1)) != cudaSuccess) { cudaGetLastError(); return DEX_ERR_NOMEM; }
+    return DEX_OK;
+}
+int dex_host_free(void* p) {
+    if (p && cudaFreeHost(p) != cudaSuccess) { cudaGetLastError(); return DEX_ERR_CUDA; }
+    return DEX_OK;
+}
+
+}  // extern "C"

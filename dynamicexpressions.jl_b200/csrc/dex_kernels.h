@@ -1,0 +1,77 @@
+// dex_kernels.h — launch interface between the C ABI (dex_api.cu) and the CUDA
+// kernels (dex_eval.cu, dex_grad.cu).  Internal.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+#include "dex_tape.h"
+
+namespace dex {
+
+struct EvalArgs {
+    int dtype;                  // DEX_F32 / DEX_F64
+    const Instr* tape;          // device
+    const int64_t* tape_off;    // device, n_trees + 1
+    int64_t n_trees;
+    const int32_t* chunk_start; // device, n_chunks + 1 (tree index ranges, balanced by tape length)
+    int32_t n_chunks;
+    int32_t max_stack;          // stack rows in front of the feature rows
+    const void* X;              // device, column-major F x N, leading dimension ldx
+    int32_t F;
+    int64_t N;
+    int64_t ldx;
+    void* out;                  // device, n_trees x N row-major (row stride ldo); may be null in loss mode
+    int64_t ldo;
+    uint8_t* ok;                // device, n_trees (pre-set to 1 by the launcher)
+    int32_t early_exit;
+    // ParametricExpression (null params => plain evaluation)
+    const void* params;         // device, per tree (n_params x n_classes) column-major
+    int32_t n_params;
+    int32_t n_classes;
+    const int32_t* classes;     // device, N
+    // fused loss (null => store results)
+    const void* y;              // device, N
+    const void* w;              // device, N or null
+    double* loss_partial;       // device, n_tiles x n_trees partial sums (deterministic 2-stage)
+    // launch shape chosen by the launcher
+    int32_t threads;
+};
+
+// Chooses the block size / shared memory, presets ok[], launches.  Returns cudaError_t.
+cudaError_t launch_eval(const EvalArgs& a, cudaStream_t stream, int sm_count, int* launches);
+// number of sample tiles launch_eval will use for (dtype, F, max_stack, N)
+int64_t eval_num_tiles(int dtype, int32_t F, int32_t max_stack, int64_t N, int* threads_out,
+                       size_t* smem_out);
+
+struct GradArgs {
+    int dtype;
+    const GInstr* gtape;        // device
+    const int64_t* gtape_off;   // device, n_trees + 1
+    const int64_t* const_off;   // device, n_trees + 1 (constant ordinal base per tree)
+    int64_t n_trees;
+    int32_t max_gstack;
+    const void* X;
+    int32_t F;
+    int64_t N;
+    int64_t ldx;
+    int32_t mode;               // DEX_GRAD_*; -1 = eval_diff along `direction`
+    int32_t direction;
+    void* out;                  // n_trees x N
+    int64_t ldo;
+    void* grad;                 // per tree (G_t x N) column-major at grad_off[t]; diff: n_trees x N rows
+    const int64_t* grad_off;    // device, n_trees + 1 (unused for diff)
+    uint8_t* ok;
+};
+// chunk_start: device table of n_chunks + 1 tree indices; Gmax: largest gradient count of any tree
+cudaError_t launch_grad_ex(const GradArgs& a, const int32_t* chunk_start, int n_chunks, int Gmax,
+                           cudaStream_t stream, int* launches);
+int64_t grad_num_tiles(int dtype, int F, int max_gstack, int Gmax, int64_t N);
+
+// tiny helpers
+cudaError_t launch_scatter_constants(int dtype, Instr* tape, const int64_t* pos, GInstr* gtape,
+                                     const int64_t* gpos, const void* values, int64_t n,
+                                     cudaStream_t stream);
+cudaError_t launch_loss_reduce(const double* partial, int64_t n_tiles, int64_t n_trees,
+                               double denom_inv, double* loss, cudaStream_t stream);
+
+}  // namespace dex

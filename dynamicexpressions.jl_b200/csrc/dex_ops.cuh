@@ -1,0 +1,163 @@
+// dex_ops.cuh — device implementations of the builtin operators (include/dex_ops.def)
+// and of their partial derivatives.
+//
+// Values follow Julia Base scalar semantics for Float32/Float64 — what the reference
+// calls as `op(...)` inside its loop kernels (/root/reference/src/Evaluate.jl:366-392)
+// — with the documented deviation that domain errors produce NaN instead of throwing.
+// Partials are the analytic form of the ChainRules scalar rules behind
+// `_zygote_gradient` (/root/reference/ext/DynamicExpressionsZygoteExt.jl:7-15).
+//
+// Each operator is one row of an X-macro so that the interpreter kernels can expand
+// "case OPCODE: for k in 0..K-1: r[k] = EXPR" — the op switch is executed once per
+// tape instruction, not once per sample.
+//   DEX_UNARY_OPS(X)    X(SYM, value(x),      d/dx(x, v))
+//   DEX_BINARY_OPS(X)   X(SYM, value(x,y),    d/dx(x,y,v), d/dy(x,y,v))
+//   DEX_TERNARY_OPS(X)  X(SYM, value(x,y,z),  d/dx, d/dy, d/dz)
+// with `v` = the value, all of element type T.
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include "../../include/dex_wire.h"
+
+namespace dex {
+
+#define DEX_M1(name)                                                            \
+    __device__ __forceinline__ float m_##name(float x) { return name##f(x); }   \
+    __device__ __forceinline__ double m_##name(double x) { return name(x); }
+#define DEX_M2(name)                                                                     \
+    __device__ __forceinline__ float m_##name(float x, float y) { return name##f(x, y); } \
+    __device__ __forceinline__ double m_##name(double x, double y) { return name(x, y); }
+DEX_M1(fabs) DEX_M1(sqrt) DEX_M1(cbrt) DEX_M1(exp) DEX_M1(exp2) DEX_M1(exp10) DEX_M1(expm1)
+DEX_M1(log) DEX_M1(log2) DEX_M1(log10) DEX_M1(log1p) DEX_M1(sin) DEX_M1(cos) DEX_M1(tan)
+DEX_M1(asin) DEX_M1(acos) DEX_M1(atan) DEX_M1(sinh) DEX_M1(cosh) DEX_M1(tanh) DEX_M1(asinh)
+DEX_M1(acosh) DEX_M1(atanh) DEX_M1(rint) DEX_M1(floor) DEX_M1(ceil) DEX_M1(trunc) DEX_M1(erf)
+DEX_M1(erfc)
+DEX_M2(pow) DEX_M2(fmod) DEX_M2(atan2) DEX_M2(copysign)
+__device__ __forceinline__ float m_fma(float a, float b, float c) { return fmaf(a, b, c); }
+__device__ __forceinline__ double m_fma(double a, double b, double c) { return fma(a, b, c); }
+#undef DEX_M1
+#undef DEX_M2
+
+template <typename T> __device__ __forceinline__ T t_nan();
+template <> __device__ __forceinline__ float t_nan<float>() { return CUDART_NAN_F; }
+template <> __device__ __forceinline__ double t_nan<double>() { return CUDART_NAN; }
+template <typename T> __device__ __forceinline__ T t_inf();
+template <> __device__ __forceinline__ float t_inf<float>() { return CUDART_INF_F; }
+template <> __device__ __forceinline__ double t_inf<double>() { return CUDART_INF; }
+
+__device__ __forceinline__ bool t_signbit(float x) { return (__float_as_uint(x) >> 31) != 0u; }
+__device__ __forceinline__ bool t_signbit(double x) { return __double2hiint(x) < 0; }
+__device__ __forceinline__ bool t_finite(float x) { return (__float_as_uint(x) & 0x7f800000u) != 0x7f800000u; }
+__device__ __forceinline__ bool t_finite(double x) { return ((unsigned)__double2hiint(x) & 0x7ff00000u) != 0x7ff00000u; }
+
+// Julia max/min: NaN if either is NaN; max(-0.0, 0.0) == 0.0
+template <typename T> __device__ __forceinline__ T j_max(T x, T y) {
+    if (x != x || y != y) return t_nan<T>();
+    if (x > y) return x;
+    if (y > x) return y;
+    return t_signbit(x) ? y : x;
+}
+template <typename T> __device__ __forceinline__ T j_min(T x, T y) {
+    if (x != x || y != y) return t_nan<T>();
+    if (x < y) return x;
+    if (y < x) return y;
+    return t_signbit(x) ? x : y;
+}
+// Julia mod: floored, result takes the sign of y
+template <typename T> __device__ __forceinline__ T j_mod(T x, T y) {
+    T r = m_fmod(x, y);
+    if (r != r) return r;
+    if (r == T(0)) return m_copysign(r, y);
+    if ((r > T(0)) != (y > T(0))) return r + y;
+    return r;
+}
+template <typename T> __device__ __forceinline__ T j_sign(T x) {
+    return x > T(0) ? T(1) : (x < T(0) ? T(-1) : x);
+}
+template <typename T> __device__ __forceinline__ T b2t(bool b) { return b ? T(1) : T(0); }
+
+#define DEX_LN2 T(0.693147180559945309417232121458176568)
+#define DEX_LN10 T(2.30258509299404568401799145468436421)
+#define DEX_2_SQRTPI T(1.12837916709551257389615890312154517)
+
+// clang-format off
+#define DEX_UNARY_OPS(X) \
+    X(NEG,        -x,                                   T(-1)) \
+    X(ABS,        m_fabs(x),                            j_sign(x)) \
+    X(ABS2,       x * x,                                T(2) * x) \
+    X(SQUARE,     x * x,                                T(2) * x) \
+    X(CUBE,       x * x * x,                            T(3) * x * x) \
+    X(INV,        T(1) / x,                             T(-1) / (x * x)) \
+    X(SQRT,       m_sqrt(x),                            T(1) / (T(2) * v)) \
+    X(CBRT,       m_cbrt(x),                            T(1) / (T(3) * v * v)) \
+    X(EXP,        m_exp(x),                             v) \
+    X(EXP2,       m_exp2(x),                            v * DEX_LN2) \
+    X(EXP10,      m_exp10(x),                           v * DEX_LN10) \
+    X(EXPM1,      m_expm1(x),                           m_exp(x)) \
+    X(LOG,        m_log(x),                             T(1) / x) \
+    X(LOG2,       m_log2(x),                            T(1) / (x * DEX_LN2)) \
+    X(LOG10,      m_log10(x),                           T(1) / (x * DEX_LN10)) \
+    X(LOG1P,      m_log1p(x),                           T(1) / (T(1) + x)) \
+    X(SIN,        m_sin(x),                             m_cos(x)) \
+    X(COS,        m_cos(x),                             -m_sin(x)) \
+    X(TAN,        m_tan(x),                             T(1) + v * v) \
+    X(ASIN,       m_asin(x),                            T(1) / m_sqrt(T(1) - x * x)) \
+    X(ACOS,       m_acos(x),                            T(-1) / m_sqrt(T(1) - x * x)) \
+    X(ATAN,       m_atan(x),                            T(1) / (T(1) + x * x)) \
+    X(SINH,       m_sinh(x),                            m_cosh(x)) \
+    X(COSH,       m_cosh(x),                            m_sinh(x)) \
+    X(TANH,       m_tanh(x),                            T(1) - v * v) \
+    X(ASINH,      m_asinh(x),                           T(1) / m_sqrt(x * x + T(1))) \
+    X(ACOSH,      m_acosh(x),                           T(1) / m_sqrt(x * x - T(1))) \
+    X(ATANH,      m_atanh(x),                           T(1) / (T(1) - x * x)) \
+    X(ROUND,      m_rint(x),                            T(0)) \
+    X(FLOOR,      m_floor(x),                           T(0)) \
+    X(CEIL,       m_ceil(x),                            T(0)) \
+    X(TRUNC,      m_trunc(x),                           T(0)) \
+    X(SIGN,       j_sign(x),                            T(0)) \
+    X(RELU,       (x < T(0) ? T(0) : x),                (x < T(0) ? T(0) : T(1))) \
+    X(IDENTITY,   x,                                    T(1)) \
+    X(SAFE_LOG,   (x <= T(0) ? t_nan<T>() : m_log(x)),      (x <= T(0) ? T(0) : T(1) / x)) \
+    X(SAFE_LOG2,  (x <= T(0) ? t_nan<T>() : m_log2(x)),     (x <= T(0) ? T(0) : T(1) / (x * DEX_LN2))) \
+    X(SAFE_LOG10, (x <= T(0) ? t_nan<T>() : m_log10(x)),    (x <= T(0) ? T(0) : T(1) / (x * DEX_LN10))) \
+    X(SAFE_LOG1P, (x <= T(-1) ? t_nan<T>() : m_log1p(x)),   (x <= T(-1) ? T(0) : T(1) / (T(1) + x))) \
+    X(SAFE_SQRT,  (x < T(0) ? t_nan<T>() : m_sqrt(x)),      (x < T(0) ? T(0) : T(1) / (T(2) * v))) \
+    X(SAFE_ACOSH, (x < T(1) ? t_nan<T>() : m_acosh(x)),     (x < T(1) ? T(0) : T(1) / m_sqrt(x * x - T(1)))) \
+    X(COS2,       sq(m_cos(x)),                         T(-2) * m_cos(x) * m_sin(x)) \
+    X(ERF,        m_erf(x),                             DEX_2_SQRTPI * m_exp(-x * x)) \
+    X(ERFC,       m_erfc(x),                            -DEX_2_SQRTPI * m_exp(-x * x))
+
+#define DEX_BINARY_OPS(X) \
+    X(ADD,        x + y,                                T(1),                       T(1)) \
+    X(SUB,        x - y,                                T(1),                       T(-1)) \
+    X(MUL,        x * y,                                y,                          x) \
+    X(DIV,        x / y,                                T(1) / y,                   -(v / y)) \
+    X(POW,        m_pow(x, y),                          y * m_pow(x, y - T(1)),     ((x == T(0) && y > T(0)) ? T(0) : v * m_log(m_fabs(x)))) \
+    X(MAX,        j_max(x, y),                          b2t<T>(x > y),              b2t<T>(!(x > y))) \
+    X(MIN,        j_min(x, y),                          b2t<T>(!(x > y)),           b2t<T>(x > y)) \
+    X(MOD,        j_mod(x, y),                          (m_floor(x / y) == x / y ? t_nan<T>() : T(1)), (m_floor(x / y) == x / y ? t_nan<T>() : -m_floor(x / y))) \
+    X(ATAN2,      m_atan2(x, y),                        y / (x * x + y * y),        -x / (x * x + y * y)) \
+    X(COPYSIGN,   m_copysign(x, y),                     (t_signbit(x) == t_signbit(y) ? T(1) : T(-1)), T(0)) \
+    X(GREATER,    b2t<T>(x > y),                        T(0),                       T(0)) \
+    X(LESS,       b2t<T>(x < y),                        T(0),                       T(0)) \
+    X(POW_ABS,    m_exp(y * m_log(m_fabs(x))),          v * y / x,                  v * m_log(m_fabs(x))) \
+    X(COND,       (x > T(0) ? y : T(0)),                T(0),                       b2t<T>(x > T(0))) \
+    X(LOGICAL_OR, b2t<T>(x > T(0) || y > T(0)),         T(0),                       T(0)) \
+    X(LOGICAL_AND,b2t<T>(x > T(0) && y > T(0)),         T(0),                       T(0)) \
+    X(GREATER_EQ, b2t<T>(x >= y),                       T(0),                       T(0)) \
+    X(LESS_EQ,    b2t<T>(x <= y),                       T(0),                       T(0))
+
+#define DEX_TERNARY_OPS(X) \
+    X(FMA,        m_fma(x, y, z),                       y, x, T(1)) \
+    X(MULADD,     m_fma(x, y, z),                       y, x, T(1)) \
+    X(CLAMP,      (x > z ? z : (x < y ? y : x)),        b2t<T>(!((x < y) || (z < x))), b2t<T>(x < y), b2t<T>(z < x)) \
+    X(MAX3,       j_max(j_max(x, y), z),                b2t<T>((j_max(x, y) > z) && (x > y)), b2t<T>((j_max(x, y) > z) && !(x > y)), b2t<T>(!(j_max(x, y) > z))) \
+    X(MIN3,       j_min(j_min(x, y), z),                b2t<T>(!(j_min(x, y) > z) && !(x > y)), b2t<T>(!(j_min(x, y) > z) && (x > y)), b2t<T>(j_min(x, y) > z)) \
+    X(ADD3,       (x + y) + z,                          T(1), T(1), T(1)) \
+    X(MUL3,       (x * y) * z,                          y * z, x * z, x * y)
+// clang-format on
+
+template <typename T> __device__ __forceinline__ T sq(T c) { return c * c; }
+
+}  // namespace dex

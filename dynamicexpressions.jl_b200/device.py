@@ -1,0 +1,390 @@
+"""ctypes binding of libdexb200.so (include/dexb200.h) plus thin object wrappers.
+
+This is the only module that touches the native library.  PyTorch is used for what
+the task calls plumbing — device memory, streams, pinned buffers, torch.distributed —
+and never for arithmetic: every number the evaluation entry points return is computed by
+the CUDA kernels in csrc/.  There is no CPU fallback: if the library is missing, or no
+CUDA device is visible, the calls below raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+from .node import MAX_DEGREE, WIRE_DTYPE, Node, to_wire_population
+from .operators import OperatorEnum
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libdexb200.so")
+
+OK = 0
+F32, F64 = 0, 1
+EVAL_EARLY_EXIT = 1
+PACK_FUSED, PACK_BUMPER = 1, 2
+GRAD_CONSTANTS, GRAD_FEATURES, GRAD_BOTH = 0, 1, 2
+
+# every symbol include/dexb200.h declares: (name, restype, argtypes)
+_P, _I32, _I64, _U8P = C.c_void_p, C.c_int32, C.c_int64, C.c_void_p
+ABI = {
+    "dex_abi_version": (C.c_int, []),
+    "dex_strerror": (C.c_char_p, [C.c_int]),
+    "dex_device_count": (C.c_int, []),
+    "dex_opcode_from_name": (C.c_int, [C.c_char_p, C.c_int]),
+    "dex_opcode_name": (C.c_char_p, [C.c_int]),
+    "dex_opcode_degree": (C.c_int, [C.c_int]),
+    "dex_ctx_create": (C.c_int, [C.c_int, C.POINTER(_P)]),
+    "dex_ctx_destroy": (C.c_int, [_P]),
+    "dex_ctx_set_stream": (C.c_int, [_P, _P]),
+    "dex_ctx_synchronize": (C.c_int, [_P]),
+    "dex_last_error": (C.c_char_p, [_P]),
+    "dex_optable_create": (C.c_int, [_P, _P, C.c_int, C.POINTER(_P)]),
+    "dex_optable_destroy": (C.c_int, [_P]),
+    "dex_population_pack": (C.c_int, [_P, _P, _P, _P, _I64, C.c_int, C.c_int, C.POINTER(_P)]),
+    "dex_population_destroy": (C.c_int, [_P]),
+    "dex_population_get_info": (C.c_int, [_P, _P]),
+    "dex_population_constant_counts": (C.c_int, [_P, _P]),
+    "dex_population_get_constants": (C.c_int, [_P, _P, _P, _I64]),
+    "dex_population_set_constants": (C.c_int, [_P, _P, _P, _I64]),
+    "dex_eval": (C.c_int, [_P, _P, _P, _I32, _I64, _I64, _P, _I64, _U8P, C.c_int]),
+    "dex_eval_parametric": (C.c_int, [_P, _P, _P, _I32, _I64, _I64, _P, _I32, _I32, _P, _P, _I64,
+                                      _U8P, C.c_int]),
+    "dex_eval_grad": (C.c_int, [_P, _P, _P, _I32, _I64, _I64, C.c_int, _P, _I64, _P, _P, _U8P]),
+    "dex_grad_offsets": (C.c_int, [_P, _I32, _I64, C.c_int, _P]),
+    "dex_eval_diff": (C.c_int, [_P, _P, _P, _I32, _I64, _I64, _I32, _P, _P, _I64, _U8P]),
+    "dex_eval_loss": (C.c_int, [_P, _P, _P, _I32, _I64, _I64, _P, _P, _P, _U8P, C.c_int]),
+    "dex_eval_host": (C.c_int, [_P, _P, _P, _I32, _I64, _I64, _P, _I64, _U8P, C.c_int]),
+    "dex_host_alloc": (C.c_int, [C.POINTER(_P), _I64]),
+    "dex_host_free": (C.c_int, [_P]),
+    "dex_ctx_launch_count": (_I64, [_P]),
+    "dex_population_copy_tape": (_I64, [_P, _P, _I64, _P]),
+}
+
+
+class DexError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libdexb200 error {code}: {msg}")
+        self.code = code
+
+
+class _Info(C.Structure):
+    _fields_ = [("n_trees", _I64), ("n_nodes", _I64), ("n_instructions", _I64),
+                ("n_constants", _I64), ("max_stack", _I32), ("max_feature", _I32),
+                ("max_parameter", _I32), ("dtype", _I32)]
+
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+def lib():
+    """Load libdexb200.so (built by ``__graft_entry__.build()`` / ``make -C csrc``)."""
+    global _lib
+    if _lib is None:
+        with _lib_lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise RuntimeError(
+                        f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; "
+                        f"g.build()'` (needs nvcc).  dexb200 has no CPU fallback.")
+                l = C.CDLL(LIB_PATH)
+                for name, (res, args) in ABI.items():
+                    fn = getattr(l, name)
+                    fn.restype = res
+                    fn.argtypes = args
+                if l.dex_abi_version() != 1:
+                    raise RuntimeError("libdexb200 ABI version mismatch")
+                _lib = l
+    return _lib
+
+
+def _ptr(a):
+    """Raw address of a numpy array / torch tensor / None."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    return a.data_ptr()
+
+
+def _dtype_code(dt):
+    import torch
+    if dt in (np.float32, torch.float32, np.dtype(np.float32)):
+        return F32
+    if dt in (np.float64, torch.float64, np.dtype(np.float64)):
+        return F64
+    raise TypeError(f"the device path evaluates Float32/Float64 only, got {dt}")
+
+
+def _torch_dtype(code):
+    import torch
+    return torch.float32 if code == F32 else torch.float64
+
+
+class Context:
+    """One ``dex_ctx`` per (host thread, device) — like the reference, nothing is shared
+    between concurrently evaluating threads."""
+
+    _tls = threading.local()
+
+    def __init__(self, device=0):
+        self.device = int(device)
+        h = _P()
+        rc = lib().dex_ctx_create(self.device, C.byref(h))
+        if rc != OK:
+            raise DexError(rc, lib().dex_strerror(rc).decode() +
+                           f" (creating a context on device {device}; dexb200 needs a CUDA GPU)")
+        self.h = h
+        self._optables = {}
+
+    @classmethod
+    def get(cls, device=None):
+        import torch
+        if device is None:
+            if not torch.cuda.is_available():
+                raise DexError(-3, "no CUDA device is available and dexb200 has no CPU fallback")
+            device = torch.cuda.current_device()
+        if isinstance(device, torch.device):
+            device = device.index if device.index is not None else torch.cuda.current_device()
+        cache = cls._tls.__dict__.setdefault("ctxs", {})
+        if device not in cache:
+            cache[device] = Context(device)
+        return cache[device]
+
+    def check(self, rc):
+        if rc != OK:
+            raise DexError(rc, lib().dex_last_error(self.h).decode() or lib().dex_strerror(rc).decode())
+
+    def use_current_stream(self):
+        import torch
+        s = torch.cuda.current_stream(self.device).cuda_stream
+        self.check(lib().dex_ctx_set_stream(self.h, _P(s)))
+
+    def synchronize(self):
+        self.check(lib().dex_ctx_synchronize(self.h))
+
+    @property
+    def launch_count(self):
+        return int(lib().dex_ctx_launch_count(self.h))
+
+    def optable(self, operators: OperatorEnum):
+        key = operators.key()
+        t = self._optables.get(key)
+        if t is None:
+            flat, offs = operators.flat_opcodes()
+            h = _P()
+            rc = lib().dex_optable_create(_ptr(flat), _ptr(offs), MAX_DEGREE, C.byref(h))
+            if rc != OK:
+                raise DexError(rc, lib().dex_strerror(rc).decode())
+            t = self._optables[key] = h
+        return t
+
+    def __del__(self):
+        try:
+            for t in self._optables.values():
+                lib().dex_optable_destroy(t)
+            lib().dex_ctx_destroy(self.h)
+        except Exception:
+            pass
+
+
+def host_context():
+    """A context that can pack/validate but not evaluate (no CUDA calls)."""
+    c = Context.__new__(Context)
+    c.device = -1
+    h = _P()
+    rc = lib().dex_ctx_create(-1, C.byref(h))
+    if rc != OK:
+        raise DexError(rc, lib().dex_strerror(rc).decode())
+    c.h = h
+    c._optables = {}
+    return c
+
+
+def as_device_matrix(X, device, dtype_code=None):
+    """Return (tensor with the memory of a column-major F x N matrix, F, N, ldx).
+
+    ``X`` has the reference's shape (F, N).  A torch CUDA tensor whose strides are already
+    (1, ldx) — e.g. ``Xt.T`` of a contiguous (N, F) tensor — is used in place; anything else
+    is copied (numpy -> pinned -> device, or a device transpose copy)."""
+    import torch
+    if isinstance(X, np.ndarray):
+        if X.ndim == 1:
+            X = X.reshape(-1, 1)
+        if dtype_code is not None:
+            X = X.astype(np.float32 if dtype_code == F32 else np.float64, copy=False)
+        Xt = torch.from_numpy(np.ascontiguousarray(X.T))
+        Xd = Xt.to(f"cuda:{device}", non_blocking=False)
+        F, N = X.shape
+        return Xd, F, N, F
+    if X.dim() == 1:
+        X = X.reshape(-1, 1)
+    if dtype_code is not None and X.dtype != _torch_dtype(dtype_code):
+        X = X.to(_torch_dtype(dtype_code))
+    F, N = X.shape
+    if not X.is_cuda or X.device.index != device:
+        X = X.to(f"cuda:{device}")
+    if N > 1 and F > 0 and X.stride(0) == 1 and X.stride(1) >= F:
+        return X, F, N, X.stride(1)
+    Xc = X.T.contiguous()  # (N, F) row-major == (F, N) column-major
+    return Xc, F, N, F
+
+
+class Population:
+    """A packed population of trees on one device (``dex_population``)."""
+
+    def __init__(self, trees, operators: OperatorEnum, dtype=np.float32, *, ctx: Context = None,
+                 bumper=False, use_fused=True, wire=None):
+        self.ctx = ctx or Context.get()
+        self.operators = operators
+        self.dtype_code = _dtype_code(dtype)
+        if wire is not None:
+            nodes, offsets = wire
+        else:
+            if isinstance(trees, Node):
+                trees = [trees]
+            nodes, offsets = to_wire_population(list(trees))
+        nodes = np.ascontiguousarray(nodes, dtype=WIRE_DTYPE)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        self.n_trees = len(offsets) - 1
+        flags = (PACK_BUMPER if bumper else 0) | (PACK_FUSED if use_fused else 0)
+        h = _P()
+        self.ctx.check(lib().dex_population_pack(self.ctx.h, self.ctx.optable(operators), _ptr(nodes),
+                                                 _ptr(offsets), self.n_trees, self.dtype_code, flags,
+                                                 C.byref(h)))
+        self.h = h
+        info = _Info()
+        lib().dex_population_get_info(self.h, C.byref(info))
+        self.info = {k: getattr(info, k) for k, _ in _Info._fields_}
+        self.n_nodes = self.info["n_nodes"]
+
+    def __del__(self):
+        try:
+            lib().dex_population_destroy(self.h)
+        except Exception:
+            pass
+
+    # -- constants -------------------------------------------------------------------
+    def constant_counts(self):
+        c = np.zeros(self.n_trees, dtype=np.int32)
+        lib().dex_population_constant_counts(self.h, _ptr(c))
+        return c
+
+    def get_constants(self):
+        v = np.zeros(self.info["n_constants"], dtype=np.float32 if self.dtype_code == F32 else np.float64)
+        self.ctx.check(lib().dex_population_get_constants(self.ctx.h, self.h, _ptr(v), len(v)))
+        return v
+
+    def set_constants(self, values):
+        v = np.ascontiguousarray(values, dtype=np.float32 if self.dtype_code == F32 else np.float64)
+        self.ctx.check(lib().dex_population_set_constants(self.ctx.h, self.h, _ptr(v), len(v)))
+
+    def tape(self):
+        """Host copy of the evaluation tape: (uint32[n, 4], offsets[n_trees + 1])."""
+        n = self.info["n_instructions"]
+        ins = np.zeros((n, 4), dtype=np.uint32)
+        off = np.zeros(self.n_trees + 1, dtype=np.int64)
+        lib().dex_population_copy_tape(self.h, _ptr(ins), n, _ptr(off))
+        return ins, off
+
+    # -- evaluation ------------------------------------------------------------------
+    def _outputs(self, N, out, ok):
+        import torch
+        dev = f"cuda:{self.ctx.device}"
+        if out is None:
+            out = torch.empty((self.n_trees, N), dtype=_torch_dtype(self.dtype_code), device=dev)
+        if ok is None:
+            ok = torch.empty(self.n_trees, dtype=torch.uint8, device=dev)
+        assert out.is_cuda and out.stride(-1) == 1 and out.shape == (self.n_trees, N)
+        return out, ok
+
+    def eval(self, X, *, early_exit=True, out=None, ok=None):
+        """Batched ``eval_tree_array``: returns (out[P, N], ok[P]) as CUDA tensors."""
+        Xd, F, N, ldx = as_device_matrix(X, self.ctx.device, self.dtype_code)
+        out, ok = self._outputs(N, out, ok)
+        self.ctx.use_current_stream()
+        self.ctx.check(lib().dex_eval(self.ctx.h, self.h, _ptr(Xd), F, N, ldx, _ptr(out),
+                                      out.stride(0) if self.n_trees else N, _ptr(ok),
+                                      EVAL_EARLY_EXIT if early_exit else 0))
+        return out, ok
+
+    def eval_parametric(self, X, parameters, classes0, *, early_exit=True, out=None, ok=None):
+        """``parameters``: (P, n_params, n_classes); ``classes0``: 0-based class per sample."""
+        import torch
+        Xd, F, N, ldx = as_device_matrix(X, self.ctx.device, self.dtype_code)
+        dev = f"cuda:{self.ctx.device}"
+        tdt = _torch_dtype(self.dtype_code)
+        params = torch.as_tensor(parameters, dtype=tdt)
+        if params.dim() == 2:
+            params = params.unsqueeze(0)
+        P, n_params, n_classes = params.shape
+        assert P == self.n_trees
+        pd = params.to(dev).permute(0, 2, 1).contiguous()  # per tree column-major (n_params x n_classes)
+        cl = torch.as_tensor(classes0).to(device=dev, dtype=torch.int32).contiguous()
+        assert cl.numel() == N
+        if N and (int(cl.min()) < 0 or int(cl.max()) >= n_classes):
+            raise DexError(-5, "class index out of range")
+        out, ok = self._outputs(N, out, ok)
+        self.ctx.use_current_stream()
+        self.ctx.check(lib().dex_eval_parametric(self.ctx.h, self.h, _ptr(Xd), F, N, ldx, _ptr(pd),
+                                                 n_params, n_classes, _ptr(cl), _ptr(out),
+                                                 out.stride(0) if self.n_trees else N, _ptr(ok),
+                                                 EVAL_EARLY_EXIT if early_exit else 0))
+        return out, ok
+
+    def grad_offsets(self, F, N, mode):
+        off = np.zeros(self.n_trees + 1, dtype=np.int64)
+        rc = lib().dex_grad_offsets(self.h, F, N, mode, _ptr(off))
+        if rc != OK:
+            raise DexError(rc, "dex_grad_offsets")
+        return off
+
+    def eval_grad(self, X, mode=GRAD_FEATURES):
+        """Batched ``eval_grad_tree_array``: (out[P, N], grad_flat, offsets, ok[P]).
+        Tree t's gradient is ``grad_flat[off[t]:off[t+1]].view(N, G_t).T`` (G_t x N)."""
+        import torch
+        Xd, F, N, ldx = as_device_matrix(X, self.ctx.device, self.dtype_code)
+        out, ok = self._outputs(N, None, None)
+        off = self.grad_offsets(F, N, mode)
+        grad = torch.empty(int(off[-1]), dtype=out.dtype, device=out.device)
+        self.ctx.use_current_stream()
+        self.ctx.check(lib().dex_eval_grad(self.ctx.h, self.h, _ptr(Xd), F, N, ldx, mode, _ptr(out),
+                                           out.stride(0) if self.n_trees else N, _ptr(grad),
+                                           _ptr(off), _ptr(ok)))
+        return out, grad, off, ok
+
+    def eval_diff(self, X, direction0):
+        import torch
+        Xd, F, N, ldx = as_device_matrix(X, self.ctx.device, self.dtype_code)
+        out, ok = self._outputs(N, None, None)
+        dout = torch.empty_like(out)
+        self.ctx.use_current_stream()
+        self.ctx.check(lib().dex_eval_diff(self.ctx.h, self.h, _ptr(Xd), F, N, ldx, int(direction0),
+                                           _ptr(out), _ptr(dout), out.stride(0) if self.n_trees else N,
+                                           _ptr(ok)))
+        return out, dout, ok
+
+    def eval_loss(self, X, y, *, early_exit=True):
+        """Fused mean-squared-error per tree without materialising the results:
+        (loss[P] float64, ok[P])."""
+        import torch
+        Xd, F, N, ldx = as_device_matrix(X, self.ctx.device, self.dtype_code)
+        dev = f"cuda:{self.ctx.device}"
+        yd = torch.as_tensor(y).to(device=dev, dtype=_torch_dtype(self.dtype_code)).contiguous()
+        assert yd.numel() == N
+        loss = torch.empty(self.n_trees, dtype=torch.float64, device=dev)
+        ok = torch.empty(self.n_trees, dtype=torch.uint8, device=dev)
+        self.ctx.use_current_stream()
+        self.ctx.check(lib().dex_eval_loss(self.ctx.h, self.h, _ptr(Xd), F, N, ldx, _ptr(yd), None,
+                                           _ptr(loss), _ptr(ok), EVAL_EARLY_EXIT if early_exit else 0))
+        return loss, ok
+
+    def eval_host(self, X_host, out_host, ok_host, *, early_exit=True):
+        """The host-buffer entry point (dex_eval_host): numpy / pinned torch CPU tensors in the
+        library's layouts — ``X_host`` is (N, F) row-major, ``out_host`` (P, N), ``ok_host`` (P,)."""
+        N, F = X_host.shape
+        self.ctx.check(lib().dex_eval_host(self.ctx.h, self.h, _ptr(X_host), F, N, F, _ptr(out_host),
+                                           N, _ptr(ok_host), EVAL_EARLY_EXIT if early_exit else 0))
+        return out_host, ok_host

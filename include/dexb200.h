@@ -1,0 +1,198 @@
+/* dexb200.h — C ABI of libdexb200.so: the B200-native batched replacement for the
+ * evaluation hot path of DynamicExpressions.jl.
+ *
+ * This is the drop-in boundary.  The reference is pure Julia; what its FFI for
+ * this path would bind (a package extension in the style of
+ * /root/reference/ext/DynamicExpressionsBumperExt.jl that overloads
+ * eval_tree_array / eval_grad_tree_array and `ccall`s a shared library) is exactly
+ * the set of entry points below.  INTEGRATION.md shows the Julia-side binding.
+ *
+ * Conventions
+ *   - plain C: opaque handles, raw pointers, sizes; no C++/torch types.
+ *   - every function returns DEX_OK (0) or a negative DEX_ERR_* code and never
+ *     throws or exits; dex_last_error(ctx) has the message of the last failure.
+ *   - indices inside the ABI are 0-BASED (the Julia shim subtracts 1).
+ *   - X is column-major (nfeatures x nsamples) with leading dimension ldx, i.e.
+ *     exactly the memory of the reference's `cX::Matrix{T}`
+ *     (/root/reference/src/Evaluate.jl:124-128: sample stride = nfeatures).
+ *   - results are (n_trees x nsamples) row-major with row stride ldo: row t is the
+ *     `Vector{T}` the reference returns for tree t.
+ *   - `_dev` pointers are device memory on the context's device, owned by the
+ *     caller; `_host` pointers are host memory.  The library owns only its context
+ *     scratch and the packed populations.
+ *   - a context is single-threaded (one per host thread, like the reference's
+ *     per-task Bumper slab); different contexts are independent => re-entrant.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point
+ *     returns DEX_ERR_CUDA.
+ */
+#ifndef DEXB200_H
+#define DEXB200_H
+
+#include <stdint.h>
+#include "dex_wire.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DEXB200_ABI_VERSION 1
+
+typedef struct dex_ctx dex_ctx;
+typedef struct dex_optable dex_optable;
+typedef struct dex_population dex_population;
+
+enum {
+    DEX_OK = 0,
+    DEX_ERR_INVALID = -1,     /* bad argument / malformed tree (index in message) */
+    DEX_ERR_NOMEM = -2,
+    DEX_ERR_CUDA = -3,        /* CUDA runtime failure or no device */
+    DEX_ERR_UNSUPPORTED = -4, /* operator without device implementation, tree too deep, ... */
+    DEX_ERR_RANGE = -5        /* feature / parameter / class index out of range */
+};
+
+/* Evaluation policy = the flags of the reference's EvalContext
+ * (/root/reference/src/Evaluate.jl:156-181).                                        */
+enum {
+    DEX_EVAL_EARLY_EXIT = 1, /* early_exit=Val(true): `complete` is false when any checked
+                                intermediate is non-finite (reference default)             */
+    DEX_EVAL_DEFAULT = 1
+};
+
+/* Pack-time policy: which validity checks the reference path performs depends on how
+ * it fuses nodes (see DESIGN.md "completion flag").                                  */
+enum {
+    DEX_PACK_FUSED = 1,   /* use_fused=Val(true), the reference default                   */
+    DEX_PACK_BUMPER = 2,  /* semantics of the Bumper evaluator
+                             (/root/reference/ext/DynamicExpressionsBumperExt.jl:11-89)    */
+    DEX_PACK_DEFAULT = 1
+};
+
+/* gradient modes: `variable` of eval_grad_tree_array
+ * (/root/reference/src/EvaluateDerivative.jl:193-228)                                */
+enum { DEX_GRAD_CONSTANTS = 0, DEX_GRAD_FEATURES = 1, DEX_GRAD_BOTH = 2 };
+
+/* ---- library ---------------------------------------------------------------------- */
+int dex_abi_version(void);
+const char* dex_strerror(int code);
+/* number of CUDA devices visible (0 when there is no GPU / driver) */
+int dex_device_count(void);
+/* builtin opcode for a Julia function name at a given arity, or -1
+ * (`(degree, op_idx) -> opcode` is what replaces OperatorEnum's tuple of functions,
+ * /root/reference/src/OperatorEnum.jl:14-49)                                         */
+int dex_opcode_from_name(const char* name, int degree);
+const char* dex_opcode_name(int opcode);
+int dex_opcode_degree(int opcode);
+
+/* ---- context ---------------------------------------------------------------------- */
+/* device < 0: host-only context (packing / validation only, no CUDA calls).           */
+int dex_ctx_create(int device, dex_ctx** out);
+int dex_ctx_destroy(dex_ctx* ctx);
+/* stream: a cudaStream_t (or NULL for the context's own stream); all device work of
+ * later calls is enqueued on it and is asynchronous w.r.t. the host, except the
+ * *_host convenience entry points, which synchronise.                                */
+int dex_ctx_set_stream(dex_ctx* ctx, void* stream);
+int dex_ctx_synchronize(dex_ctx* ctx);
+const char* dex_last_error(const dex_ctx* ctx);
+
+/* ---- operators -------------------------------------------------------------------- */
+/* opcodes[degree_offsets[d-1] .. degree_offsets[d]) are the builtin opcodes of
+ * operators[d] in order; max_degree <= DEX_MAX_DEGREE.                               */
+int dex_optable_create(const int32_t* opcodes, const int32_t* degree_offsets, int max_degree,
+                       dex_optable** out);
+int dex_optable_destroy(dex_optable* t);
+
+/* ---- populations ------------------------------------------------------------------ */
+/* Flatten n_trees wire trees (nodes[offsets[t] .. offsets[t+1])) into device tapes.
+ * dtype: DEX_F32 / DEX_F64.  Validates arity, operator indices and leaf kinds
+ * (feature / parameter ranges are checked at evaluation time against the actual X).
+ * replaces: the per-call recursive walk of /root/reference/src/Evaluate.jl:337-364.   */
+int dex_population_pack(dex_ctx* ctx, const dex_optable* ops, const dex_node* nodes,
+                        const int64_t* offsets, int64_t n_trees, int dtype, int pack_flags,
+                        dex_population** out);
+int dex_population_destroy(dex_population* pop);
+
+typedef struct dex_population_info {
+    int64_t n_trees;
+    int64_t n_nodes;          /* sum of count_nodes(tree) — the node-ops/sample of the metric */
+    int64_t n_instructions;   /* fused evaluation tape length                                   */
+    int64_t n_constants;      /* sum of count_constant_nodes(tree)                              */
+    int32_t max_stack;        /* operand-stack rows the evaluation tape needs                   */
+    int32_t max_feature;      /* largest feature index used (0-based), -1 if none               */
+    int32_t max_parameter;    /* largest parameter index used (0-based), -1 if none             */
+    int32_t dtype;
+} dex_population_info;
+int dex_population_get_info(const dex_population* pop, dex_population_info* info);
+/* per-tree count_constant_nodes (/root/reference/src/NodeUtils.jl:43-51); counts[n_trees] */
+int dex_population_constant_counts(const dex_population* pop, int32_t* counts);
+/* get/set_scalar_constants (/root/reference/src/NodeUtils.jl:99-143) for the whole
+ * population without re-packing: values are in tree order, then depth-first
+ * left-to-right leaf order inside a tree; n_values must equal info.n_constants.
+ * Element type = the population dtype.                                               */
+int dex_population_get_constants(dex_ctx* ctx, const dex_population* pop, void* values_host,
+                                 int64_t n_values);
+int dex_population_set_constants(dex_ctx* ctx, dex_population* pop, const void* values_host,
+                                 int64_t n_values);
+
+/* ---- evaluation ------------------------------------------------------------------- */
+/* Batched eval_tree_array (/root/reference/src/Evaluate.jl:279-309), one launch for the
+ * population: out_dev[t*ldo + j] = tree_t(X[:, j]);  ok_dev[t] = `complete` flag.      */
+int dex_eval(dex_ctx* ctx, const dex_population* pop, const void* X_dev, int32_t nfeatures,
+             int64_t nsamples, int64_t ldx, void* out_dev, int64_t ldo, uint8_t* ok_dev,
+             int eval_flags);
+
+/* ParametricExpression evaluation (/root/reference/src/ParametricExpression.jl:371-390)
+ * without materialising parameters[:, classes] or the vcat: params_dev holds, per tree,
+ * an (n_params x n_classes) column-major block; classes_dev[j] in [0, n_classes).       */
+int dex_eval_parametric(dex_ctx* ctx, const dex_population* pop, const void* X_dev,
+                        int32_t nfeatures, int64_t nsamples, int64_t ldx, const void* params_dev,
+                        int32_t n_params, int32_t n_classes, const int32_t* classes_dev,
+                        void* out_dev, int64_t ldo, uint8_t* ok_dev, int eval_flags);
+
+/* Batched eval_grad_tree_array (/root/reference/src/EvaluateDerivative.jl:193-404).
+ * Tree t writes a (G_t x nsamples) column-major block (gradient index fastest) at
+ * grad_dev + grad_offsets[t] (element offsets, host array of n_trees+1 entries);
+ * G_t = nfeatures | n_constants(t) | nfeatures + n_constants(t) by mode.              */
+int dex_eval_grad(dex_ctx* ctx, const dex_population* pop, const void* X_dev, int32_t nfeatures,
+                  int64_t nsamples, int64_t ldx, int mode, void* out_dev, int64_t ldo,
+                  void* grad_dev, const int64_t* grad_offsets_host, uint8_t* ok_dev);
+/* fills offsets[n_trees+1] for the layout above */
+int dex_grad_offsets(const dex_population* pop, int32_t nfeatures, int64_t nsamples, int mode,
+                     int64_t* offsets_host);
+
+/* Batched eval_diff_tree_array (/root/reference/src/EvaluateDerivative.jl:40-168):
+ * derivative along feature `direction` (0-based); never reports failure (ok = 1).      */
+int dex_eval_diff(dex_ctx* ctx, const dex_population* pop, const void* X_dev, int32_t nfeatures,
+                  int64_t nsamples, int64_t ldx, int32_t direction, void* out_dev,
+                  void* dout_dev, int64_t ldo, uint8_t* ok_dev);
+
+/* Fused loss reduction (what callers of the path consume):
+ * loss_dev[t] = sum_j w_j (tree_t(X[:,j]) - y[j])^2 / sum_j w_j   (weights may be NULL),
+ * without writing the (n_trees x nsamples) result matrix.  loss is float64.            */
+int dex_eval_loss(dex_ctx* ctx, const dex_population* pop, const void* X_dev, int32_t nfeatures,
+                  int64_t nsamples, int64_t ldx, const void* y_dev, const void* weights_dev,
+                  double* loss_dev, uint8_t* ok_dev, int eval_flags);
+
+/* ---- host-buffer convenience (the reference-facing call: host arrays in, host arrays
+ * out; copies are issued on the context stream through pinned staging buffers and the
+ * call returns after the results have landed)                                          */
+int dex_eval_host(dex_ctx* ctx, const dex_population* pop, const void* X_host, int32_t nfeatures,
+                  int64_t nsamples, int64_t ldx, void* out_host, int64_t ldo, uint8_t* ok_host,
+                  int eval_flags);
+
+/* pinned (page-locked) host buffers, so the copies of the *_host entry points run at full
+ * PCIe speed and asynchronously */
+int dex_host_alloc(void** out, int64_t bytes);
+int dex_host_free(void* p);
+
+/* ---- introspection (tests, benchmarks) -------------------------------------------------- */
+/* kernels launched through this context so far */
+int64_t dex_ctx_launch_count(const dex_ctx* ctx);
+/* copies the host image of the evaluation tape (16-byte instructions, csrc/dex_tape.h);
+ * returns the instruction count; offsets (n_trees+1) may be NULL */
+int64_t dex_population_copy_tape(const dex_population* pop, void* instrs, int64_t capacity,
+                                 int64_t* offsets);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEXB200_H */

@@ -1,0 +1,230 @@
+"""CPU-only checks of the native library: the C ABI exports every declared symbol, the
+host-only context packs/validates, and the flattened tapes (executed by a numpy tape
+interpreter, tests/tape_sim.py) agree with the CPU oracle — values AND the `complete`
+flag, for every EvalContext policy.  No compute call touches a GPU here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import dexb200
+from dexb200 import device as D
+from dexb200 import treegen
+from tests.golden_util import (CONTEXTS, load_cases, make_matrix, make_operators, make_tree)
+from tests.tape_sim import run_tape
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "dexb200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(dex_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 25
+    raw = C.CDLL(D.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(raw, name), f"{name} is declared in include/dexb200.h but not exported"
+    assert declared <= set(D.ABI), declared - set(D.ABI)
+    assert D.lib().dex_abi_version() == 1
+
+
+def test_opcode_lookup_matches_def_file():
+    l = D.lib()
+    for (name, deg), code in dexb200.OPCODE_TABLE.items():
+        got = l.dex_opcode_from_name(name.encode(), deg)
+        if got != code:
+            # python-side table also knows lower-cased symbol names; C side knows name + aliases
+            assert name == dexb200.OPCODE_INFO[code][0].lower()
+            continue
+        assert l.dex_opcode_degree(code) == deg
+    assert l.dex_opcode_from_name(b"no_such_operator", 1) == -1
+    assert l.dex_opcode_from_name(b"cos", 2) == -1
+
+
+def test_compute_without_gpu_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    ops = dexb200.OperatorEnum({1: ("cos",), 2: ("+", "*")})
+    tree = dexb200.Node(1, dexb200.Node(feature=1))
+    with pytest.raises(D.DexError):
+        dexb200.eval_tree_array(tree, np.ones((1, 4), np.float32), ops)
+    # and through the raw ABI on a host-only context
+    ctx = D.host_context()
+    pop = D.Population([tree], ops, np.float32, ctx=ctx)
+    out = np.zeros((1, 4), np.float32)
+    ok = np.zeros(1, np.uint8)
+    X = np.ones((4, 1), np.float32)
+    rc = D.lib().dex_eval(ctx.h, pop.h, X.ctypes.data, 1, 4, 1, out.ctypes.data, 4, ok.ctypes.data, 1)
+    assert rc == -3 and b"no CPU fallback" in D.lib().dex_last_error(ctx.h)
+
+
+def test_pack_validation_errors():
+    ctx = D.host_context()
+    ops = dexb200.OperatorEnum({1: ("cos",), 2: ("+",)})
+    N = dexb200.Node
+    bad_op = N(3, N(feature=1), N(val=1.0))          # only one binary operator
+    with pytest.raises(D.DexError, match="op index"):
+        D.Population([N(1, N(feature=1)), bad_op], ops, np.float32, ctx=ctx)
+    # truncated wire array
+    w = dexb200.to_wire(N(1, N(feature=1), N(val=2.0)))[:2]
+    with pytest.raises(D.DexError, match="tree 0"):
+        D.Population(None, ops, np.float32, ctx=ctx, wire=(w, np.array([0, 2])))
+    with pytest.raises(ValueError, match="no device implementation"):
+        dexb200.OperatorEnum({1: ("my_custom_function",)})
+
+
+def test_population_info_and_constants_roundtrip():
+    ctx = D.host_context()
+    ops = dexb200.OperatorEnum({1: ("cos",), 2: ("+", "*", "-")})
+    N = dexb200.Node
+    t1 = N(2, N(1, N(val=1.5), N(3, N(feature=1), N(val=2.5))), N(1, N(1, N(val=3.5), N(val=4.5))))
+    t2 = N(1, N(feature=3))
+    pop = D.Population([t1, t2], ops, np.float64, ctx=ctx)
+    assert pop.info["n_trees"] == 2 and pop.info["n_nodes"] == 10 + 2
+    assert pop.info["max_feature"] == 2 and pop.info["n_constants"] == 4
+    assert list(pop.constant_counts()) == [4, 0]
+    assert list(pop.get_constants()) == [1.5, 2.5, 3.5, 4.5]      # leaf order, NodeUtils.jl:99-116
+    pop.set_constants([10.0, 20.0, 30.0, 40.0])
+    assert list(pop.get_constants()) == [10.0, 20.0, 30.0, 40.0]
+
+
+def _flags(o, ctx):
+    return ((o.EARLY_EXIT if ctx.get("early_exit", True) else 0) |
+            (o.USE_FUSED if ctx.get("use_fused", True) else 0) | (o.BUMPER if ctx.get("bumper") else 0))
+
+
+ALL_CTX = ["default", "bumper", "unfused", "no_early_exit", "bumper_no_early_exit"]
+
+
+@pytest.mark.parametrize("case", load_cases(), ids=lambda c: c["id"])
+def test_flattened_tape_matches_oracle_on_golden_cases(case, oracle):
+    hctx = D.host_context()
+    for dt in case["dtypes"]:
+        dtype = np.dtype(dt).type
+        ops = make_operators(case)
+        tree = make_tree(case["tree"], ops, dtype)
+        wire = dexb200.to_wire(tree)
+        X = make_matrix(case["X"], dtype)
+        P = cls0 = None
+        if "parameters" in case:
+            P = make_matrix(case["parameters"], dtype)
+            cls0 = np.array(case["classes"], dtype=np.int64) - 1
+        for cname in ALL_CTX:
+            c = CONTEXTS[cname]
+            pop = D.Population([tree], ops, dtype, ctx=hctx, bumper=c.get("bumper", False),
+                               use_fused=c.get("use_fused", True))
+            ins, off = pop.tape()
+            y, ok = run_tape(ins, X, pop.info["max_stack"], dexb200.OPCODE_INFO, dtype,
+                             early_exit=c.get("early_exit", True), params=P, classes0=cls0)
+            if P is not None:
+                ry, rok = oracle.eval_parametric(wire, ops.opcodes, X, P, cls0, _flags(oracle, c))
+            else:
+                ry, rok = oracle.eval_tree_array(wire, ops.opcodes, X, _flags(oracle, c))
+            assert ok == rok, (case["id"], dt, cname)
+            if rok:
+                tol = 1e-4 if dtype == np.float32 else 1e-9
+                fin = np.isfinite(ry)
+                np.testing.assert_allclose(y[fin], ry[fin], rtol=tol, atol=tol)
+                assert (np.isfinite(y) == fin).all()
+
+
+def _nonfinite_X(rng, F, N, dtype):
+    X = rng.standard_normal((F, N)).astype(dtype)
+    # sprinkle Inf / NaN into some columns so that the path-dependent validity rules matter
+    for _ in range(3):
+        X[rng.integers(F), rng.integers(N)] = rng.choice([np.inf, -np.inf, np.nan])
+    return X
+
+
+@pytest.mark.parametrize("seed", range(6))
+@pytest.mark.parametrize("cname", ALL_CTX)
+def test_flattened_tape_matches_oracle_on_random_trees(seed, cname, oracle):
+    """Random trees incl. ternary operators, >15-operator enums, non-finite constants and
+    non-finite X: the `complete` flag of the tape equals the oracle's for every policy."""
+    rng = np.random.default_rng(1000 + seed)
+    hctx = D.host_context()
+    big = seed % 3 == 2
+    spec = {1: ("cos", "exp", "abs", "sin") + (("square",) * 14 if big else ()),
+            2: ("+", "-", "*", "/", "max") + (("+",) * 12 if big else ()),
+            3: ("fma", "clamp")}
+    ops = dexb200.OperatorEnum(spec)
+    c = CONTEXTS[cname]
+    F, N = 4, 24
+    n_checked = 0
+    for k in range(60):
+        w = _random_wire(rng, ops, F, max_nodes=int(rng.integers(1, 40)))
+        dtype = np.float32 if k % 2 else np.float64
+        X = _nonfinite_X(rng, F, N, dtype) if k % 3 == 0 else rng.standard_normal((F, N)).astype(dtype)
+        pop = D.Population(None, ops, dtype, ctx=hctx, wire=(w, np.array([0, len(w)])),
+                           bumper=c.get("bumper", False), use_fused=c.get("use_fused", True))
+        ins, _ = pop.tape()
+        y, ok = run_tape(ins, X, pop.info["max_stack"], dexb200.OPCODE_INFO, dtype,
+                         early_exit=c.get("early_exit", True))
+        ry, rok = oracle.eval_tree_array(w, ops.opcodes, X, _flags(oracle, c))
+        assert ok == rok, (seed, k, cname, dexb200.string_tree(dexb200.from_wire(w), ops))
+        if rok:
+            n_checked += 1
+            tol = 2e-4 if dtype == np.float32 else 1e-8
+            fin = np.isfinite(ry) & (np.abs(ry) < 1e30)
+            np.testing.assert_allclose(y[fin], ry[fin], rtol=tol, atol=tol)
+    assert n_checked > 5
+
+
+def _random_wire(rng, ops, F, max_nodes):
+    """Random tree with unary/binary/ternary nodes and occasional Inf/NaN constants."""
+    N = dexb200.Node
+
+    def leaf():
+        r = rng.random()
+        if r < 0.45:
+            return N(feature=int(rng.integers(F)) + 1)
+        if r < 0.48:
+            return N(val=float(rng.choice([np.inf, -np.inf, np.nan])))
+        return N(val=float(np.float32(rng.standard_normal())))
+
+    def grow(budget):
+        if budget <= 1 or rng.random() < 0.15:
+            return leaf(), 1
+        deg = int(rng.choice([1, 2, 2, 2, 3]))
+        deg = min(deg, budget - 1)
+        used = 1
+        ch = []
+        for k in range(deg):
+            sub, n = grow(max(1, (budget - used) // (deg - k)))
+            ch.append(sub)
+            used += n
+        return N(int(rng.integers(ops.nops(deg))) + 1, *ch), used
+
+    t, _ = grow(max_nodes)
+    return dexb200.to_wire(t)
+
+
+def test_stack_need_uses_sethi_ullman_order():
+    """A right-deep tree needs no more stack rows than its left-deep mirror."""
+    hctx = D.host_context()
+    ops = dexb200.OperatorEnum({1: ("cos",), 2: ("+", "*")})
+    N = dexb200.Node
+
+    def deep(side, d):
+        if d == 0:
+            return N(1, N(feature=1))
+        sub = deep(side, d - 1)
+        other = N(1, N(feature=2))
+        return N(2, sub, other) if side == "l" else N(2, other, sub)
+
+    a = D.Population([deep("l", 12)], ops, np.float32, ctx=hctx).info["max_stack"]
+    b = D.Population([deep("r", 12)], ops, np.float32, ctx=hctx).info["max_stack"]
+    assert a == b == 1
+
+
+def test_treegen_depth_and_determinism():
+    nodes, off = treegen.gen_population(50, 8, 2, 4, 5, seed=7)
+    nodes2, off2 = treegen.gen_population(50, 8, 2, 4, 5, seed=7)
+    assert (off == off2).all() and (nodes == nodes2).all()
+    for i in range(50):
+        t = dexb200.from_wire(nodes[off[i]:off[i + 1]])
+        assert dexb200.count_depth(t) == 8
+        assert dexb200.count_nodes(t) == off[i + 1] - off[i] <= 255

