@@ -33,6 +33,8 @@ struct dex_ctx {
     size_t scratch_bytes = 0;
     void* pinned = nullptr;
     size_t pinned_bytes = 0;
+    void* xt = nullptr;      // feature-major padded copy of X for the interpreter
+    size_t xt_bytes = 0;
     void* dev_io = nullptr;  // device staging for the *_host entry points
     size_t dev_io_bytes = 0;
     cudaEvent_t ev[2] = {nullptr, nullptr};
@@ -106,6 +108,13 @@ int ensure_scratch(dex_ctx* ctx, size_t bytes) {
     if (ctx->scratch) { CU(ctx, cudaStreamSynchronize(ctx->stream)); CU(ctx, cudaFree(ctx->scratch)); ctx->scratch = nullptr; ctx->scratch_bytes = 0; }
     CU(ctx, cudaMalloc(&ctx->scratch, bytes));
     ctx->scratch_bytes = bytes;
+    return DEX_OK;
+}
+int ensure_xt(dex_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->xt_bytes) return DEX_OK;
+    if (ctx->xt) { CU(ctx, cudaStreamSynchronize(ctx->stream)); CU(ctx, cudaFree(ctx->xt)); ctx->xt = nullptr; ctx->xt_bytes = 0; }
+    CU(ctx, cudaMalloc(&ctx->xt, bytes));
+    ctx->xt_bytes = bytes;
     return DEX_OK;
 }
 int ensure_dev_io(dex_ctx* ctx, size_t bytes) {
@@ -203,7 +212,8 @@ int run_eval(dex_ctx* ctx, const dex_population* cpop, const void* X, int32_t F,
     if (rc) return rc;
     a.n_chunks = (int32_t)n_chunks;
     a.max_stack = h.max_stack;
-    a.X = X; a.F = F; a.N = N; a.ldx = ldx;
+    if ((rc = ensure_xt(ctx, eval_xt_bytes(h.dtype, F, h.max_stack, N)))) return rc;
+    a.X = X; a.F = F; a.N = N; a.ldx = ldx; a.xt = ctx->xt;
     a.out = out; a.ldo = ldo; a.ok = ok;
     a.early_exit = (eval_flags & DEX_EVAL_EARLY_EXIT) ? 1 : 0;
     a.params = params; a.n_params = n_params; a.n_classes = n_classes; a.classes = classes;
@@ -289,6 +299,7 @@ int dex_ctx_destroy(dex_ctx* ctx) {
         cudaSetDevice(ctx->device);
         cudaStreamSynchronize(ctx->stream);
         if (ctx->scratch) cudaFree(ctx->scratch);
+        if (ctx->xt) cudaFree(ctx->xt);
         if (ctx->dev_io) cudaFree(ctx->dev_io);
         if (ctx->pinned) cudaFreeHost(ctx->pinned);
         for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
@@ -301,7 +312,13 @@ int dex_ctx_destroy(dex_ctx* ctx) {
 
 int dex_ctx_set_stream(dex_ctx* ctx, void* stream) {
     if (!ctx) return DEX_ERR_INVALID;
-    ctx->stream = stream ? static_cast<cudaStream_t>(stream) : ctx->own_stream;
+    ctx->stream = static_cast<cudaStream_t>(stream);
+    return DEX_OK;
+}
+
+int dex_ctx_use_own_stream(dex_ctx* ctx) {
+    if (!ctx) return DEX_ERR_INVALID;
+    ctx->stream = ctx->own_stream;
     return DEX_OK;
 }
 
@@ -392,6 +409,8 @@ int dex_population_get_info(const dex_population* pop, dex_population_info* info
     info->max_feature = pop->h.max_feature;
     info->max_parameter = pop->h.max_parameter;
     info->dtype = pop->h.dtype;
+    info->n_generic = pop->h.n_generic;
+    info->n_checks = pop->h.n_checks;
     return DEX_OK;
 }
 
@@ -399,6 +418,23 @@ int dex_population_constant_counts(const dex_population* pop, int32_t* counts) {
     if (!pop || !counts) return DEX_ERR_INVALID;
     std::copy(pop->h.n_const_tree.begin(), pop->h.n_const_tree.end(), counts);
     return DEX_OK;
+}
+
+const char* dex_handler_name(int h) {
+    static const char* names[] = {
+        "GENERIC", "LOAD_R", "LOAD_C",
+#define X(S) #S "_A", #S "_R",
+        DEX_FAST_UNARY(X)
+#undef X
+#define X(S) #S "_AR", #S "_AC", #S "_RR", #S "_RC",
+        DEX_FAST_BIN_COMM(X)
+#undef X
+#define X(S) #S "_AR", #S "_RA", #S "_AC", #S "_CA", #S "_RR", #S "_RC", #S "_CR",
+        DEX_FAST_BIN_NC(X)
+#undef X
+    };
+    static_assert(sizeof(names) / sizeof(names[0]) == H__COUNT, "handler name table out of sync");
+    return (h >= 0 && h < (int)H__COUNT) ? names[h] : nullptr;
 }
 
 // debugging / tests: copy out the host image of the evaluation tape

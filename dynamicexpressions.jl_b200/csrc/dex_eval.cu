@@ -11,34 +11,49 @@
 //   grid.x  sample tiles of TILE = blockDim.x * K samples; the (F x TILE) slab of the
 //           column-major X is staged ONCE per CTA into shared memory, feature-major
 //   grid.y  chunks of trees (balanced by tape length on the host)
-//   thread  K consecutive samples (K * sizeof(T) = 16 bytes => one LDS.128 per operand,
-//           one STG.128 per result); accumulator, operands and validity accumulators
-//           live in registers; the operand stack is rows of the same shared array
+//   thread  K = U * C samples held as U 16-byte chunks (C = 4 floats / 2 doubles):
+//           chunk u of thread t covers samples u*(blockDim.x*C) + t*C .. +C-1, so every
+//           operand fetch is a conflict-free LDS.128 and every result store a fully
+//           coalesced STG.128.  Accumulator, operands and validity accumulators live in
+//           registers; the operand stack is rows of the same shared array.
 //   CTA     walks the tapes of its chunk; the tape pointer depends only on blockIdx and
-//           loop counters, so instruction fetch/decode/branch are warp-uniform
-//           (no divergence on the op switch).
+//           loop counters, so instruction fetch/decode/branch are warp-uniform and run on
+//           the uniform datapath (no divergence on the op switch).
+// The kernel is instruction-issue bound (ncu: >90 % of peak issue rate), so the design
+// goal is the fewest SASS instructions per tape instruction: one indirect branch to a
+// handler specialised for (operator, operand sources), K samples per dispatch, validity
+// checks elided on the host where a later check subsumes them.
 // No tensor cores: the path is elementwise, not a contraction.
 #include "dex_kernels.h"
 #include "dex_ops.cuh"
 
 #include <algorithm>
+#include <cstdlib>
+
+// samples per thread = DEX_EVAL_U chunks of 16 bytes (8 floats / 4 doubles for U = 2)
+#ifndef DEX_EVAL_U
+#define DEX_EVAL_U 2
+#endif
 
 namespace dex {
 
 namespace {
 
-template <typename T> struct KOf;
-template <> struct KOf<float> { static constexpr int K = 4; };
-template <> struct KOf<double> { static constexpr int K = 2; };
+template <typename T> struct ChunkOf;
+template <> struct ChunkOf<float> { static constexpr int C = 4; };
+template <> struct ChunkOf<double> { static constexpr int C = 2; };
 
-template <typename T, int K> __device__ __forceinline__ void ld_row(T (&v)[K], const T* p) {
-    static_assert(sizeof(T) * K == 16, "row vectors are 16 bytes");
-    const uint4 u = *reinterpret_cast<const uint4*>(p);
-    *reinterpret_cast<uint4*>(v) = u;
-}
-template <typename T, int K> __device__ __forceinline__ void st_row(T* p, const T (&v)[K]) {
-    *reinterpret_cast<uint4*>(p) = *reinterpret_cast<const uint4*>(v);
-}
+// operators as compile-time functors: Op1<DEX_OP_COS, T>::f(x)
+template <int OPC, typename T> struct Op1;
+template <int OPC, typename T> struct Op2;
+#define X1(SYM, VEXPR, GEXPR) \
+    template <typename T> struct Op1<DEX_OP_##SYM, T> { static __device__ __forceinline__ T f(T x) { return (VEXPR); } };
+DEX_UNARY_OPS(X1)
+#undef X1
+#define X2(SYM, VEXPR, G0, G1) \
+    template <typename T> struct Op2<DEX_OP_##SYM, T> { static __device__ __forceinline__ T f(T x, T y) { return (VEXPR); } };
+DEX_BINARY_OPS(X2)
+#undef X2
 
 template <typename T> __device__ __forceinline__ T const_of(const uint4& ins);
 template <> __device__ __forceinline__ float const_of<float>(const uint4& ins) { return __uint_as_float(ins.z); }
@@ -60,46 +75,104 @@ template <typename T> struct KArgs {
     int32_t F, max_stack, early_exit, n_params, n_classes;
 };
 
-template <typename T, bool PARAM, bool LOSS>
-__global__ void __launch_bounds__(256) eval_kernel(const KArgs<T> a) {
-    constexpr int K = KOf<T>::K;
+// A row vector of one thread: U chunks of C elements.
+template <typename T, int U> struct Vec {
+    static constexpr int C = ChunkOf<T>::C;
+    static constexpr int K = U * C;
+    T v[K];
+};
+
+template <typename T, int U>
+__device__ __forceinline__ void ld_row(Vec<T, U>& r, const T* row_base, int chunk_stride) {
+    // row_base already includes the thread offset t*C
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const uint4 q = *reinterpret_cast<const uint4*>(row_base + u * chunk_stride);
+        *reinterpret_cast<uint4*>(&r.v[u * Vec<T, U>::C]) = q;
+    }
+}
+template <typename T, int U>
+__device__ __forceinline__ void st_row(T* row_base, int chunk_stride, const Vec<T, U>& r) {
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+        *reinterpret_cast<uint4*>(row_base + u * chunk_stride) = *reinterpret_cast<const uint4*>(&r.v[u * Vec<T, U>::C]);
+}
+
+// validity accumulator: nf stays +-0 while every checked value is finite and turns NaN
+// forever once one is not (v * 0 is NaN for Inf and NaN)  — is_valid, ValueInterface.jl:5-9
+template <typename T, int U>
+__device__ __forceinline__ void check(T (&nf)[2], const Vec<T, U>& r) {
+#pragma unroll
+    for (int k = 0; k < Vec<T, U>::K; ++k) nf[k & 1] = m_fma(r.v[k], T(0), nf[k & 1]);
+}
+
+template <typename T, int U, bool FAST, bool PARAM, bool LOSS>
+__global__ void __launch_bounds__(256, 3) eval_kernel(const KArgs<T> a) {
+    using V = Vec<T, U>;
+    constexpr int C = V::C;
+    constexpr int K = V::K;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* rows = reinterpret_cast<T*>(smem_raw);
     const int tid = threadIdx.x;
     const int nthr = blockDim.x;
-    const int TILE = nthr * K;
+    const int TILE = nthr * K;          // samples per CTA = row stride in elements
+    const int CS = nthr * C;            // chunk stride in elements
     const int64_t s0 = (int64_t)blockIdx.x * TILE;
 
     // ---- stage the X slab feature-major: xs[f][s] = X[f, s0 + s] -------------------
+    // a.X is the feature-major, tile-padded copy XT[f][Npad] written by transpose_pad_kernel
+    // (tail columns replay the last valid sample), so every feature row of this tile is one
+    // contiguous, 16-byte aligned run of TILE elements: one elected thread issues F bulk
+    // async copies (TMA, cp.async.bulk -> SASS UBLKCP) that complete on an mbarrier.
+    __shared__ __align__(8) unsigned long long stage_bar;
     {
         T* xs = rows + (size_t)a.max_stack * TILE;
-        const int F = a.F;
-        const int total = F * TILE;
-        int s = tid / F, f = tid - s * F;
-        const int ds = nthr / F, df = nthr - ds * F;
-        for (int idx = tid; idx < total; idx += nthr) {
-            int64_t gs = s0 + s;
-            if (gs >= a.N) gs = a.N - 1;  // tail lanes replay the last valid sample
-            xs[(size_t)f * TILE + s] = __ldg(a.X + gs * a.ldx + f);
-            s += ds;
-            f += df;
-            if (f >= F) { f -= F; ++s; }
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&stage_bar);
+        const uint32_t row_bytes = (uint32_t)TILE * (uint32_t)sizeof(T);
+        if (tid == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar),
+                         "r"(row_bytes * (uint32_t)a.F)
+                         : "memory");
+            for (int f = 0; f < a.F; ++f) {
+                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(xs + (size_t)f * TILE);
+                const T* src = a.X + (size_t)f * a.ldx + s0;
+                asm volatile(
+                    "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                    "l"(src), "r"(row_bytes), "r"(bar)
+                    : "memory");
+            }
+        }
+        __syncthreads();  // the barrier is initialised before anybody polls it
+        if (a.F > 0) {
+            uint32_t done = 0;
+            while (!done) {
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\t"
+                    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+                    "selp.u32 %0, 1, 0, p;\n\t}"
+                    : "=r"(done)
+                    : "r"(bar)
+                    : "memory");
+            }
         }
     }
-    int cls[K];
+    // sample index of element k of this thread: (k / C) * CS + tid * C + k % C
+    int cls[PARAM ? K : 1];
     if (PARAM) {
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            int64_t gs = s0 + (int64_t)tid * K + k;
+            int64_t gs = s0 + (k / C) * CS + tid * C + (k % C);
             if (gs >= a.N) gs = a.N - 1;
             cls[k] = __ldg(a.classes + gs) * a.n_params;
         }
     }
-    T yv[K], wv[K];
+    T yv[LOSS ? K : 1], wv[LOSS ? K : 1];
     if (LOSS) {
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            int64_t gs = s0 + (int64_t)tid * K + k;
+            int64_t gs = s0 + (k / C) * CS + tid * C + (k % C);
             const bool in = gs < a.N;
             if (!in) gs = a.N - 1;
             yv[k] = __ldg(a.y + gs);
@@ -108,10 +181,10 @@ __global__ void __launch_bounds__(256) eval_kernel(const KArgs<T> a) {
     }
     __syncthreads();
 
-    T* my = rows + tid * K;  // this thread's 16-byte column inside every row
+    T* my = rows + tid * C;  // this thread's first chunk inside row 0
     const int t0 = a.chunk_start[blockIdx.y], t1 = a.chunk_start[blockIdx.y + 1];
-    const bool early = a.early_exit != 0;
-    const bool full_tile = (s0 + TILE <= a.N) && ((a.ldo % K) == 0) &&
+    const bool early = FAST ? true : (a.early_exit != 0);
+    const bool full_tile = (s0 + TILE <= a.N) && ((a.ldo % C) == 0) &&
                            ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0);
 
     for (int t = t0; t < t1; ++t) {
@@ -119,119 +192,193 @@ __global__ void __launch_bounds__(256) eval_kernel(const KArgs<T> a) {
         const int n = (int)(a.tape_off[t + 1] - off);
         const uint4* ip = a.tape + off;
         const T* ptree = PARAM ? a.params + (size_t)t * a.n_params * a.n_classes : nullptr;
-        T acc[K], nf[K];
+        V acc;
+        T nf[2] = {T(0), T(0)};
 #pragma unroll
-        for (int k = 0; k < K; ++k) { acc[k] = T(0); nf[k] = T(0); }
+        for (int k = 0; k < K; ++k) acc.v[k] = T(0);
 
         uint4 ins = __ldg(ip);
         for (int pc = 0; pc < n; ++pc) {
             uint4 nxt = ins;
             if (pc + 1 < n) nxt = __ldg(ip + pc + 1);  // prefetch the next instruction
             const uint32_t w0 = ins.x;
-            if (w0 & F_PUSH) st_row<T, K>(my + (size_t)(w0 >> 24) * TILE, acc);
+            const T* ra = my + (size_t)(ins.y & 0xfffu) * TILE;
+            const T* rb = my + (size_t)((ins.y >> 12) & 0xfffu) * TILE;
             const T c = const_of<T>(ins);
-            T va[K], vb[K], r[K];
-            // operand A
-            {
-                const uint32_t src = (w0 >> 8) & 3u, row = ins.y & 0xffffu;
-                if (src == SRC_ROW) ld_row<T, K>(va, my + (size_t)row * TILE);
-                else if (src == SRC_CONST) {
+            if (w0 & F_PUSH) st_row<T, U>(my + (size_t)(ins.y >> 24) * TILE, CS, acc);
+
+            const uint32_t h = FAST ? (w0 & 0xffu) : (uint32_t)H_GENERIC;
+            switch (h) {
+                // ---- specialised handlers: one indirect branch, no operand decoding ----
+                case H_LOAD_R: {
+                    ld_row<T, U>(acc, ra, CS);
+                    if (w0 & F_CHK_A) check<T, U>(nf, acc);
+                } break;
+                case H_LOAD_C: {
 #pragma unroll
-                    for (int k = 0; k < K; ++k) va[k] = c;
-                } else if (PARAM && src == SRC_PARAM) {
-#pragma unroll
-                    for (int k = 0; k < K; ++k) va[k] = __ldg(ptree + cls[k] + row);
-                } else {
-#pragma unroll
-                    for (int k = 0; k < K; ++k) va[k] = acc[k];
-                }
-            }
-            // operand B
-            {
-                const uint32_t src = (w0 >> 10) & 3u, row = ins.y >> 16;
-                if (src == SRC_ROW) ld_row<T, K>(vb, my + (size_t)row * TILE);
-                else if (src == SRC_CONST) {
-#pragma unroll
-                    for (int k = 0; k < K; ++k) vb[k] = c;
-                } else if (PARAM && src == SRC_PARAM) {
-#pragma unroll
-                    for (int k = 0; k < K; ++k) vb[k] = __ldg(ptree + cls[k] + row);
-                } else {
-#pragma unroll
-                    for (int k = 0; k < K; ++k) vb[k] = acc[k];
-                }
-            }
-            const bool chk = early || (w0 & F_ALWAYS);
-            if (chk && (w0 & F_CHK_A)) {
-#pragma unroll
-                for (int k = 0; k < K; ++k) nf[k] = m_fma(va[k], T(0), nf[k]);
-            }
-            if (chk && (w0 & F_CHK_B)) {
-#pragma unroll
-                for (int k = 0; k < K; ++k) nf[k] = m_fma(vb[k], T(0), nf[k]);
-            }
-            switch (w0 & 0xffu) {
-#define U_CASE(SYM, VEXPR, GEXPR)                                   \
-    case DEX_OP_##SYM: {                                            \
-        _Pragma("unroll") for (int k = 0; k < K; ++k) {             \
-            const T x = va[k];                                      \
-            r[k] = (VEXPR);                                         \
-        }                                                           \
+                    for (int k = 0; k < K; ++k) acc.v[k] = c;
+                    if (w0 & F_CHK_CONST) nf[0] = m_fma(c, T(0), nf[0]);
+                } break;
+#define UNARY_HANDLERS(S)                                                          \
+    case H_##S##_A: {                                                              \
+        _Pragma("unroll") for (int k = 0; k < K; ++k) acc.v[k] = Op1<DEX_OP_##S, T>::f(acc.v[k]); \
+    } break;                                                                       \
+    case H_##S##_R: {                                                              \
+        V x;                                                                       \
+        ld_row<T, U>(x, ra, CS);                                                   \
+        if (w0 & F_CHK_A) check<T, U>(nf, x);                                      \
+        _Pragma("unroll") for (int k = 0; k < K; ++k) acc.v[k] = Op1<DEX_OP_##S, T>::f(x.v[k]); \
     } break;
-                DEX_UNARY_OPS(U_CASE)
-#undef U_CASE
-#define B_CASE(SYM, VEXPR, G0, G1)                                  \
-    case DEX_OP_##SYM: {                                            \
-        _Pragma("unroll") for (int k = 0; k < K; ++k) {             \
-            const T x = va[k], y = vb[k];                           \
-            r[k] = (VEXPR);                                         \
-        }                                                           \
+                DEX_FAST_UNARY(UNARY_HANDLERS)
+#undef UNARY_HANDLERS
+#define BIN_AR(S)                                                                  \
+    case H_##S##_AR: {                                                             \
+        V y;                                                                       \
+        ld_row<T, U>(y, rb, CS);                                                   \
+        _Pragma("unroll") for (int k = 0; k < K; ++k) acc.v[k] = Op2<DEX_OP_##S, T>::f(acc.v[k], y.v[k]); \
     } break;
-                DEX_BINARY_OPS(B_CASE)
-#undef B_CASE
-#define T_CASE(SYM, VEXPR, G0, G1, G2)                              \
-    case DEX_OP_##SYM: {                                            \
-        _Pragma("unroll") for (int k = 0; k < K; ++k) {             \
-            const T x = va[k], y = vb[k], z = acc[k];               \
-            r[k] = (VEXPR);                                         \
-        }                                                           \
+#define BIN_RA(S)                                                                  \
+    case H_##S##_RA: {                                                             \
+        V x;                                                                       \
+        ld_row<T, U>(x, ra, CS);                                                   \
+        _Pragma("unroll") for (int k = 0; k < K; ++k) acc.v[k] = Op2<DEX_OP_##S, T>::f(x.v[k], acc.v[k]); \
     } break;
-                DEX_TERNARY_OPS(T_CASE)
-#undef T_CASE
+#define BIN_AC(S)                                                                  \
+    case H_##S##_AC: {                                                             \
+        if (w0 & F_CHK_CONST) nf[0] = m_fma(c, T(0), nf[0]);                       \
+        _Pragma("unroll") for (int k = 0; k < K; ++k) acc.v[k] = Op2<DEX_OP_##S, T>::f(acc.v[k], c); \
+    } break;
+#define BIN_CA(S)                                                                  \
+    case H_##S##_CA: {                                                             \
+        if (w0 & F_CHK_CONST) nf[0] = m_fma(c, T(0), nf[0]);                       \
+        _Pragma("unroll") for (int k = 0; k < K; ++k) acc.v[k] = Op2<DEX_OP_##S, T>::f(c, acc.v[k]); \
+    } break;
+#define BIN_RR(S)                                                                  \
+    case H_##S##_RR: {                                                             \
+        V x, y;                                                                    \
+        ld_row<T, U>(x, ra, CS);                                                   \
+        ld_row<T, U>(y, rb, CS);                                                   \
+        _Pragma("unroll") for (int k = 0; k < K; ++k) acc.v[k] = Op2<DEX_OP_##S, T>::f(x.v[k], y.v[k]); \
+    } break;
+#define BIN_RC(S)                                                                  \
+    case H_##S##_RC: {                                                             \
+        V x;                                                                       \
+        ld_row<T, U>(x, ra, CS);                                                   \
+        if (w0 & F_CHK_CONST) nf[0] = m_fma(c, T(0), nf[0]);                       \
+        _Pragma("unroll") for (int k = 0; k < K; ++k) acc.v[k] = Op2<DEX_OP_##S, T>::f(x.v[k], c); \
+    } break;
+#define BIN_CR(S)                                                                  \
+    case H_##S##_CR: {                                                             \
+        V y;                                                                       \
+        ld_row<T, U>(y, rb, CS);                                                   \
+        if (w0 & F_CHK_CONST) nf[0] = m_fma(c, T(0), nf[0]);                       \
+        _Pragma("unroll") for (int k = 0; k < K; ++k) acc.v[k] = Op2<DEX_OP_##S, T>::f(c, y.v[k]); \
+    } break;
+#define COMM_HANDLERS(S) BIN_AR(S) BIN_AC(S) BIN_RR(S) BIN_RC(S)
+#define NC_HANDLERS(S) BIN_AR(S) BIN_RA(S) BIN_AC(S) BIN_CA(S) BIN_RR(S) BIN_RC(S) BIN_CR(S)
+                DEX_FAST_BIN_COMM(COMM_HANDLERS)
+                DEX_FAST_BIN_NC(NC_HANDLERS)
+#undef COMM_HANDLERS
+#undef NC_HANDLERS
+#undef BIN_AR
+#undef BIN_RA
+#undef BIN_AC
+#undef BIN_CA
+#undef BIN_RR
+#undef BIN_RC
+#undef BIN_CR
+                // ---- generic handler: any operator, any operand source, every flag --------
                 default: {
+                    V va, vb;
+                    {
+                        const uint32_t src = (w0 >> 16) & 3u;
+                        if (src == SRC_ROW) ld_row<T, U>(va, ra, CS);
+                        else if (src == SRC_CONST) {
 #pragma unroll
-                    for (int k = 0; k < K; ++k) r[k] = t_nan<T>();
+                            for (int k = 0; k < K; ++k) va.v[k] = c;
+                        } else if (PARAM && src == SRC_PARAM) {
+#pragma unroll
+                            for (int k = 0; k < K; ++k) va.v[k] = __ldg(ptree + cls[k] + (ins.y & 0xfffu));
+                        } else va = acc;
+                    }
+                    {
+                        const uint32_t src = (w0 >> 18) & 3u;
+                        if (src == SRC_ROW) ld_row<T, U>(vb, rb, CS);
+                        else if (src == SRC_CONST) {
+#pragma unroll
+                            for (int k = 0; k < K; ++k) vb.v[k] = c;
+                        } else if (PARAM && src == SRC_PARAM) {
+#pragma unroll
+                            for (int k = 0; k < K; ++k) vb.v[k] = __ldg(ptree + cls[k] + ((ins.y >> 12) & 0xfffu));
+                        } else vb = acc;
+                    }
+                    const bool chk = early || (w0 & F_ALWAYS);
+                    if (chk && (w0 & F_CHK_A)) check<T, U>(nf, va);
+                    if (chk && (w0 & F_CHK_B)) check<T, U>(nf, vb);
+                    // FAST kernels keep this rarely taken path small (one rolled loop over the K
+                    // samples, operands in local memory) so the hot handlers stay in the
+                    // instruction cache; the early_exit-off kernel runs every instruction here
+                    // and gets the fully unrolled, register-resident form.
+                    V r;
+                    {
+                        T la[K], lb[K], lz[K], lr[K];
+#pragma unroll
+                        for (int k = 0; k < K; ++k) { la[k] = va.v[k]; lb[k] = vb.v[k]; lz[k] = acc.v[k]; }
+                        const uint32_t opc = (w0 >> 8) & 0xffu;
+                        const bool guard = !FAST && (w0 & F_GUARD);
+#pragma unroll(FAST ? 1 : K)
+                        for (int k = 0; k < K; ++k) {
+                            const T x = la[k], y = lb[k], z = lz[k];
+                            T v;
+                            switch (opc) {
+#define U_CASE(SYM, VEXPR, GEXPR) case DEX_OP_##SYM: v = (VEXPR); break;
+                                DEX_UNARY_OPS(U_CASE)
+#undef U_CASE
+#define B_CASE(SYM, VEXPR, G0, G1) case DEX_OP_##SYM: v = (VEXPR); break;
+                                DEX_BINARY_OPS(B_CASE)
+#undef B_CASE
+#define T_CASE(SYM, VEXPR, G0, G1, G2) case DEX_OP_##SYM: v = (VEXPR); break;
+                                DEX_TERNARY_OPS(T_CASE)
+#undef T_CASE
+                                default: v = t_nan<T>(); break;
+                            }
+                            // the reference's fused unary kernels substitute Inf where the inner
+                            // value is invalid; only observable when early_exit is off
+                            if (guard && !t_finite(x)) v = t_inf<T>();
+                            lr[k] = v;
+                            (void)y; (void)z;
+                        }
+#pragma unroll
+                        for (int k = 0; k < K; ++k) r.v[k] = lr[k];
+                    }
+                    acc = r;
+                    if (!chk) goto next_instruction;  // CHK_OUT below is unconditional for FAST
                 } break;
             }
-            if (w0 & F_GUARD) {
-#pragma unroll
-                for (int k = 0; k < K; ++k)
-                    if (!t_finite(va[k])) r[k] = t_inf<T>();
-            }
-#pragma unroll
-            for (int k = 0; k < K; ++k) acc[k] = r[k];
-            if (chk && (w0 & F_CHK_OUT)) {
-#pragma unroll
-                for (int k = 0; k < K; ++k) nf[k] = m_fma(r[k], T(0), nf[k]);
-            }
+            if (w0 & F_CHK_OUT) check<T, U>(nf, acc);
+        next_instruction:
             ins = nxt;
         }
 
         // ---- result row segment ----------------------------------------------------
         if (!LOSS) {
-            T* o = a.out + (size_t)t * a.ldo + s0 + (size_t)tid * K;
+            T* o = a.out + (size_t)t * a.ldo + s0 + (size_t)tid * C;
             if (full_tile) {
-                __stcs(reinterpret_cast<float4*>(o), *reinterpret_cast<const float4*>(acc));
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    __stcs(reinterpret_cast<float4*>(o + u * CS), *reinterpret_cast<const float4*>(&acc.v[u * C]));
             } else {
 #pragma unroll
-                for (int k = 0; k < K; ++k)
-                    if (s0 + (int64_t)tid * K + k < a.N) o[k] = acc[k];
+                for (int k = 0; k < K; ++k) {
+                    const int64_t s = (k / C) * CS + tid * C + (k % C);
+                    if (s0 + s < a.N) a.out[(size_t)t * a.ldo + s0 + s] = acc.v[k];
+                }
             }
         } else {
             double ls = 0.0;
 #pragma unroll
             for (int k = 0; k < K; ++k) {
-                const double d = (double)acc[k] - (double)yv[k];
+                const double d = (double)acc.v[k] - (double)yv[k];
                 ls += (double)wv[k] * d * d;
             }
             // deterministic block reduction -> loss_partial[tile][tree]
@@ -247,16 +394,22 @@ __global__ void __launch_bounds__(256) eval_kernel(const KArgs<T> a) {
                 a.loss_partial[(size_t)blockIdx.x * a.n_trees + t] = s;
             }
         }
-        bool bad = false;
-#pragma unroll
-        for (int k = 0; k < K; ++k) bad |= (nf[k] != nf[k]);
+        const bool bad = (nf[0] != nf[0]) || (nf[1] != nf[1]);
         if (__any_sync(0xffffffffu, bad) && (tid & 31) == 0) a.ok[t] = 0;
     }
 }
 
-__global__ void fill_u8_kernel(uint8_t* p, int64_t n, uint8_t v) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) p[i] = v;
+// Pre-pass: XT[f][s] = X[f, min(s, N-1)] for s < Npad — the feature-major, tile-padded image
+// of the caller's column-major X that the interpreter stages with bulk async copies.  Also
+// presets ok[] to 1.  X is tiny next to the results (F*N vs P*N elements).
+template <typename T>
+__global__ void transpose_pad_kernel(const T* __restrict__ X, int64_t ldx, int F, int64_t N,
+                                     T* __restrict__ XT, int64_t Npad, uint8_t* ok, int64_t n_trees) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n_trees) ok[s] = 1;
+    if (s >= Npad) return;
+    const T* col = X + (s < N ? s : N - 1) * ldx;
+    for (int f = 0; f < F; ++f) XT[(size_t)f * Npad + s] = __ldg(col + f);
 }
 
 template <typename T>
@@ -283,7 +436,7 @@ __global__ void loss_reduce_kernel(const double* partial, int64_t n_tiles, int64
 
 constexpr size_t SMEM_LIMIT = 227 * 1024;
 
-template <typename T>
+template <typename T, int U>
 cudaError_t launch_typed(const EvalArgs& e, cudaStream_t stream, int threads, size_t smem,
                          int64_t n_tiles) {
     KArgs<T> a;
@@ -302,10 +455,16 @@ cudaError_t launch_typed(const EvalArgs& e, cudaStream_t stream, int threads, si
     a.F = e.F; a.max_stack = e.max_stack; a.early_exit = e.early_exit;
     a.n_params = e.n_params; a.n_classes = e.n_classes;
     dim3 grid((unsigned)n_tiles, (unsigned)e.n_chunks);
-    const bool param = e.params != nullptr, loss = e.y != nullptr;
-    void (*kern)(const KArgs<T>) =
-        loss ? (param ? eval_kernel<T, true, true> : eval_kernel<T, false, true>)
-             : (param ? eval_kernel<T, true, false> : eval_kernel<T, false, false>);
+    const bool param = e.params != nullptr, loss = e.y != nullptr, fast = e.early_exit != 0;
+    void (*kern)(const KArgs<T>);
+    if (fast) {
+        kern = loss ? (param ? eval_kernel<T, U, true, true, true> : eval_kernel<T, U, true, false, true>)
+                    : (param ? eval_kernel<T, U, true, true, false> : eval_kernel<T, U, true, false, false>);
+    } else {
+        // early_exit off: the generic path for every instruction (GUARD, ALWAYS-only checks)
+        kern = loss ? (param ? eval_kernel<T, U, false, true, true> : eval_kernel<T, U, false, false, true>)
+                    : (param ? eval_kernel<T, U, false, true, false> : eval_kernel<T, U, false, false, false>);
+    }
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
     kern<<<grid, threads, smem, stream>>>(a);
@@ -314,12 +473,27 @@ cudaError_t launch_typed(const EvalArgs& e, cudaStream_t stream, int threads, si
 
 }  // namespace
 
+// samples per thread: U chunks of 16 bytes
+constexpr int EVAL_U = DEX_EVAL_U;
+
+size_t eval_xt_bytes(int dtype, int32_t F, int32_t max_stack, int64_t N) {
+    int threads;
+    size_t smem;
+    const int64_t n_tiles = eval_num_tiles(dtype, F, max_stack, N, &threads, &smem);
+    const int64_t tile = (int64_t)threads * (dtype == DEX_F32 ? 4 : 2) * EVAL_U;
+    return (size_t)std::max<int64_t>(n_tiles * tile, 1) * (size_t)std::max(F, 1) * (dtype == DEX_F32 ? 4 : 8);
+}
+
 int64_t eval_num_tiles(int dtype, int32_t F, int32_t max_stack, int64_t N, int* threads_out,
                        size_t* smem_out) {
-    const int K = dtype == DEX_F32 ? 4 : 2;
+    const int K = (dtype == DEX_F32 ? 4 : 2) * EVAL_U;
     const size_t es = dtype == DEX_F32 ? 4 : 8;
     const size_t rows = (size_t)F + (size_t)max_stack;
     int threads = 256;
+    if (const char* env = getenv("DEXB200_THREADS")) {   // tuning knob for experiments
+        const int v = atoi(env);
+        if (v == 32 || v == 64 || v == 128 || v == 256) threads = v;
+    }
     // keep >= 2 CTAs resident per SM when possible; shrink the block if the rows do not fit
     while (threads > 32 && rows * (size_t)threads * K * es > SMEM_LIMIT / 2) threads >>= 1;
     if (N < (int64_t)threads * K) {  // tiny inputs: do not stage more columns than exist
@@ -340,12 +514,23 @@ cudaError_t launch_eval(const EvalArgs& e, cudaStream_t stream, int sm_count, in
     const int64_t n_tiles = eval_num_tiles(e.dtype, e.F, e.max_stack, e.N, &threads, &smem);
     if (smem > SMEM_LIMIT) return cudaErrorInvalidConfiguration;
     if (e.n_trees == 0 || e.N == 0) return cudaSuccess;
-    fill_u8_kernel<<<(unsigned)((e.n_trees + 255) / 256), 256, 0, stream>>>(e.ok, e.n_trees, 1);
+    const int64_t tile = (int64_t)threads * (e.dtype == DEX_F32 ? 4 : 2) * EVAL_U;
+    const int64_t Npad = n_tiles * tile;
+    const int64_t cover = std::max<int64_t>(Npad, e.n_trees);
+    if (e.dtype == DEX_F32)
+        transpose_pad_kernel<float><<<(unsigned)((cover + 255) / 256), 256, 0, stream>>>(
+            static_cast<const float*>(e.X), e.ldx, e.F, e.N, static_cast<float*>(e.xt), Npad, e.ok, e.n_trees);
+    else
+        transpose_pad_kernel<double><<<(unsigned)((cover + 255) / 256), 256, 0, stream>>>(
+            static_cast<const double*>(e.X), e.ldx, e.F, e.N, static_cast<double*>(e.xt), Npad, e.ok, e.n_trees);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return err;
     if (launches) *launches += 1;
-    err = e.dtype == DEX_F32 ? launch_typed<float>(e, stream, threads, smem, n_tiles)
-                             : launch_typed<double>(e, stream, threads, smem, n_tiles);
+    EvalArgs k = e;   // the interpreter reads the staged copy
+    k.X = e.xt;
+    k.ldx = Npad;
+    err = e.dtype == DEX_F32 ? launch_typed<float, EVAL_U>(k, stream, threads, smem, n_tiles)
+                             : launch_typed<double, EVAL_U>(k, stream, threads, smem, n_tiles);
     if (err == cudaSuccess && launches) *launches += 1;
     return err;
 }

@@ -111,6 +111,15 @@ struct Flattener {
         int32_t cord = -1;
         bool chk = false;
     };
+    // one instruction before lowering
+    struct EIns {
+        int op;
+        Opnd a, b;
+        uint32_t flags;   // F_CHK_OUT | F_ALWAYS | F_GUARD
+        int push_slot;
+    };
+    std::vector<EIns> cur;  // instructions of the tree being flattened
+    int last = -1;          // index in `cur` of the instruction that produced the latest value
 
     // `feature_checked`: whether the reference kernel that consumes this leaf checks it
     Opnd leaf_operand(int64_t i, bool feature_checked, bool const_mode) const {
@@ -154,25 +163,56 @@ struct Flattener {
         }
     }
 
-    // Emits one instruction.  Feature rows are stored as feature index here and are
-    // rebased to absolute rows (max_stack + f) once the population's max_stack is known.
-    void emit(int op, const Opnd& a, const Opnd& b, uint32_t flags, int push_slot) {
-        Instr ins{};
-        ins.w0 = (uint32_t)op | (a.src << 8) | (b.src << 10) | flags;
-        if (a.chk) ins.w0 |= F_CHK_A;
-        if (b.chk) ins.w0 |= F_CHK_B;
-        if (push_slot >= 0) {
-            ins.w0 |= F_PUSH | ((uint32_t)push_slot << 24);
-            max_slot = std::max(max_slot, push_slot + 1);
+    // ---- check elision ------------------------------------------------------------------
+    // transparent(op, k): a non-finite k-th operand ALWAYS yields a non-finite result
+    // (per sample).  A value consumed through a transparent operand position of a checked
+    // instruction does not need a check of its own: its non-finiteness reaches the
+    // consumer's check (by induction, ultimately the root's).  The `complete` flag is
+    // unchanged; only redundant work is removed.
+    static bool transparent(int op, int k) {
+        switch (op) {
+            case DEX_OP_NEG: case DEX_OP_ABS: case DEX_OP_ABS2: case DEX_OP_SQUARE: case DEX_OP_CUBE:
+            case DEX_OP_SQRT: case DEX_OP_CBRT: case DEX_OP_LOG: case DEX_OP_LOG2: case DEX_OP_LOG10:
+            case DEX_OP_LOG1P: case DEX_OP_SIN: case DEX_OP_COS: case DEX_OP_TAN: case DEX_OP_ASIN:
+            case DEX_OP_ACOS: case DEX_OP_SINH: case DEX_OP_COSH: case DEX_OP_ASINH: case DEX_OP_ACOSH:
+            case DEX_OP_ATANH: case DEX_OP_ROUND: case DEX_OP_FLOOR: case DEX_OP_CEIL: case DEX_OP_TRUNC:
+            case DEX_OP_IDENTITY: case DEX_OP_SAFE_LOG: case DEX_OP_SAFE_LOG2: case DEX_OP_SAFE_LOG10:
+            case DEX_OP_SAFE_LOG1P: case DEX_OP_SAFE_SQRT: case DEX_OP_SAFE_ACOSH: case DEX_OP_COS2:
+                return true;
+            case DEX_OP_ADD: case DEX_OP_SUB: case DEX_OP_MUL: return true;   // Inf-Inf, Inf*0 -> NaN
+            case DEX_OP_DIV: return k == 0;                                   // x/Inf = 0 hides the denominator
+            case DEX_OP_MOD: return k == 0;
+            case DEX_OP_COPYSIGN: return k == 0;
+            case DEX_OP_FMA: case DEX_OP_MULADD: case DEX_OP_ADD3: case DEX_OP_MUL3: return true;
+            default: return false;  // exp(-Inf)=0, 1/Inf=0, max(-Inf,1)=1, Inf^0=1, tanh, atan, ...
         }
-        // bit 15 of each row field marks "feature row, rebase later"
-        uint32_t ra = a.row | (a.is_feature ? 0x8000u : 0u);
-        uint32_t rb = b.row | (b.is_feature ? 0x8000u : 0u);
-        ins.w1 = ra | (rb << 16);
-        int64_t idx = (int64_t)out.tape.size();
-        if (a.src == SRC_CONST) { put_const(ins, a.c); if (a.cord >= 0) out.const_pos[const_base + a.cord] = idx; }
-        if (b.src == SRC_CONST) { put_const(ins, b.c); if (b.cord >= 0) out.const_pos[const_base + b.cord] = idx; }
-        out.tape.push_back(ins);
+    }
+    // the value produced by cur[child] is consumed as operand k of cur[parent]
+    void elide_result(int child, int parent, int k) {
+        if (child < 0 || !elide) return;
+        EIns& c = cur[(size_t)child];
+        const EIns& p = cur[(size_t)parent];
+        if (!(p.flags & F_CHK_OUT)) return;
+        if ((c.flags & F_ALWAYS) && !(p.flags & F_ALWAYS)) return;  // root of a constant subtree
+        if (!transparent(p.op, k)) return;
+        if (c.op == DEX_OP_IDENTITY && c.b.src == SRC_ACC && c.a.src != SRC_ACC && !(c.flags & F_CHK_OUT))
+            c.a.chk = false;  // a LOAD: the check sits on its operand
+        c.flags &= ~F_CHK_OUT;
+    }
+    void elide_operand(Opnd& o, int op, int k, uint32_t pflags) const {
+        if (elide && o.src != SRC_ACC && (pflags & F_CHK_OUT) && transparent(op, k)) o.chk = false;
+    }
+
+    // Emits one instruction into `cur`; returns its index.
+    int emit(int op, Opnd a, Opnd b, uint32_t flags, int push_slot) {
+        int deg = op >= 128 ? 3 : (op >= 64 ? 2 : 1);
+        elide_operand(a, op, 0, flags);
+        if (deg >= 2) elide_operand(b, op, 1, flags);
+        EIns e{op, a, b, flags, push_slot};
+        if (push_slot >= 0) max_slot = std::max(max_slot, push_slot + 1);
+        cur.push_back(e);
+        last = (int)cur.size() - 1;
+        return last;
     }
 
     uint32_t out_flags(bool const_mode, bool guard) const {
@@ -183,12 +223,17 @@ struct Flattener {
     }
 
     // Materialise a leaf into ACC (LOAD = IDENTITY with the leaf as operand A).
-    void emit_load(int64_t i, bool feature_checked, bool const_mode, int push_slot) {
+    int emit_load(int64_t i, bool feature_checked, bool const_mode, int push_slot) {
         Opnd a = leaf_operand(i, feature_checked, const_mode);
-        emit(DEX_OP_IDENTITY, a, acc(), const_mode ? F_ALWAYS : 0u, push_slot);
+        const bool keep = elide;
+        elide = false;  // the check of a LOAD lives on its operand
+        int idx = emit(DEX_OP_IDENTITY, a, acc(), const_mode ? F_ALWAYS : 0u, push_slot);
+        elide = keep;
+        return idx;
     }
 
-    // Emit code leaving the value of operator node i in ACC.
+    // Emit code leaving the value of operator node i in ACC (and its producing instruction
+    // index in `last`).
     //   push_slot  >= 0: ACC holds a live value that must be saved to that slot by the
     //              first instruction emitted here
     //   depth      first free stack slot (after the pending push)
@@ -224,7 +269,9 @@ struct Flattener {
                 else if (ch.degree == 1 && leaf(c + 1)) { guard = true; inner_unchecked = true; }                              // :633-640
             }
             if ((rc = gen(c, push_slot, depth, const_mode, inner_unchecked, rec + 1))) return rc;
-            emit(op, acc(), acc(), out_flags(const_mode, guard), -1);
+            const int ci = last;
+            const int p = emit(op, acc(), acc(), out_flags(const_mode, guard), -1);
+            elide_result(ci, p, 0);
             return DEX_OK;
         }
         if (x.degree == 2) {
@@ -235,8 +282,9 @@ struct Flattener {
                 bool chk = !(fused2 || unchecked_leaves);
                 Opnd a = leaf_operand(l, chk, const_mode), b = leaf_operand(r, chk, const_mode);
                 if (a.src == SRC_CONST && b.src == SRC_CONST) {
-                    emit(DEX_OP_IDENTITY, a, acc(), const_mode ? F_ALWAYS : 0u, push_slot);
-                    emit(op, acc(), b, out_flags(const_mode, false), -1);
+                    const int li = emit_load(l, chk, const_mode, push_slot);
+                    const int p = emit(op, acc(), b, out_flags(const_mode, false), -1);
+                    elide_result(li, p, 0);
                 } else {
                     emit(op, a, b, out_flags(const_mode, false), push_slot);
                 }
@@ -248,7 +296,9 @@ struct Flattener {
                 bool branch0 = fused2 && L.degree == 2 && leaf(child(l, 0)) && leaf(child(l, 1));
                 if (branch0) chk = true;  // branch0 :left, x3 checked (:799)
                 if ((rc = gen(l, push_slot, depth, const_mode, false, rec + 1, !branch0))) return rc;
-                emit(op, acc(), leaf_operand(r, chk, const_mode), out_flags(const_mode, false), -1);
+                const int ci = last;
+                const int p = emit(op, acc(), leaf_operand(r, chk, const_mode), out_flags(const_mode, false), -1);
+                elide_result(ci, p, 0);
                 return DEX_OK;
             }
             if (ll) {  // op(leaf, branch)
@@ -257,16 +307,23 @@ struct Flattener {
                 bool branch0 = fused2 && R.degree == 2 && leaf(child(r, 0)) && leaf(child(r, 1));
                 if (branch0) chk = true;  // branch0 :right, x1 checked (:810)
                 if ((rc = gen(r, push_slot, depth, const_mode, false, rec + 1, !branch0))) return rc;
-                emit(op, leaf_operand(l, chk, const_mode), acc(), out_flags(const_mode, false), -1);
+                const int ci = last;
+                const int p = emit(op, leaf_operand(l, chk, const_mode), acc(), out_flags(const_mode, false), -1);
+                elide_result(ci, p, 1);
                 return DEX_OK;
             }
             // both children are operators: evaluate the one needing more stack first
             bool left_first = need[l] >= need[r];
             int64_t first = left_first ? l : r, second = left_first ? r : l;
             if ((rc = gen(first, push_slot, depth, const_mode, false, rec + 1))) return rc;
+            const int fi = last;
             if ((rc = gen(second, depth, depth + 1, const_mode, false, rec + 1))) return rc;
-            if (left_first) emit(op, slot(depth), acc(), out_flags(const_mode, false), -1);
-            else emit(op, acc(), slot(depth), out_flags(const_mode, false), -1);
+            const int si = last;
+            int p;
+            if (left_first) p = emit(op, slot(depth), acc(), out_flags(const_mode, false), -1);
+            else p = emit(op, acc(), slot(depth), out_flags(const_mode, false), -1);
+            elide_result(fi, p, left_first ? 0 : 1);
+            elide_result(si, p, left_first ? 1 : 0);
             return DEX_OK;
         }
         // degree 3 (dispatch_degn_eval :428-467): every child goes through
@@ -274,36 +331,145 @@ struct Flattener {
         // leaf or a stack slot; C is always ACC.
         int64_t c[3] = {child(i, 0), child(i, 1), child(i, 2)};
         Opnd o[2];
-        bool have[2] = {false, false};
-        int pending = push_slot;   // push to attach to the next ACC-overwriting instruction
-        int acc_holds = -1;        // which of c[0], c[1] currently lives in ACC
+        int prod[3] = {-1, -1, -1};  // producing instruction of each child (when not a direct leaf)
+        int pending = push_slot;     // push to attach to the next ACC-overwriting instruction
+        int acc_holds = -1;          // which of c[0], c[1] currently lives in ACC
         int d = depth;
         bool const_ab = leaf(c[0]) && leaf(c[1]) && nd[c[0]].kind == DEX_LEAF_CONST && nd[c[1]].kind == DEX_LEAF_CONST;
         for (int k = 0; k < 3; ++k) {
             bool direct = k < 2 && leaf(c[k]) && !(k == 0 && const_ab);
             if (direct) {
                 o[k] = leaf_operand(c[k], true, const_mode);
-                have[k] = true;
                 continue;
             }
             int ps = pending;
             if (acc_holds >= 0) {  // save the earlier operand into slot d
                 ps = d;
                 o[acc_holds] = slot(d);
-                have[acc_holds] = true;
                 ++d;
                 if (d >= MAX_STACK_ROWS) return fail(DEX_ERR_UNSUPPORTED, "operand stack too deep");
             }
-            if (leaf(c[k])) emit_load(c[k], true, const_mode, ps);
-            else if ((rc = gen(c[k], ps, d, const_mode, false, rec + 1))) return rc;
+            if (leaf(c[k])) prod[k] = emit_load(c[k], true, const_mode, ps);
+            else {
+                if ((rc = gen(c[k], ps, d, const_mode, false, rec + 1))) return rc;
+                prod[k] = last;
+            }
             pending = -1;
             acc_holds = k < 2 ? k : -1;
         }
-        (void)have;
         // encode: A = o[0], B = o[1], C = ACC
-        emit(op, o[0], o[1], out_flags(const_mode, false), -1);
+        const int p = emit(op, o[0], o[1], out_flags(const_mode, false), -1);
+        for (int k = 0; k < 3; ++k) elide_result(prod[k], p, k);
         return DEX_OK;
     }
+
+    // ---- lowering: EIns -> device encoding -------------------------------------------------
+    static uint32_t pick_handler(const EIns& e, bool a_chk_row, bool b_chk_row) {
+        const uint32_t sa = e.a.src, sb = e.b.src;
+        if (sa == SRC_PARAM || sb == SRC_PARAM) return H_GENERIC;
+        const int deg = e.op >= 128 ? 3 : (e.op >= 64 ? 2 : 1);
+        if (deg == 1) {
+            if (e.op == DEX_OP_IDENTITY) {
+                if (sa == SRC_ROW) return H_LOAD_R;
+                if (sa == SRC_CONST) return H_LOAD_C;
+                return H_GENERIC;
+            }
+            if (sa == SRC_CONST) return H_GENERIC;
+            switch (e.op) {
+#define X(S) case DEX_OP_##S: return sa == SRC_ACC ? H_##S##_A : H_##S##_R;
+                DEX_FAST_UNARY(X)
+#undef X
+                default: return H_GENERIC;
+            }
+        }
+        if (deg == 2) {
+            if (a_chk_row || b_chk_row) return H_GENERIC;  // checked feature operand of a binary op: rare
+            switch (e.op) {
+#define X(S)                                                              \
+    case DEX_OP_##S:                                                      \
+        if (sa == SRC_ACC && sb == SRC_ROW) return H_##S##_AR;            \
+        if (sa == SRC_ACC && sb == SRC_CONST) return H_##S##_AC;          \
+        if (sa == SRC_ROW && sb == SRC_ROW) return H_##S##_RR;            \
+        if (sa == SRC_ROW && sb == SRC_CONST) return H_##S##_RC;          \
+        return H_GENERIC;
+                DEX_FAST_BIN_COMM(X)
+#undef X
+#define X(S)                                                              \
+    case DEX_OP_##S:                                                      \
+        if (sa == SRC_ACC && sb == SRC_ROW) return H_##S##_AR;            \
+        if (sa == SRC_ROW && sb == SRC_ACC) return H_##S##_RA;            \
+        if (sa == SRC_ACC && sb == SRC_CONST) return H_##S##_AC;          \
+        if (sa == SRC_CONST && sb == SRC_ACC) return H_##S##_CA;          \
+        if (sa == SRC_ROW && sb == SRC_ROW) return H_##S##_RR;            \
+        if (sa == SRC_ROW && sb == SRC_CONST) return H_##S##_RC;          \
+        if (sa == SRC_CONST && sb == SRC_ROW) return H_##S##_CR;          \
+        return H_GENERIC;
+                DEX_FAST_BIN_NC(X)
+#undef X
+                default: return H_GENERIC;
+            }
+        }
+        return H_GENERIC;
+    }
+    static bool commutative(int op) {
+        return op == DEX_OP_ADD || op == DEX_OP_MUL || op == DEX_OP_MAX || op == DEX_OP_MIN;
+    }
+
+    static bool fast_unary(int op) {
+        switch (op) {
+#define X(S) case DEX_OP_##S: return true;
+            DEX_FAST_UNARY(X)
+#undef X
+            default: return false;
+        }
+    }
+
+    void lower_tree() {
+        // unary operator on an inline constant (only inside constant subtrees): split into
+        // LOAD_C + OP_A so that both halves take specialised handlers
+        std::vector<EIns> split;
+        split.reserve(cur.size());
+        for (const EIns& e : cur) {
+            if (e.op < 64 && e.op != DEX_OP_IDENTITY && e.a.src == SRC_CONST && fast_unary(e.op)) {
+                EIns ld{DEX_OP_IDENTITY, e.a, acc(), e.flags & F_ALWAYS, e.push_slot};
+                EIns op{e.op, acc(), acc(), e.flags, -1};
+                split.push_back(ld);
+                split.push_back(op);
+            } else {
+                split.push_back(e);
+            }
+        }
+        for (EIns e : split) {
+            // commutative operators: bring the operands into (ACC|ROW, ROW|CONST) order
+            if (commutative(e.op)) {
+                auto rank = [](const Opnd& o) { return o.src == SRC_ACC ? 0 : o.src == SRC_ROW ? 1 : o.src == SRC_PARAM ? 1 : 2; };
+                if (rank(e.a) > rank(e.b)) std::swap(e.a, e.b);
+            }
+            Instr ins{};
+            const bool a_chk_row = e.a.chk && e.a.src != SRC_CONST && e.a.src != SRC_ACC;
+            const bool b_chk_row = e.b.chk && e.b.src != SRC_CONST && e.b.src != SRC_ACC;
+            const uint32_t h = pick_handler(e, a_chk_row, b_chk_row);
+            ins.w0 = h | ((uint32_t)e.op << 8) | (e.a.src << 16) | (e.b.src << 18) | e.flags;
+            if (e.a.chk) ins.w0 |= F_CHK_A;
+            if (e.b.chk) ins.w0 |= F_CHK_B;
+            if ((e.a.chk && e.a.src == SRC_CONST) || (e.b.chk && e.b.src == SRC_CONST)) ins.w0 |= F_CHK_CONST;
+            uint32_t push_row = 0;
+            if (e.push_slot >= 0) { ins.w0 |= F_PUSH; push_row = (uint32_t)e.push_slot; }
+            // feature rows are rebased behind the stack rows once max_stack is known:
+            // bit 31/30 of the scratch word c_hi-independent marker is kept in `rebase`
+            uint32_t ra = e.a.row, rb = e.b.row;
+            ins.w1 = (ra & 0xfffu) | ((rb & 0xfffu) << 12) | (push_row << 24);
+            rebase.push_back((uint8_t)((e.a.is_feature ? 1 : 0) | (e.b.is_feature ? 2 : 0)));
+            const int64_t idx = (int64_t)out.tape.size();
+            if (e.a.src == SRC_CONST) { put_const(ins, e.a.c); if (e.a.cord >= 0) out.const_pos[const_base + e.a.cord] = idx; }
+            if (e.b.src == SRC_CONST) { put_const(ins, e.b.c); if (e.b.cord >= 0) out.const_pos[const_base + e.b.cord] = idx; }
+            if (h == H_GENERIC) ++out.n_generic;
+            out.n_checks += ((ins.w0 & F_CHK_OUT) ? 1 : 0) + (e.a.chk ? 1 : 0) + (e.b.chk ? 1 : 0);
+            out.tape.push_back(ins);
+        }
+    }
+    std::vector<uint8_t> rebase;  // per tape instruction: bit0 rowA is a feature, bit1 rowB is a feature
+    bool elide = true;
 
     // ---- gradient tape -----------------------------------------------------------------
     void gemit(uint32_t w0, uint32_t w1, double c) {
@@ -364,6 +530,8 @@ struct Flattener {
             out.gconst_pos.resize((size_t)(const_base + nc), -1);
             max_slot = 0;
             max_gslot = 0;
+            cur.clear();
+            last = -1;
             if (nd[0].degree == 0) {
                 // a bare leaf: deg0_eval then the final is_valid_array (:304-308); Bumper
                 // checks constants only (ext/...BumperExt.jl:29)
@@ -371,6 +539,7 @@ struct Flattener {
             } else if ((rc = gen(0, -1, 0, false, false, 0))) {
                 return rc;
             }
+            lower_tree();
             if ((rc = ggen(0, 0, 0))) return rc;
             out.max_stack = std::max(out.max_stack, max_slot);
             out.max_gstack = std::max(out.max_gstack, max_gslot);
@@ -384,11 +553,15 @@ struct Flattener {
         }
         // rebase feature rows behind the stack rows
         const uint32_t base = (uint32_t)out.max_stack;
-        for (Instr& ins : out.tape) {
-            uint32_t ra = ins.w1 & 0xffffu, rb = ins.w1 >> 16;
-            if (ra & 0x8000u) ra = (ra & 0x7fffu) + base;
-            if (rb & 0x8000u) rb = (rb & 0x7fffu) + base;
-            ins.w1 = ra | (rb << 16);
+        if (out.max_feature >= 0 && (int64_t)out.max_feature + base > MAX_ROWS)
+            return fail(DEX_ERR_UNSUPPORTED, "feature index " + std::to_string(out.max_feature) +
+                                                 " + stack rows exceed the device row limit " + std::to_string(MAX_ROWS));
+        for (size_t k = 0; k < out.tape.size(); ++k) {
+            Instr& ins = out.tape[k];
+            uint32_t ra = ins.w1 & 0xfffu, rb = (ins.w1 >> 12) & 0xfffu;
+            if (rebase[k] & 1) ra += base;
+            if (rebase[k] & 2) rb += base;
+            ins.w1 = (ins.w1 & 0xff000000u) | ra | (rb << 12);
         }
         out.n_trees = n_trees;
         return DEX_OK;
@@ -406,7 +579,6 @@ int flatten_population(const OpTable& ops, const void* nodes, const int64_t* off
     Flattener f(ops, dtype, pack_flags, out, err);
     int rc = f.run(reinterpret_cast<const dex_node*>(nodes), offsets, n_trees);
     if (rc) return rc;
-    if (out.max_feature >= 0x7fff) { err = "feature index " + std::to_string(out.max_feature) + " exceeds the device limit 32766"; return DEX_ERR_UNSUPPORTED; }
     return DEX_OK;
 }
 

@@ -17,6 +17,7 @@ struct EvalArgs {
     int32_t n_chunks;
     int32_t max_stack;          // stack rows in front of the feature rows
     const void* X;              // device, column-major F x N, leading dimension ldx
+    void* xt;                   // device scratch >= eval_xt_bytes(): feature-major padded copy of X
     int32_t F;
     int64_t N;
     int64_t ldx;
@@ -39,6 +40,7 @@ struct EvalArgs {
 
 // Chooses the block size / shared memory, presets ok[], launches.  Returns cudaError_t.
 cudaError_t launch_eval(const EvalArgs& a, cudaStream_t stream, int sm_count, int* launches);
+size_t eval_xt_bytes(int dtype, int32_t F, int32_t max_stack, int64_t N);
 // number of sample tiles launch_eval will use for (dtype, F, max_stack, N)
 int64_t eval_num_tiles(int dtype, int32_t F, int32_t max_stack, int64_t N, int* threads_out,
                        size_t* smem_out);

@@ -29,7 +29,7 @@ namespace dex {
     __device__ __forceinline__ float m_##name(float x, float y) { return name##f(x, y); } \
     __device__ __forceinline__ double m_##name(double x, double y) { return name(x, y); }
 DEX_M1(fabs) DEX_M1(sqrt) DEX_M1(cbrt) DEX_M1(exp) DEX_M1(exp2) DEX_M1(exp10) DEX_M1(expm1)
-DEX_M1(log) DEX_M1(log2) DEX_M1(log10) DEX_M1(log1p) DEX_M1(sin) DEX_M1(cos) DEX_M1(tan)
+DEX_M1(log) DEX_M1(log2) DEX_M1(log10) DEX_M1(log1p) DEX_M1(tan)
 DEX_M1(asin) DEX_M1(acos) DEX_M1(atan) DEX_M1(sinh) DEX_M1(cosh) DEX_M1(tanh) DEX_M1(asinh)
 DEX_M1(acosh) DEX_M1(atanh) DEX_M1(rint) DEX_M1(floor) DEX_M1(ceil) DEX_M1(trunc) DEX_M1(erf)
 DEX_M1(erfc)
@@ -38,6 +38,46 @@ __device__ __forceinline__ float m_fma(float a, float b, float c) { return fmaf(
 __device__ __forceinline__ double m_fma(double a, double b, double c) { return fma(a, b, c); }
 #undef DEX_M1
 #undef DEX_M2
+
+// ---- sin / cos ------------------------------------------------------------------------
+// Float32: an inline fast path (three-constant Cody-Waite reduction by pi/2 carried in FMAs,
+// Cephes minimax polynomials on [-pi/4, pi/4]; <= ~1.5 ulp) for |x| <= 105615, and ONE shared
+// out-of-line call to the CUDA library function (Payne-Hanek reduction) for huge or
+// infinite arguments.  The interpreter unrolls every operator K times per handler; keeping
+// the rare, large slow path out of line keeps the hot loop inside the instruction cache.
+// Float64: the library functions, out of line for the same reason.
+static __device__ __noinline__ float slow_sinf(float x) { return sinf(x); }
+static __device__ __noinline__ float slow_cosf(float x) { return cosf(x); }
+static __device__ __noinline__ double slow_sin(double x) { return sin(x); }
+static __device__ __noinline__ double slow_cos(double x) { return cos(x); }
+
+template <int QADD> __device__ __forceinline__ float fast_sincosf(float x) {
+    const float j = rintf(x * 0.636619772367581343f);  // x * 2/pi
+    const int q = __float2int_rn(j) + QADD;
+    float r = fmaf(-j, 1.5707962513e+00f, x);
+    r = fmaf(-j, 7.5497894159e-08f, r);
+    r = fmaf(-j, 5.3903029534e-15f, r);
+    const float z = r * r;
+    // sin(r) = r + r z (s2 + z (s1 + z s0)),  cos(r) = 1 - z/2 + z^2 (c2 + z (c1 + z c0))
+    float sp = fmaf(z, -1.9515295891e-4f, 8.3321608736e-3f);
+    sp = fmaf(sp, z, -1.6666654611e-1f);
+    sp = fmaf(sp * z, r, r);
+    float cp = fmaf(z, 2.443315711809948e-5f, -1.388731625493765e-3f);
+    cp = fmaf(cp, z, 4.166664568298827e-2f);
+    cp = fmaf(cp * z, z, fmaf(z, -0.5f, 1.0f));
+    float v = (q & 1) ? cp : sp;
+    return (q & 2) ? -v : v;
+}
+__device__ __forceinline__ float m_sin(float x) {
+    if (fabsf(x) > 105615.0f) return slow_sinf(x);   // false for NaN: the fast path propagates it
+    return fast_sincosf<0>(x);
+}
+__device__ __forceinline__ float m_cos(float x) {
+    if (fabsf(x) > 105615.0f) return slow_cosf(x);
+    return fast_sincosf<1>(x);
+}
+__device__ __forceinline__ double m_sin(double x) { return slow_sin(x); }
+__device__ __forceinline__ double m_cos(double x) { return slow_cos(x); }
 
 template <typename T> __device__ __forceinline__ T t_nan();
 template <> __device__ __forceinline__ float t_nan<float>() { return CUDART_NAN_F; }

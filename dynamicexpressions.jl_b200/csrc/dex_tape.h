@@ -12,6 +12,11 @@
 // Stack slots and feature rows are ABSOLUTE shared-memory row indices fixed at pack
 // time: rows [0, max_stack) are the operand stack, rows [max_stack, max_stack+F)
 // are the features, so the interpreter never maintains a stack pointer.
+//
+// Every instruction also carries a HANDLER id: the index of a code path in the
+// interpreter that is specialised for (operator, operand sources), so that the hot
+// operators need one indirect branch and no operand decoding.  Handler 0 is the
+// generic path (any operator, any operand source, every flag).
 #pragma once
 #include <cstdint>
 #include <vector>
@@ -21,20 +26,23 @@ namespace dex {
 
 // ---- evaluation tape -------------------------------------------------------------
 // 16 bytes, fetched as one uint4 (x=w0, y=w1, z/w = constant).
-//   w0 [ 7: 0] opcode   builtin opcode of include/dex_ops.def (IDENTITY doubles as LOAD)
-//      [ 9: 8] srcA     SRC_*
-//      [11:10] srcB     SRC_*   (ternary: third operand is always ACC)
-//      [12]    PUSH     store ACC to row push_row BEFORE executing
-//      [13]    CHK_OUT  result participates in the `complete` flag
-//      [14]    CHK_A    operand A (a leaf) participates
-//      [15]    CHK_B    operand B (a leaf) participates
-//      [16]    ALWAYS   checks apply even when early_exit is off (constant-subtree
+//   w0 [ 7: 0] handler  HANDLER id (H_*), 0 = generic
+//      [15: 8] opcode   builtin opcode of include/dex_ops.def (IDENTITY doubles as LOAD)
+//      [17:16] srcA     SRC_*
+//      [19:18] srcB     SRC_*   (ternary: third operand is always ACC)
+//      [20]    PUSH     store ACC to row push_row BEFORE executing
+//      [21]    CHK_OUT  result participates in the `complete` flag
+//      [22]    CHK_A    operand A (a leaf) participates
+//      [23]    CHK_B    operand B (a leaf) participates
+//      [24]    ALWAYS   checks apply even when early_exit is off (constant-subtree
 //                       folding, /root/reference/src/Evaluate.jl:1059-1067)
-//      [17]    GUARD    unary: result = isfinite(arg) ? op(arg) : Inf
+//      [25]    GUARD    unary: result = isfinite(arg) ? op(arg) : Inf
 //                       (/root/reference/src/Evaluate.jl:722, 737, 754, 787)
+//      [26]    CHK_CONST  the inline constant participates (= CHK_A/CHK_B of the
+//                       constant operand; what the specialised handlers test)
+//   w1 [11: 0] rowA  (ROW: smem row; PARAM: parameter index)
+//      [23:12] rowB
 //      [31:24] push_row
-//   w1 [15: 0] rowA  (ROW: smem row; PARAM: parameter index)
-//      [31:16] rowB
 //   c  inline constant: float in .z (F32) or double in .z/.w (F64)
 struct Instr {
     uint32_t w0;
@@ -46,14 +54,41 @@ static_assert(sizeof(Instr) == 16, "tape instruction must be 16 bytes");
 
 enum : uint32_t { SRC_ACC = 0, SRC_ROW = 1, SRC_CONST = 2, SRC_PARAM = 3 };
 enum : uint32_t {
-    F_PUSH = 1u << 12,
-    F_CHK_OUT = 1u << 13,
-    F_CHK_A = 1u << 14,
-    F_CHK_B = 1u << 15,
-    F_ALWAYS = 1u << 16,
-    F_GUARD = 1u << 17,
+    F_PUSH = 1u << 20,
+    F_CHK_OUT = 1u << 21,
+    F_CHK_A = 1u << 22,
+    F_CHK_B = 1u << 23,
+    F_ALWAYS = 1u << 24,
+    F_GUARD = 1u << 25,
+    F_CHK_CONST = 1u << 26,
 };
 constexpr int MAX_STACK_ROWS = 250;  // push_row is 8 bits
+constexpr int MAX_ROWS = 4095;       // row fields are 12 bits
+
+// Operators with specialised handlers.  Unary: operand in ACC (_A) or in a ROW (_R).
+// Commutative binary: (ACC,ROW) (ACC,CONST) (ROW,ROW) (ROW,CONST) — the flattener swaps
+// operands into these forms.  Non-commutative binary: all seven operand forms.
+#define DEX_FAST_UNARY(X) \
+    X(NEG) X(ABS) X(SQUARE) X(CUBE) X(INV) X(SQRT) X(EXP) X(LOG) X(SIN) X(COS) X(TANH) \
+    X(RELU) X(SAFE_LOG) X(SAFE_SQRT)
+#define DEX_FAST_BIN_COMM(X) X(ADD) X(MUL) X(MAX) X(MIN)
+#define DEX_FAST_BIN_NC(X) X(SUB) X(DIV)
+
+enum Handler : uint32_t {
+    H_GENERIC = 0,
+    H_LOAD_R,  // ACC = ROW
+    H_LOAD_C,  // ACC = const
+#define X(S) H_##S##_A, H_##S##_R,
+    DEX_FAST_UNARY(X)
+#undef X
+#define X(S) H_##S##_AR, H_##S##_AC, H_##S##_RR, H_##S##_RC,
+    DEX_FAST_BIN_COMM(X)
+#undef X
+#define X(S) H_##S##_AR, H_##S##_RA, H_##S##_AC, H_##S##_CA, H_##S##_RR, H_##S##_RC, H_##S##_CR,
+    DEX_FAST_BIN_NC(X)
+#undef X
+    H__COUNT
+};
 
 // ---- gradient tape ---------------------------------------------------------------
 // Unfused post-order stack machine (the reference's derivative evaluator has no
@@ -86,6 +121,8 @@ struct PackedPopulation {
     int32_t max_gstack = 0;      // grad tape stack slots
     int32_t max_feature = -1;
     int32_t max_parameter = -1;
+    int64_t n_generic = 0;       // instructions that take the generic handler
+    int64_t n_checks = 0;        // validity checks left after elision
     std::vector<Instr> tape;               // all trees, concatenated
     std::vector<int64_t> tape_off;         // n_trees + 1
     std::vector<GInstr> gtape;
@@ -100,7 +137,6 @@ struct PackedPopulation {
 
 // Flatten `n_trees` wire trees.  Returns 0 or a negative DEX_ERR_* code with a
 // message (tree index included) in `err`.
-struct WireNode;  // = dex_node
 int flatten_population(const OpTable& ops, const void* nodes, const int64_t* offsets,
                        int64_t n_trees, int dtype, int pack_flags, PackedPopulation& out,
                        std::string& err);

@@ -18,7 +18,7 @@ from .node import MAX_DEGREE, WIRE_DTYPE, Node, to_wire_population
 from .operators import OperatorEnum
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libdexb200.so")
+LIB_PATH = os.environ.get("DEXB200_LIB") or os.path.join(_HERE, "lib", "libdexb200.so")
 
 OK = 0
 F32, F64 = 0, 1
@@ -38,6 +38,7 @@ ABI = {
     "dex_ctx_create": (C.c_int, [C.c_int, C.POINTER(_P)]),
     "dex_ctx_destroy": (C.c_int, [_P]),
     "dex_ctx_set_stream": (C.c_int, [_P, _P]),
+    "dex_ctx_use_own_stream": (C.c_int, [_P]),
     "dex_ctx_synchronize": (C.c_int, [_P]),
     "dex_last_error": (C.c_char_p, [_P]),
     "dex_optable_create": (C.c_int, [_P, _P, C.c_int, C.POINTER(_P)]),
@@ -60,6 +61,7 @@ ABI = {
     "dex_host_free": (C.c_int, [_P]),
     "dex_ctx_launch_count": (_I64, [_P]),
     "dex_population_copy_tape": (_I64, [_P, _P, _I64, _P]),
+    "dex_handler_name": (C.c_char_p, [C.c_int]),
 }
 
 
@@ -72,7 +74,7 @@ class DexError(RuntimeError):
 class _Info(C.Structure):
     _fields_ = [("n_trees", _I64), ("n_nodes", _I64), ("n_instructions", _I64),
                 ("n_constants", _I64), ("max_stack", _I32), ("max_feature", _I32),
-                ("max_parameter", _I32), ("dtype", _I32)]
+                ("max_parameter", _I32), ("dtype", _I32), ("n_generic", _I64), ("n_checks", _I64)]
 
 
 _lib = None

@@ -87,10 +87,12 @@ int dex_opcode_degree(int opcode);
 /* device < 0: host-only context (packing / validation only, no CUDA calls).           */
 int dex_ctx_create(int device, dex_ctx** out);
 int dex_ctx_destroy(dex_ctx* ctx);
-/* stream: a cudaStream_t (or NULL for the context's own stream); all device work of
- * later calls is enqueued on it and is asynchronous w.r.t. the host, except the
- * *_host convenience entry points, which synchronise.                                */
+/* stream: a cudaStream_t; NULL is CUDA's legacy default stream.  All device work of later
+ * calls is enqueued on it and is asynchronous w.r.t. the host, except the *_host
+ * convenience entry points, which synchronise.  A new context uses a private
+ * non-blocking stream; dex_ctx_use_own_stream returns to it.                          */
 int dex_ctx_set_stream(dex_ctx* ctx, void* stream);
+int dex_ctx_use_own_stream(dex_ctx* ctx);
 int dex_ctx_synchronize(dex_ctx* ctx);
 const char* dex_last_error(const dex_ctx* ctx);
 
@@ -120,6 +122,8 @@ typedef struct dex_population_info {
     int32_t max_feature;      /* largest feature index used (0-based), -1 if none               */
     int32_t max_parameter;    /* largest parameter index used (0-based), -1 if none             */
     int32_t dtype;
+    int64_t n_generic;        /* instructions executed by the generic (non-specialised) handler */
+    int64_t n_checks;         /* validity checks left after host-side elision                   */
 } dex_population_info;
 int dex_population_get_info(const dex_population* pop, dex_population_info* info);
 /* per-tree count_constant_nodes (/root/reference/src/NodeUtils.jl:43-51); counts[n_trees] */
@@ -187,6 +191,8 @@ int dex_host_free(void* p);
 /* ---- introspection (tests, benchmarks) -------------------------------------------------- */
 /* kernels launched through this context so far */
 int64_t dex_ctx_launch_count(const dex_ctx* ctx);
+/* name of an interpreter handler id ("ADD_AR", "COS_R", ...; csrc/dex_tape.h), NULL if none */
+const char* dex_handler_name(int handler);
 /* copies the host image of the evaluation tape (16-byte instructions, csrc/dex_tape.h);
  * returns the instruction count; offsets (n_trees+1) may be NULL */
 int64_t dex_population_copy_tape(const dex_population* pop, void* instrs, int64_t capacity,

@@ -86,6 +86,13 @@ int32_t dexo_count_constants(const dex_node* nodes, int64_t n_nodes) {
     return number_constants(nodes, n_nodes, NULL);
 }
 
+/* DEXO_ELEMENTWISE: validity of an array = every element finite, instead of the
+ * reference's isfinite(sum(x)).  The two differ only when a sum of finite values
+ * overflows (e.g. 3000 samples of 1e36 in Float32) — the one documented deviation of the
+ * device path (DESIGN.md "completion flag"); the tests use this mode to tell that case
+ * apart from a real disagreement. */
+static __thread int g_elementwise = 0;
+
 /* ---- instantiate for Float32 and Float64 ------------------------------------ */
 #define T float
 #define S(name) name##_f32
@@ -98,6 +105,16 @@ int32_t dexo_count_constants(const dex_node* nodes, int64_t n_nodes) {
 #define T double
 #define S(name) name##_f64
 #define M(fn) fn
+#include "dex_oracle_impl.inc"
+#undef T
+#undef S
+#undef M
+
+/* extended precision (x87 80-bit): NOT a reference path — the yardstick the parity tests use
+ * to measure how sensitive a tree is to intermediate rounding (see dexo_eval_population_f80) */
+#define T long double
+#define S(name) name##_f80
+#define M(fn) fn##l
 #include "dex_oracle_impl.inc"
 #undef T
 #undef S
@@ -130,6 +147,8 @@ static int grad_common(const dex_node* nodes, int64_t n_nodes, const dexo_optabl
                        int32_t direction, void* out, void* grad, int64_t grad_capacity,
                        int32_t* n_grad_out, uint8_t* ok) {
     tree_info tr;
+    g_elementwise = (mode & DEXO_GRAD_ELEMENTWISE) != 0;
+    if (mode >= 0) mode &= 3;
     int rc = tree_info_init(&tr, nodes, n_nodes, ops, F);
     if (rc) return rc;
     int32_t* cidx = (int32_t*)malloc(sizeof(int32_t) * (size_t)n_nodes);
@@ -168,7 +187,7 @@ int dexo_eval_grad_tree_array(const dex_node* nodes, int64_t n_nodes, const dexo
                               int dtype, const void* X, int32_t F, int64_t N, int64_t ldx,
                               int mode, void* out, void* grad, int64_t grad_capacity,
                               int32_t* n_grad_out, uint8_t* ok) {
-    if (mode < 0 || mode > 2) return -1;
+    if (mode < 0 || (mode & 3) > 2) return -1;
     return grad_common(nodes, n_nodes, ops, dtype, X, F, N, ldx, mode, 0, out, grad,
                        grad_capacity, n_grad_out, ok);
 }
@@ -278,6 +297,43 @@ int dexo_eval_parametric_population(const dex_node* nodes, const int64_t* offset
                                       (char*)out + (size_t)t * (size_t)N * es, &ok[t]);
         if (rc) { err = rc; ok[t] = 0; }
     }
+    return err;
+}
+
+/* Float64 inputs, every intermediate in 80-bit long double, Float64 outputs.  Comparing this
+ * with the Float64 evaluation of the same tree tells how much of a disagreement between two
+ * correct Float64 implementations is explained by rounding amplification alone. */
+int dexo_eval_population_f80(const dex_node* nodes, const int64_t* offsets, int64_t n_trees,
+                             const dexo_optable* ops, const double* X, int32_t F, int64_t N,
+                             int64_t ldx, int flags, int nthreads, double* out, uint8_t* ok) {
+    int err = 0;
+    int nt = pick_threads(nthreads);
+    (void)nt;
+    long double* XL = (long double*)malloc(sizeof(long double) * (size_t)F * (size_t)(N > 0 ? N : 1));
+    if (!XL) return -2;
+    for (int64_t j = 0; j < N; ++j)
+        for (int32_t f = 0; f < F; ++f) XL[f + (int64_t)F * j] = X[f + ldx * j];
+#pragma omp parallel num_threads(nt)
+    {
+        ctx_f80 c;
+        memset(&c, 0, sizeof(c));
+        long double* tmp = (long double*)malloc(sizeof(long double) * (size_t)(N > 0 ? N : 1));
+#pragma omp for schedule(dynamic, 1)
+        for (int64_t t = 0; t < n_trees; ++t) {
+            tree_info tr;
+            int rc = tree_info_init(&tr, nodes + offsets[t], offsets[t + 1] - offsets[t], ops, F);
+            if (rc) { err = rc; ok[t] = 0; continue; }
+            c.tr = &tr; c.ops = ops; c.X = XL; c.F = F; c.N = N; c.ldx = F;
+            c.early_exit = (flags & DEXO_EARLY_EXIT) != 0;
+            c.use_fused = (flags & DEXO_USE_FUSED) != 0;
+            eval_entry_f80(&c, flags, tmp, &ok[t]);
+            for (int64_t j = 0; j < N; ++j) out[(size_t)t * (size_t)N + j] = (double)tmp[j];
+            tree_info_free(&tr);
+        }
+        free(tmp);
+        ctx_free_f80(&c);
+    }
+    free(XL);
     return err;
 }
 

@@ -48,11 +48,14 @@ typedef struct dexo_optable {
 enum {
     DEXO_EARLY_EXIT = 1, /* early_exit = Val(true) (reference default)  */
     DEXO_USE_FUSED = 2,  /* use_fused  = Val(true) (reference default)  */
-    DEXO_BUMPER = 4      /* bumper     = Val(true): unfused post-order evaluator */
+    DEXO_BUMPER = 4,     /* bumper     = Val(true): unfused post-order evaluator */
+    DEXO_ELEMENTWISE = 8 /* NOT a reference mode: array validity = all elements finite
+                            (instead of isfinite(sum)); isolates sum-overflow cases      */
 };
 
 /* gradient modes (src/EvaluateDerivative.jl:200-202) */
-enum { DEXO_GRAD_CONSTANTS = 0, DEXO_GRAD_FEATURES = 1, DEXO_GRAD_BOTH = 2 };
+enum { DEXO_GRAD_CONSTANTS = 0, DEXO_GRAD_FEATURES = 1, DEXO_GRAD_BOTH = 2,
+       DEXO_GRAD_ELEMENTWISE = 8 /* or-ed into mode: same meaning as DEXO_ELEMENTWISE */ };
 
 /* All entry points: dtype = DEX_F32 / DEX_F64; X is column-major F x N with
  * leading dimension ldx (>= F).  Return 0 on success, <0 on malformed input.
@@ -88,6 +91,12 @@ int dexo_eval_population(const dex_node* nodes, const int64_t* offsets, int64_t 
                          const dexo_optable* ops, int dtype, const void* X, int32_t nfeatures,
                          int64_t nsamples, int64_t ldx, int flags, int nthreads, void* out,
                          uint8_t* ok);
+
+/* conditioning yardstick for the Float64 parity tests: same algorithm, 80-bit intermediates */
+int dexo_eval_population_f80(const dex_node* nodes, const int64_t* offsets, int64_t n_trees,
+                             const dexo_optable* ops, const double* X, int32_t nfeatures,
+                             int64_t nsamples, int64_t ldx, int flags, int nthreads, double* out,
+                             uint8_t* ok);
 
 int dexo_eval_grad_population(const dex_node* nodes, const int64_t* offsets, int64_t n_trees,
                               const dexo_optable* ops, int dtype, const void* X,

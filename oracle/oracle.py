@@ -18,7 +18,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_build", "libdexoracle.so")
 
-EARLY_EXIT, USE_FUSED, BUMPER = 1, 2, 4
+EARLY_EXIT, USE_FUSED, BUMPER, ELEMENTWISE = 1, 2, 4, 8
+GRAD_ELEMENTWISE = 8
 DEFAULT_FLAGS = EARLY_EXIT | USE_FUSED
 GRAD_CONSTANTS, GRAD_FEATURES, GRAD_BOTH = 0, 1, 2
 F32, F64 = 0, 1
@@ -134,7 +135,8 @@ def eval_grad_tree_array(wire, opcodes, X, mode):
     F, N, Xc = _prep_X(X)
     t, keep = _optable(opcodes)
     nc = count_constants(wire)
-    G = F if mode == GRAD_FEATURES else nc if mode == GRAD_CONSTANTS else F + nc
+    m = mode & 3
+    G = F if m == GRAD_FEATURES else nc if m == GRAD_CONSTANTS else F + nc
     out = np.full(N, np.nan, dtype=Xc.dtype)
     grad = np.full((N, G), np.nan, dtype=Xc.dtype)  # column-major (G x N)
     ok = C.c_uint8(0)
@@ -187,6 +189,23 @@ def eval_population(nodes, offsets, opcodes, X, flags=DEFAULT_FLAGS, nthreads=0,
     return out, ok.astype(bool)
 
 
+def eval_population_f80(nodes, offsets, opcodes, X, flags=DEFAULT_FLAGS, nthreads=0):
+    """Float64 in/out with 80-bit intermediates: the rounding-sensitivity yardstick."""
+    F, N, Xc = _prep_X(np.asarray(X, dtype=np.float64))
+    t, keep = _optable(opcodes)
+    P = len(offsets) - 1
+    out = np.empty((P, N), dtype=np.float64)
+    ok = np.zeros(P, dtype=np.uint8)
+    nodes = np.ascontiguousarray(nodes)
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    rc = lib().dexo_eval_population_f80(_p(nodes), _p(offsets), C.c_int64(P), C.byref(t), _p(Xc),
+                                        C.c_int32(F), C.c_int64(N), C.c_int64(F), C.c_int(flags),
+                                        C.c_int(nthreads), _p(out), _p(ok))
+    if rc:
+        raise ValueError(f"oracle rejected a tree (rc={rc})")
+    return out, ok.astype(bool)
+
+
 def eval_grad_population(nodes, offsets, opcodes, X, mode, nthreads=0):
     """(out[P, N], [grad_t (G_t, N)], ok[P])."""
     F, N, Xc = _prep_X(X)
@@ -197,7 +216,8 @@ def eval_grad_population(nodes, offsets, opcodes, X, mode, nthreads=0):
     G = np.zeros(P, dtype=np.int64)
     for i in range(P):
         nc = count_constants(nodes[offsets[i]:offsets[i + 1]])
-        G[i] = F if mode == GRAD_FEATURES else nc if mode == GRAD_CONSTANTS else F + nc
+        m = mode & 3
+        G[i] = F if m == GRAD_FEATURES else nc if m == GRAD_CONSTANTS else F + nc
     goff = np.zeros(P + 1, dtype=np.int64)
     np.cumsum(G * N, out=goff[1:])
     out = np.empty((P, N), dtype=Xc.dtype)

@@ -1,22 +1,31 @@
 """numpy interpreter for the device evaluation tape (csrc/dex_tape.h) — TEST ONLY.
 
-It executes exactly what csrc/dex_eval.cu executes (same operand sources, PUSH rows,
-check flags, GUARD), with numpy ufuncs as the arithmetic, so that the host-side
-flattener (csrc/dex_flatten.cpp) can be checked against the CPU oracle in this
-GPU-less container.  It is not part of the product and is never imported by it.
+It executes exactly what csrc/dex_eval.cu executes — including the choice between a
+specialised handler (operands implied by the handler id) and the generic handler
+(operands decoded from the source fields) — with numpy ufuncs as the arithmetic, so that
+the host-side flattener (csrc/dex_flatten.cpp: evaluation order, stack slots, check flags,
+check elision, handler lowering) can be checked against the CPU oracle in this GPU-less
+container.  It is not part of the product and is never imported by it.
 """
 import numpy as np
 
+from dexb200 import device as D
 from oracle.oracle import _np_ops
 
 SRC_ACC, SRC_ROW, SRC_CONST, SRC_PARAM = 0, 1, 2, 3
-F_PUSH, F_CHK_OUT, F_CHK_A, F_CHK_B, F_ALWAYS, F_GUARD = (1 << 12, 1 << 13, 1 << 14, 1 << 15,
-                                                           1 << 16, 1 << 17)
+F_PUSH, F_CHK_OUT, F_CHK_A, F_CHK_B, F_ALWAYS, F_GUARD, F_CHK_CONST = (1 << 20, 1 << 21, 1 << 22,
+                                                                        1 << 23, 1 << 24, 1 << 25, 1 << 26)
+
+
+def handler_name(h):
+    s = D.lib().dex_handler_name(int(h))
+    return s.decode() if s else None
 
 
 def run_tape(ins, X, max_stack, opcode_info, dtype, early_exit=True, params=None, classes0=None):
     """ins: uint32[n, 4] of one tree; X: (F, N).  Returns (out[N], ok)."""
     u, b, t = _np_ops()
+    sym2code = {v[0]: k for k, v in opcode_info.items()}
     F, N = X.shape
     rows = np.zeros((max_stack + F, N), dtype=dtype)
     rows[max_stack:] = X
@@ -28,28 +37,72 @@ def run_tape(ins, X, max_stack, opcode_info, dtype, early_exit=True, params=None
             return np.array([w[2]], dtype=np.uint32).view(np.float32)[0]
         return np.array([w[2], w[3]], dtype=np.uint32).view(np.float64)[0]
 
-    def fetch(src, row, c):
-        if src == SRC_ROW:
-            return rows[row].copy()
-        if src == SRC_CONST:
-            return np.full(N, c, dtype=dtype)
-        if src == SRC_PARAM:
-            return np.asarray(params, dtype=dtype)[row, classes0]
-        return acc.copy()
+    def bad(v):
+        return not np.isfinite(v).all()
 
     for w in ins:
-        w0 = int(w[0])
+        w0, w1 = int(w[0]), int(w[1])
+        rowA, rowB, push_row = w1 & 0xFFF, (w1 >> 12) & 0xFFF, w1 >> 24
         if w0 & F_PUSH:
-            rows[w0 >> 24] = acc
+            rows[push_row] = acc
         c = const_of(w)
-        va = fetch((w0 >> 8) & 3, int(w[1]) & 0xFFFF, c)
-        vb = fetch((w0 >> 10) & 3, int(w[1]) >> 16, c)
+        cvec = np.full(N, c, dtype=dtype)
+        h = (w0 & 0xFF) if early_exit else 0          # early_exit off => generic kernel
+        code = (w0 >> 8) & 0xFF
+        if h != 0:
+            name = handler_name(h)
+            opname, pat = name.rsplit("_", 1)
+            if opname == "LOAD":
+                va = rows[rowA].copy() if pat == "R" else cvec
+                if pat == "R" and (w0 & F_CHK_A) and bad(va):
+                    ok = False
+                if pat == "C" and (w0 & F_CHK_CONST) and bad(cvec):
+                    ok = False
+                assert opcode_info[code][0] == "IDENTITY"
+                r = va
+            else:
+                hcode = sym2code[opname]
+                assert hcode == code, (name, opcode_info[code])
+                deg = opcode_info[code][1]
+                if deg == 1:
+                    va = acc.copy() if pat == "A" else rows[rowA].copy()
+                    assert ((w0 >> 16) & 3) == (SRC_ACC if pat == "A" else SRC_ROW)
+                    if pat == "R" and (w0 & F_CHK_A) and bad(va):
+                        ok = False
+                    with np.errstate(all="ignore"):
+                        r = u[opname](va)
+                else:
+                    srcs = {"A": SRC_ACC, "R": SRC_ROW, "C": SRC_CONST}
+                    assert ((w0 >> 16) & 3) == srcs[pat[0]] and ((w0 >> 18) & 3) == srcs[pat[1]]
+                    assert not (w0 & F_CHK_A and pat[0] == "R") and not (w0 & F_CHK_B and pat[1] == "R")
+                    va = {"A": acc, "R": rows[rowA], "C": cvec}[pat[0]].copy()
+                    vb = {"A": acc, "R": rows[rowB], "C": cvec}[pat[1]].copy()
+                    if "C" in pat and (w0 & F_CHK_CONST) and bad(cvec):
+                        ok = False
+                    assert bool(w0 & F_CHK_CONST) == bool(("C" in pat) and (w0 & (F_CHK_A | F_CHK_B)))
+                    with np.errstate(all="ignore"):
+                        r = b[opname](va, vb)
+            acc = np.asarray(r, dtype=dtype)
+            if (w0 & F_CHK_OUT) and bad(acc):
+                ok = False
+            continue
+
+        def fetch(src, row):
+            if src == SRC_ROW:
+                return rows[row].copy()
+            if src == SRC_CONST:
+                return cvec.copy()
+            if src == SRC_PARAM:
+                return np.asarray(params, dtype=dtype)[row, classes0]
+            return acc.copy()
+
+        va = fetch((w0 >> 16) & 3, rowA)
+        vb = fetch((w0 >> 18) & 3, rowB)
         chk = early_exit or bool(w0 & F_ALWAYS)
-        if chk and (w0 & F_CHK_A) and not np.isfinite(va).all():
+        if chk and (w0 & F_CHK_A) and bad(va):
             ok = False
-        if chk and (w0 & F_CHK_B) and not np.isfinite(vb).all():
+        if chk and (w0 & F_CHK_B) and bad(vb):
             ok = False
-        code = w0 & 0xFF
         sym, deg, _ = opcode_info[code]
         with np.errstate(all="ignore"):
             if deg == 1:
@@ -59,9 +112,9 @@ def run_tape(ins, X, max_stack, opcode_info, dtype, early_exit=True, params=None
             else:
                 r = t[sym](va, vb, acc)
         r = np.asarray(r, dtype=dtype)
-        if w0 & F_GUARD:
+        if (not early_exit) and (w0 & F_GUARD):
             r = np.where(np.isfinite(va), r, np.inf).astype(dtype)
         acc = r
-        if chk and (w0 & F_CHK_OUT) and not np.isfinite(r).all():
+        if chk and (w0 & F_CHK_OUT) and bad(r):
             ok = False
     return acc, ok
