@@ -176,7 +176,7 @@ int check_eval_args(dex_ctx* ctx, const dex_population* pop, const void* X, int3
     if (N > 0 && (!X && F > 0)) return set_err(ctx, DEX_ERR_INVALID, "null X");
     if (ldx < F) return set_err(ctx, DEX_ERR_INVALID, "ldx < nfeatures");
     if (out && ldo < N) return set_err(ctx, DEX_ERR_INVALID, "ldo < nsamples");
-    if (!ok) return set_err(ctx, DEX_ERR_INVALID, "null ok");
+    if (!ok && pop->h.n_trees > 0) return set_err(ctx, DEX_ERR_INVALID, "null ok");
     if (pop->h.max_feature >= F)
         return set_err(ctx, DEX_ERR_RANGE,
                        "population uses feature " + std::to_string(pop->h.max_feature + 1) +
@@ -494,7 +494,7 @@ int dex_eval(dex_ctx* ctx, const dex_population* pop, const void* X_dev, int32_t
     int rc = ensure_device(ctx);
     if (rc) return rc;
     if ((rc = check_eval_args(ctx, pop, X_dev, nfeatures, nsamples, ldx, out_dev, ldo, ok_dev))) return rc;
-    if (!out_dev) return set_err(ctx, DEX_ERR_INVALID, "null out");
+    if (!out_dev && nsamples > 0 && pop->h.n_trees > 0) return set_err(ctx, DEX_ERR_INVALID, "null out");
     if (pop->h.max_parameter >= 0) return set_err(ctx, DEX_ERR_INVALID, "population has parameter leaves: use dex_eval_parametric");
     return run_eval(ctx, pop, X_dev, nfeatures, nsamples, ldx, out_dev, ldo, ok_dev, eval_flags,
                     nullptr, 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr);
@@ -507,7 +507,7 @@ int dex_eval_parametric(dex_ctx* ctx, const dex_population* pop, const void* X_d
     int rc = ensure_device(ctx);
     if (rc) return rc;
     if ((rc = check_eval_args(ctx, pop, X_dev, nfeatures, nsamples, ldx, out_dev, ldo, ok_dev))) return rc;
-    if (!out_dev) return set_err(ctx, DEX_ERR_INVALID, "null out");
+    if (!out_dev && nsamples > 0 && pop->h.n_trees > 0) return set_err(ctx, DEX_ERR_INVALID, "null out");
     if (n_params < 0 || n_classes < 1 || !classes_dev || (n_params > 0 && !params_dev))
         return set_err(ctx, DEX_ERR_INVALID, "bad parameter arguments");
     if (pop->h.max_parameter >= n_params)
@@ -605,7 +605,7 @@ int dex_eval_grad(dex_ctx* ctx, const dex_population* pop, const void* X_dev, in
     if (rc) return rc;
     if ((rc = check_eval_args(ctx, pop, X_dev, nfeatures, nsamples, ldx, out_dev, ldo, ok_dev))) return rc;
     if (mode < 0 || mode > 2) return set_err(ctx, DEX_ERR_INVALID, "mode must be DEX_GRAD_CONSTANTS/FEATURES/BOTH");
-    if (!out_dev || !grad_offsets_host) return set_err(ctx, DEX_ERR_INVALID, "null out / grad_offsets");
+    if ((!out_dev && nsamples > 0 && pop->h.n_trees > 0) || !grad_offsets_host) return set_err(ctx, DEX_ERR_INVALID, "null out / grad_offsets");
     if (!grad_dev && grad_offsets_host[pop->h.n_trees] > 0) return set_err(ctx, DEX_ERR_INVALID, "null grad");
     return run_grad(ctx, pop, X_dev, nfeatures, nsamples, ldx, mode, 0, out_dev, ldo, grad_dev, grad_offsets_host, ok_dev);
 }
@@ -616,7 +616,7 @@ int dex_eval_diff(dex_ctx* ctx, const dex_population* pop, const void* X_dev, in
     int rc = ensure_device(ctx);
     if (rc) return rc;
     if ((rc = check_eval_args(ctx, pop, X_dev, nfeatures, nsamples, ldx, out_dev, ldo, ok_dev))) return rc;
-    if (!out_dev || !dout_dev) return set_err(ctx, DEX_ERR_INVALID, "null out / dout");
+    if ((!out_dev || !dout_dev) && nsamples > 0 && pop->h.n_trees > 0) return set_err(ctx, DEX_ERR_INVALID, "null out / dout");
     if (direction < 0) return set_err(ctx, DEX_ERR_RANGE, "direction must be a feature index");
     return run_grad(ctx, pop, X_dev, nfeatures, nsamples, ldx, -1, direction, out_dev, ldo, dout_dev, nullptr, ok_dev);
 }

@@ -34,6 +34,21 @@
 #ifndef DEX_EVAL_U
 #define DEX_EVAL_U 2
 #endif
+#ifndef DEX_TAIL_DUP
+#define DEX_TAIL_DUP 0
+#endif
+#ifndef DEX_MIN_CTAS
+#define DEX_MIN_CTAS 3
+#endif
+#ifndef DEX_MAX_THREADS
+#define DEX_MAX_THREADS 256
+#endif
+#ifndef DEX_SYNC_TREE
+#define DEX_SYNC_TREE 0
+#endif
+#ifndef DEX_SYNC_INSTR
+#define DEX_SYNC_INSTR 0
+#endif
 
 namespace dex {
 
@@ -107,7 +122,7 @@ __device__ __forceinline__ void check(T (&nf)[2], const Vec<T, U>& r) {
 }
 
 template <typename T, int U, bool FAST, bool PARAM, bool LOSS>
-__global__ void __launch_bounds__(256, 3) eval_kernel(const KArgs<T> a) {
+__global__ void __launch_bounds__(DEX_MAX_THREADS, DEX_MIN_CTAS) eval_kernel(const KArgs<T> a) {
     using V = Vec<T, U>;
     constexpr int C = V::C;
     constexpr int K = V::K;
@@ -188,6 +203,9 @@ __global__ void __launch_bounds__(256, 3) eval_kernel(const KArgs<T> a) {
                            ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0);
 
     for (int t = t0; t < t1; ++t) {
+#if DEX_SYNC_TREE
+        __syncthreads();  // experiment: re-align the warps of the CTA at every tree
+#endif
         const int64_t off = a.tape_off[t];
         const int n = (int)(a.tape_off[t + 1] - off);
         const uint4* ip = a.tape + off;
@@ -208,27 +226,40 @@ __global__ void __launch_bounds__(256, 3) eval_kernel(const KArgs<T> a) {
             if (w0 & F_PUSH) st_row<T, U>(my + (size_t)(ins.y >> 24) * TILE, CS, acc);
 
             const uint32_t h = FAST ? (w0 & 0xffu) : (uint32_t)H_GENERIC;
+#if DEX_TAIL_DUP
+// every specialised handler carries its own copy of the loop tail, so the accumulator is
+// updated in place and no register shuffling is needed at a shared merge point
+#define HANDLER_END                                   \
+    if (w0 & F_CHK_OUT) check<T, U>(nf, acc);         \
+    ins = nxt;                                        \
+    continue;
+#else
+#define HANDLER_END break;
+#endif
+#if DEX_SYNC_INSTR
+            __syncthreads();  // experiment: keep the warps of a CTA on the same handler
+#endif
             switch (h) {
                 // ---- specialised handlers: one indirect branch, no operand decoding ----
                 case H_LOAD_R: {
                     ld_row<T, U>(acc, ra, CS);
                     if (w0 & F_CHK_A) check<T, U>(nf, acc);
-                } break;
+                } HANDLER_END
                 case H_LOAD_C: {
 #pragma unroll
                     for (int k = 0; k < K; ++k) acc.v[k] = c;
                     if (w0 & F_CHK_CONST) nf[0] = m_fma(c, T(0), nf[0]);
-                } break;
+                } HANDLER_END
 #define UNARY_HANDLERS(S)                                                          \
     case H_##S##_A: {                                                              \
         _Pragma("unroll") for (int k = 0; k < K; ++k) acc.v[k] = Op1<DEX_OP_##S, T>::f(acc.v[k]); \
-    } break;                                                                       \
+    } HANDLER_END                                                                  \
     case H_##S##_R: {                                                              \
         V x;                                                                       \
         ld_row<T, U>(x, ra, CS);                                                   \
         if (w0 & F_CHK_A) check<T, U>(nf, x);                                      \
         _Pragma("unroll") for (int k = 0; k < K; ++k) acc.v[k] = Op1<DEX_OP_##S, T>::f(x.v[k]); \
-    } break;
+    } HANDLER_END
                 DEX_FAST_UNARY(UNARY_HANDLERS)
 #undef UNARY_HANDLERS
 #define BIN_AR(S)                                                                  \
@@ -236,44 +267,44 @@ __global__ void __launch_bounds__(256, 3) eval_kernel(const KArgs<T> a) {
         V y;                                                                       \
         ld_row<T, U>(y, rb, CS);                                                   \
         _Pragma("unroll") for (int k = 0; k < K; ++k) acc.v[k] = Op2<DEX_OP_##S, T>::f(acc.v[k], y.v[k]); \
-    } break;
+    } HANDLER_END
 #define BIN_RA(S)                                                                  \
     case H_##S##_RA: {                                                             \
         V x;                                                                       \
         ld_row<T, U>(x, ra, CS);                                                   \
         _Pragma("unroll") for (int k = 0; k < K; ++k) acc.v[k] = Op2<DEX_OP_##S, T>::f(x.v[k], acc.v[k]); \
-    } break;
+    } HANDLER_END
 #define BIN_AC(S)                                                                  \
     case H_##S##_AC: {                                                             \
         if (w0 & F_CHK_CONST) nf[0] = m_fma(c, T(0), nf[0]);                       \
         _Pragma("unroll") for (int k = 0; k < K; ++k) acc.v[k] = Op2<DEX_OP_##S, T>::f(acc.v[k], c); \
-    } break;
+    } HANDLER_END
 #define BIN_CA(S)                                                                  \
     case H_##S##_CA: {                                                             \
         if (w0 & F_CHK_CONST) nf[0] = m_fma(c, T(0), nf[0]);                       \
         _Pragma("unroll") for (int k = 0; k < K; ++k) acc.v[k] = Op2<DEX_OP_##S, T>::f(c, acc.v[k]); \
-    } break;
+    } HANDLER_END
 #define BIN_RR(S)                                                                  \
     case H_##S##_RR: {                                                             \
         V x, y;                                                                    \
         ld_row<T, U>(x, ra, CS);                                                   \
         ld_row<T, U>(y, rb, CS);                                                   \
         _Pragma("unroll") for (int k = 0; k < K; ++k) acc.v[k] = Op2<DEX_OP_##S, T>::f(x.v[k], y.v[k]); \
-    } break;
+    } HANDLER_END
 #define BIN_RC(S)                                                                  \
     case H_##S##_RC: {                                                             \
         V x;                                                                       \
         ld_row<T, U>(x, ra, CS);                                                   \
         if (w0 & F_CHK_CONST) nf[0] = m_fma(c, T(0), nf[0]);                       \
         _Pragma("unroll") for (int k = 0; k < K; ++k) acc.v[k] = Op2<DEX_OP_##S, T>::f(x.v[k], c); \
-    } break;
+    } HANDLER_END
 #define BIN_CR(S)                                                                  \
     case H_##S##_CR: {                                                             \
         V y;                                                                       \
         ld_row<T, U>(y, rb, CS);                                                   \
         if (w0 & F_CHK_CONST) nf[0] = m_fma(c, T(0), nf[0]);                       \
         _Pragma("unroll") for (int k = 0; k < K; ++k) acc.v[k] = Op2<DEX_OP_##S, T>::f(c, y.v[k]); \
-    } break;
+    } HANDLER_END
 #define COMM_HANDLERS(S) BIN_AR(S) BIN_AC(S) BIN_RR(S) BIN_RC(S)
 #define NC_HANDLERS(S) BIN_AR(S) BIN_RA(S) BIN_AC(S) BIN_CA(S) BIN_RR(S) BIN_RC(S) BIN_CR(S)
                 DEX_FAST_BIN_COMM(COMM_HANDLERS)
@@ -384,7 +415,7 @@ __global__ void __launch_bounds__(256, 3) eval_kernel(const KArgs<T> a) {
             // deterministic block reduction -> loss_partial[tile][tree]
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) ls += __shfl_xor_sync(0xffffffffu, ls, o);
-            __shared__ double red[8];
+            __shared__ double red[DEX_MAX_THREADS / 32];
             __syncthreads();
             if ((tid & 31) == 0) red[tid >> 5] = ls;
             __syncthreads();
@@ -490,12 +521,14 @@ int64_t eval_num_tiles(int dtype, int32_t F, int32_t max_stack, int64_t N, int* 
     const size_t es = dtype == DEX_F32 ? 4 : 8;
     const size_t rows = (size_t)F + (size_t)max_stack;
     int threads = 256;
+    bool forced = false;
     if (const char* env = getenv("DEXB200_THREADS")) {   // tuning knob for experiments
         const int v = atoi(env);
-        if (v == 32 || v == 64 || v == 128 || v == 256) threads = v;
+        if (v >= 32 && v <= DEX_MAX_THREADS && v % 32 == 0) { threads = v; forced = true; }
     }
     // keep >= 2 CTAs resident per SM when possible; shrink the block if the rows do not fit
-    while (threads > 32 && rows * (size_t)threads * K * es > SMEM_LIMIT / 2) threads >>= 1;
+    const size_t budget = forced ? SMEM_LIMIT : SMEM_LIMIT / 2;
+    while (threads > 32 && rows * (size_t)threads * K * es > budget) threads >>= 1;
     if (N < (int64_t)threads * K) {  // tiny inputs: do not stage more columns than exist
         while (threads > 32 && (int64_t)(threads / 2) * K >= N) threads >>= 1;
     }

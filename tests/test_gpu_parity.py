@@ -282,8 +282,9 @@ def test_strided_inputs_and_outputs(oracle):
     _flags_agree(ok.cpu().numpy(), rok, rok_elem, "strided")
     assert (big[:, N:] == -7.0).all()
     o = out.cpu().numpy()
+    ref64, _ = oracle.eval_population(nodes, offsets, ops.opcodes, Xpad[:, :4].T.astype(np.float64))
     for t in np.nonzero(rok)[0]:
-        assert _relerr(o[t], ref[t]) < 1e-4
+        assert _relerr(o[t], ref[t]) <= max(1e-4, 30 * _relerr(ref[t], ref64[t]))
     # torch in => torch out, same values
     y, okk = dexb200.eval_trees_array([dexb200.from_wire(nodes[offsets[0]:offsets[1]])], Xview, ops)
     assert y.is_cuda and torch.equal(y[0], out[0])
