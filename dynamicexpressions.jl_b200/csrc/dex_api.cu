@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <new>
@@ -135,7 +136,8 @@ int ensure_pinned(dex_ctx* ctx, size_t bytes) {
 template <typename U>
 int upload(dex_ctx* ctx, U** dptr, const std::vector<U>& v) {
     *dptr = nullptr;
-    const size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(U);
+    // 64 elements of slack: the interpreter prefetches tape lines a little past the end
+    const size_t bytes = (std::max<size_t>(v.size(), 1) + 64) * sizeof(U);
     CU(ctx, cudaMalloc(reinterpret_cast<void**>(dptr), bytes));
     if (!v.empty()) CU(ctx, cudaMemcpyAsync(*dptr, v.data(), v.size() * sizeof(U), cudaMemcpyHostToDevice, ctx->stream));
     return DEX_OK;
@@ -199,9 +201,16 @@ int run_eval(dex_ctx* ctx, const dex_population* cpop, const void* X, int32_t F,
         return set_err(ctx, DEX_ERR_UNSUPPORTED,
                        "nfeatures + stack rows = " + std::to_string(F + h.max_stack) +
                            " do not fit in shared memory");
-    // enough CTAs for ~4 waves of 8 resident CTAs per SM, never more chunks than trees
+    // Chunking policy.  (a) enough CTAs for ~4 waves of 8 resident CTAs per SM; (b) chunks of at
+    // most ~chunk_instr tape instructions: CTAs are dispatched tile-fastest, so with short
+    // chunks the CTAs running at any moment write the rows of only a few dozen trees — the
+    // output pages they touch stay within TLB reach (with 10^3 trees per chunk every store
+    // after a tree switch is a page walk, and a 42 GB result costs +70 % time).
     const int64_t want = (int64_t)ctx->sm_count * 8 * 4;
     int64_t n_chunks = std::max<int64_t>(1, (want + n_tiles - 1) / n_tiles);
+    int64_t chunk_instr = 128;
+    if (const char* env = getenv("DEXB200_CHUNK_INSTR")) chunk_instr = std::max<int64_t>(1, atoll(env));
+    n_chunks = std::max<int64_t>(n_chunks, ((int64_t)h.tape.size() + chunk_instr - 1) / chunk_instr);
     n_chunks = std::min<int64_t>(n_chunks, std::min<int64_t>(h.n_trees, 65535));
     EvalArgs a{};
     a.dtype = h.dtype;

@@ -40,6 +40,9 @@
 #ifndef DEX_MIN_CTAS
 #define DEX_MIN_CTAS 3
 #endif
+#ifndef DEX_PACKED_FP32
+#define DEX_PACKED_FP32 1
+#endif
 #ifndef DEX_MAX_THREADS
 #define DEX_MAX_THREADS 256
 #endif
@@ -69,6 +72,90 @@ DEX_UNARY_OPS(X1)
     template <typename T> struct Op2<DEX_OP_##SYM, T> { static __device__ __forceinline__ T f(T x, T y) { return (VEXPR); } };
 DEX_BINARY_OPS(X2)
 #undef X2
+
+// ---- vector-level operator application ------------------------------------------------
+// out[k] = op(x[k]) / op(x[k], y[k]) over the K samples of a thread.  The generic form is the
+// scalar functor unrolled K times.  For Float32 the cheap arithmetic operators and sin/cos use
+// Blackwell's packed FP32 instructions (FADD2 / FMUL2 / FFMA2 via __fadd2_rn / __fmul2_rn /
+// __ffma2_rn: two IEEE-754 single-precision operations per issued instruction, bit-identical
+// to the scalar forms) — the kernel is issue-bound, so halving the instruction count of the
+// arithmetic is a direct win.
+template <int OPC, typename T, int K> struct VOp1 {
+    static __device__ __forceinline__ void f(T* out, const T* x) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) out[k] = Op1<OPC, T>::f(x[k]);
+    }
+};
+template <int OPC, typename T, int K> struct VOp2 {
+    static __device__ __forceinline__ void f(T* out, const T* x, const T* y) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) out[k] = Op2<OPC, T>::f(x[k], y[k]);
+    }
+};
+#if DEX_PACKED_FP32
+__device__ __forceinline__ float2 f2(const float* p) { return make_float2(p[0], p[1]); }
+template <int K> struct VOp2<DEX_OP_ADD, float, K> {
+    static __device__ __forceinline__ void f(float* out, const float* x, const float* y) {
+#pragma unroll
+        for (int k = 0; k < K; k += 2) { const float2 r = __fadd2_rn(f2(x + k), f2(y + k)); out[k] = r.x; out[k + 1] = r.y; }
+    }
+};
+template <int K> struct VOp2<DEX_OP_SUB, float, K> {
+    static __device__ __forceinline__ void f(float* out, const float* x, const float* y) {
+#pragma unroll
+        for (int k = 0; k < K; k += 2) {
+            const float2 r = __fadd2_rn(f2(x + k), make_float2(-y[k], -y[k + 1]));
+            out[k] = r.x; out[k + 1] = r.y;
+        }
+    }
+};
+template <int K> struct VOp2<DEX_OP_MUL, float, K> {
+    static __device__ __forceinline__ void f(float* out, const float* x, const float* y) {
+#pragma unroll
+        for (int k = 0; k < K; k += 2) { const float2 r = __fmul2_rn(f2(x + k), f2(y + k)); out[k] = r.x; out[k + 1] = r.y; }
+    }
+};
+// packed sin/cos: the same algorithm as fast_sincosf (dex_ops.cuh) on pairs; rint() by the
+// 1.5*2^23 magic-number add (exact for |x * 2/pi| < 2^22), quadrant from the low mantissa bits.
+template <int QADD, int K> __device__ __forceinline__ void sincos_packed(float* out, const float* x) {
+    float big = 0.f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) big = fmaxf(big, fabsf(x[k]));
+    if (!(big <= 105615.0f)) {   // some sample needs Payne-Hanek (or is NaN/Inf): scalar path for all
+#pragma unroll
+        for (int k = 0; k < K; ++k) out[k] = QADD ? m_cos(x[k]) : m_sin(x[k]);
+        return;
+    }
+    const float2 MAGIC = make_float2(12582912.0f, 12582912.0f);
+#pragma unroll
+    for (int k = 0; k < K; k += 2) {
+        const float2 xx = f2(x + k);
+        const float2 m = __ffma2_rn(xx, make_float2(0.636619772367581343f, 0.636619772367581343f), MAGIC);
+        const float2 j = __fadd2_rn(m, make_float2(-12582912.0f, -12582912.0f));
+        const float2 nj = make_float2(-j.x, -j.y);
+        float2 r = __ffma2_rn(nj, make_float2(1.5707962513e+00f, 1.5707962513e+00f), xx);
+        r = __ffma2_rn(nj, make_float2(7.5497894159e-08f, 7.5497894159e-08f), r);
+        r = __ffma2_rn(nj, make_float2(5.3903029534e-15f, 5.3903029534e-15f), r);
+        const float2 z = __fmul2_rn(r, r);
+        float2 sp = __ffma2_rn(z, make_float2(-1.9515295891e-4f, -1.9515295891e-4f), make_float2(8.3321608736e-3f, 8.3321608736e-3f));
+        sp = __ffma2_rn(sp, z, make_float2(-1.6666654611e-1f, -1.6666654611e-1f));
+        sp = __ffma2_rn(__fmul2_rn(sp, z), r, r);
+        float2 cp = __ffma2_rn(z, make_float2(2.443315711809948e-5f, 2.443315711809948e-5f), make_float2(-1.388731625493765e-3f, -1.388731625493765e-3f));
+        cp = __ffma2_rn(cp, z, make_float2(4.166664568298827e-2f, 4.166664568298827e-2f));
+        cp = __ffma2_rn(__fmul2_rn(cp, z), z, __ffma2_rn(z, make_float2(-0.5f, -0.5f), make_float2(1.0f, 1.0f)));
+        const int q0 = __float_as_int(m.x) + QADD, q1 = __float_as_int(m.y) + QADD;
+        const float v0 = (q0 & 1) ? cp.x : sp.x, v1 = (q1 & 1) ? cp.y : sp.y;
+        out[k] = __int_as_float(__float_as_int(v0) ^ ((q0 & 2) << 30));
+        out[k + 1] = __int_as_float(__float_as_int(v1) ^ ((q1 & 2) << 30));
+    }
+}
+template <int K> struct VOp1<DEX_OP_SIN, float, K> {
+    static __device__ __forceinline__ void f(float* out, const float* x) { sincos_packed<0, K>(out, x); }
+};
+template <int K> struct VOp1<DEX_OP_COS, float, K> {
+    static __device__ __forceinline__ void f(float* out, const float* x) { sincos_packed<1, K>(out, x); }
+};
+#endif
 
 template <typename T> __device__ __forceinline__ T const_of(const uint4& ins);
 template <> __device__ __forceinline__ float const_of<float>(const uint4& ins) { return __uint_as_float(ins.z); }
@@ -120,6 +207,15 @@ __device__ __forceinline__ void check(T (&nf)[2], const Vec<T, U>& r) {
 #pragma unroll
     for (int k = 0; k < Vec<T, U>::K; ++k) nf[k & 1] = m_fma(r.v[k], T(0), nf[k & 1]);
 }
+#if DEX_PACKED_FP32
+template <int U>
+__device__ __forceinline__ void check(float (&nf)[2], const Vec<float, U>& r) {
+    float2 a = make_float2(nf[0], nf[1]);
+#pragma unroll
+    for (int k = 0; k < Vec<float, U>::K; k += 2) a = __ffma2_rn(f2(&r.v[k]), make_float2(0.f, 0.f), a);
+    nf[0] = a.x; nf[1] = a.y;
+}
+#endif
 
 template <typename T, int U, bool FAST, bool PARAM, bool LOSS>
 __global__ void __launch_bounds__(DEX_MAX_THREADS, DEX_MIN_CTAS) eval_kernel(const KArgs<T> a) {
@@ -219,10 +315,18 @@ __global__ void __launch_bounds__(DEX_MAX_THREADS, DEX_MIN_CTAS) eval_kernel(con
         for (int pc = 0; pc < n; ++pc) {
             uint4 nxt = ins;
             if (pc + 1 < n) nxt = __ldg(ip + pc + 1);  // prefetch the next instruction
+            // pull the tape line two lines (16 instructions) ahead into L1: with thousands of
+            // trees per CTA the tape no longer stays L1-resident and an L2 miss per line would
+            // otherwise be exposed (tapes of consecutive trees are contiguous; the buffer is
+            // padded, so running past this tree's end just prefetches the next tree)
+            if ((pc & 7) == 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(ip + pc + 16));
             const uint32_t w0 = ins.x;
             const T* ra = my + (size_t)(ins.y & 0xfffu) * TILE;
             const T* rb = my + (size_t)((ins.y >> 12) & 0xfffu) * TILE;
             const T c = const_of<T>(ins);
+            V cv;  // the inline constant broadcast over the K samples
+#pragma unroll
+            for (int k = 0; k < K; ++k) cv.v[k] = c;
             if (w0 & F_PUSH) st_row<T, U>(my + (size_t)(ins.y >> 24) * TILE, CS, acc);
 
             const uint32_t h = FAST ? (w0 & 0xffu) : (uint32_t)H_GENERIC;
@@ -252,13 +356,13 @@ __global__ void __launch_bounds__(DEX_MAX_THREADS, DEX_MIN_CTAS) eval_kernel(con
                 } HANDLER_END
 #define UNARY_HANDLERS(S)                                                          \
     case H_##S##_A: {                                                              \
-        _Pragma("unroll") for (int k = 0; k < K; ++k) acc.v[k] = Op1<DEX_OP_##S, T>::f(acc.v[k]); \
+        VOp1<DEX_OP_##S, T, K>::f(acc.v, acc.v);                                   \
     } HANDLER_END                                                                  \
     case H_##S##_R: {                                                              \
         V x;                                                                       \
         ld_row<T, U>(x, ra, CS);                                                   \
         if (w0 & F_CHK_A) check<T, U>(nf, x);                                      \
-        _Pragma("unroll") for (int k = 0; k < K; ++k) acc.v[k] = Op1<DEX_OP_##S, T>::f(x.v[k]); \
+        VOp1<DEX_OP_##S, T, K>::f(acc.v, x.v);                                     \
     } HANDLER_END
                 DEX_FAST_UNARY(UNARY_HANDLERS)
 #undef UNARY_HANDLERS
@@ -266,44 +370,44 @@ __global__ void __launch_bounds__(DEX_MAX_THREADS, DEX_MIN_CTAS) eval_kernel(con
     case H_##S##_AR: {                                                             \
         V y;                                                                       \
         ld_row<T, U>(y, rb, CS);                                                   \
-        _Pragma("unroll") for (int k = 0; k < K; ++k) acc.v[k] = Op2<DEX_OP_##S, T>::f(acc.v[k], y.v[k]); \
+        VOp2<DEX_OP_##S, T, K>::f(acc.v, acc.v, y.v);                              \
     } HANDLER_END
 #define BIN_RA(S)                                                                  \
     case H_##S##_RA: {                                                             \
         V x;                                                                       \
         ld_row<T, U>(x, ra, CS);                                                   \
-        _Pragma("unroll") for (int k = 0; k < K; ++k) acc.v[k] = Op2<DEX_OP_##S, T>::f(x.v[k], acc.v[k]); \
+        VOp2<DEX_OP_##S, T, K>::f(acc.v, x.v, acc.v);                              \
     } HANDLER_END
 #define BIN_AC(S)                                                                  \
     case H_##S##_AC: {                                                             \
         if (w0 & F_CHK_CONST) nf[0] = m_fma(c, T(0), nf[0]);                       \
-        _Pragma("unroll") for (int k = 0; k < K; ++k) acc.v[k] = Op2<DEX_OP_##S, T>::f(acc.v[k], c); \
+        VOp2<DEX_OP_##S, T, K>::f(acc.v, acc.v, cv.v);                             \
     } HANDLER_END
 #define BIN_CA(S)                                                                  \
     case H_##S##_CA: {                                                             \
         if (w0 & F_CHK_CONST) nf[0] = m_fma(c, T(0), nf[0]);                       \
-        _Pragma("unroll") for (int k = 0; k < K; ++k) acc.v[k] = Op2<DEX_OP_##S, T>::f(c, acc.v[k]); \
+        VOp2<DEX_OP_##S, T, K>::f(acc.v, cv.v, acc.v);                             \
     } HANDLER_END
 #define BIN_RR(S)                                                                  \
     case H_##S##_RR: {                                                             \
         V x, y;                                                                    \
         ld_row<T, U>(x, ra, CS);                                                   \
         ld_row<T, U>(y, rb, CS);                                                   \
-        _Pragma("unroll") for (int k = 0; k < K; ++k) acc.v[k] = Op2<DEX_OP_##S, T>::f(x.v[k], y.v[k]); \
+        VOp2<DEX_OP_##S, T, K>::f(acc.v, x.v, y.v);                                \
     } HANDLER_END
 #define BIN_RC(S)                                                                  \
     case H_##S##_RC: {                                                             \
         V x;                                                                       \
         ld_row<T, U>(x, ra, CS);                                                   \
         if (w0 & F_CHK_CONST) nf[0] = m_fma(c, T(0), nf[0]);                       \
-        _Pragma("unroll") for (int k = 0; k < K; ++k) acc.v[k] = Op2<DEX_OP_##S, T>::f(x.v[k], c); \
+        VOp2<DEX_OP_##S, T, K>::f(acc.v, x.v, cv.v);                               \
     } HANDLER_END
 #define BIN_CR(S)                                                                  \
     case H_##S##_CR: {                                                             \
         V y;                                                                       \
         ld_row<T, U>(y, rb, CS);                                                   \
         if (w0 & F_CHK_CONST) nf[0] = m_fma(c, T(0), nf[0]);                       \
-        _Pragma("unroll") for (int k = 0; k < K; ++k) acc.v[k] = Op2<DEX_OP_##S, T>::f(c, y.v[k]); \
+        VOp2<DEX_OP_##S, T, K>::f(acc.v, cv.v, y.v);                               \
     } HANDLER_END
 #define COMM_HANDLERS(S) BIN_AR(S) BIN_AC(S) BIN_RR(S) BIN_RC(S)
 #define NC_HANDLERS(S) BIN_AR(S) BIN_RA(S) BIN_AC(S) BIN_CA(S) BIN_RR(S) BIN_RC(S) BIN_CR(S)

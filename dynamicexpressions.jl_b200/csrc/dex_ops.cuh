@@ -52,8 +52,12 @@ static __device__ __noinline__ double slow_sin(double x) { return sin(x); }
 static __device__ __noinline__ double slow_cos(double x) { return cos(x); }
 
 template <int QADD> __device__ __forceinline__ float fast_sincosf(float x) {
-    const float j = rintf(x * 0.636619772367581343f);  // x * 2/pi
-    const int q = __float2int_rn(j) + QADD;
+    // j = rint(x * 2/pi) by the 1.5 * 2^23 magic-number add (exact for |x * 2/pi| < 2^22); the
+    // quadrant is in the low mantissa bits of m.  Must stay bit-identical to sincos_packed
+    // (dex_eval.cu), which evaluates the same formula on pairs with FFMA2.
+    const float m = fmaf(x, 0.636619772367581343f, 12582912.0f);
+    const float j = m - 12582912.0f;
+    const int q = __float_as_int(m) + QADD;
     float r = fmaf(-j, 1.5707962513e+00f, x);
     r = fmaf(-j, 7.5497894159e-08f, r);
     r = fmaf(-j, 5.3903029534e-15f, r);
