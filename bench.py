@@ -106,10 +106,18 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def host_cores():
+    """Host threads this process may use (torchrun exports OMP_NUM_THREADS=1, so ask the OS)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
 def cpu_baseline(nodes, offsets, opcodes, X_nf, budget_s=10.0):
     """The oracle timed on this box: all threads, the whole workload repeated for ~budget_s."""
     from oracle import oracle
-    cores = oracle.max_threads()
+    cores = host_cores()
     X = np.ascontiguousarray(X_nf.T)        # (F, N) view the wrapper expects
     out = np.empty((N_TREES, X.shape[1]), np.float32)
     oracle.eval_population(nodes, offsets, opcodes, X, nthreads=cores, out=out)      # warm-up
@@ -139,7 +147,7 @@ def run_reference(args, rank, world):
     nodes, offsets = workload()
     ops = dexb200.OperatorEnum(treegen.OPSET_A)
     X = np.ascontiguousarray(make_X(0).T)
-    cores = oracle.max_threads()
+    cores = host_cores()
     # each step: the whole workload (it takes ~0.1 s on a multi-core host)
     ns = NSAMPLES
     Xs = np.ascontiguousarray(X[:, :ns])

@@ -47,11 +47,9 @@ struct dex_population {
     int device = -1;
     Instr* d_tape = nullptr;
     int64_t* d_tape_off = nullptr;
-    GInstr* d_gtape = nullptr;
-    int64_t* d_gtape_off = nullptr;
+    int32_t* d_const_ord = nullptr;
     int64_t* d_const_off = nullptr;
     int64_t* d_const_pos = nullptr;
-    int64_t* d_gconst_pos = nullptr;
     std::map<int32_t, int32_t*> chunk_tables;  // n_chunks -> device table
     std::map<std::string, int64_t*> grad_off_tables;
 };
@@ -144,14 +142,14 @@ int upload(dex_ctx* ctx, U** dptr, const std::vector<U>& v) {
 }
 
 // tree-index ranges with balanced tape length
-int chunk_table(dex_ctx* ctx, dex_population* pop, int32_t n_chunks, const int32_t** out, bool grad = false) {
-    const int32_t key = grad ? -n_chunks : n_chunks;
+int chunk_table(dex_ctx* ctx, dex_population* pop, int32_t n_chunks, const int32_t** out) {
+    const int32_t key = n_chunks;
     auto it = pop->chunk_tables.find(key);
     if (it != pop->chunk_tables.end()) { *out = it->second; return DEX_OK; }
     const PackedPopulation& h = pop->h;
     std::vector<int32_t> tab((size_t)n_chunks + 1, 0);
     // cost of trees [0, t) = tape instructions + a fixed per-tree cost of one
-    const std::vector<int64_t>& toff = grad ? h.gtape_off : h.tape_off;
+    const std::vector<int64_t>& toff = h.tape_off;
     auto cum = [&](int64_t t) { return toff[(size_t)t] + t; };
     const int64_t total = cum(h.n_trees);
     int64_t t = 0;
@@ -382,11 +380,9 @@ int dex_population_pack(dex_ctx* ctx, const dex_optable* ops, const dex_node* no
         rc = ensure_device(ctx);
         if (!rc) rc = upload(ctx, &pop->d_tape, pop->h.tape);
         if (!rc) rc = upload(ctx, &pop->d_tape_off, pop->h.tape_off);
-        if (!rc) rc = upload(ctx, &pop->d_gtape, pop->h.gtape);
-        if (!rc) rc = upload(ctx, &pop->d_gtape_off, pop->h.gtape_off);
+        if (!rc) rc = upload(ctx, &pop->d_const_ord, pop->h.tape_const_ord);
         if (!rc) rc = upload(ctx, &pop->d_const_off, pop->h.const_off);
         if (!rc) rc = upload(ctx, &pop->d_const_pos, pop->h.const_pos);
-        if (!rc) rc = upload(ctx, &pop->d_gconst_pos, pop->h.gconst_pos);
         if (!rc && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = set_err(ctx, DEX_ERR_CUDA, "tape upload failed");
         if (rc) { dex_population_destroy(pop); return rc; }
     }
@@ -398,9 +394,8 @@ int dex_population_destroy(dex_population* pop) {
     if (!pop) return DEX_OK;
     if (pop->device >= 0) {
         cudaSetDevice(pop->device);
-        cudaFree(pop->d_tape); cudaFree(pop->d_tape_off); cudaFree(pop->d_gtape);
-        cudaFree(pop->d_gtape_off); cudaFree(pop->d_const_off); cudaFree(pop->d_const_pos);
-        cudaFree(pop->d_gconst_pos);
+        cudaFree(pop->d_tape); cudaFree(pop->d_tape_off); cudaFree(pop->d_const_ord);
+        cudaFree(pop->d_const_off); cudaFree(pop->d_const_pos);
         for (auto& kv : pop->chunk_tables) cudaFree(kv.second);
         for (auto& kv : pop->grad_off_tables) cudaFree(kv.second);
     }
@@ -476,10 +471,8 @@ int dex_population_set_constants(dex_ctx* ctx, dex_population* pop, const void* 
     // host image
     for (int64_t k = 0; k < n_values; ++k) {
         Instr& ins = pop->h.tape[(size_t)pop->h.const_pos[(size_t)k]];
-        GInstr& g = pop->h.gtape[(size_t)pop->h.gconst_pos[(size_t)k]];
         if (es == 4) { std::memcpy(&ins.c_lo, static_cast<const float*>(values_host) + k, 4); ins.c_hi = 0; }
         else { uint64_t u; std::memcpy(&u, static_cast<const double*>(values_host) + k, 8); ins.c_lo = (uint32_t)u; ins.c_hi = (uint32_t)(u >> 32); }
-        g.c_lo = ins.c_lo; g.c_hi = ins.c_hi;
     }
     if (pop->device < 0 || n_values == 0) return DEX_OK;
     int rc = ensure_device(ctx);
@@ -488,8 +481,8 @@ int dex_population_set_constants(dex_ctx* ctx, dex_population* pop, const void* 
     if ((rc = ensure_dev_io(ctx, (size_t)n_values * es))) return rc;
     std::memcpy(ctx->pinned, values_host, (size_t)n_values * es);
     CU(ctx, cudaMemcpyAsync(ctx->dev_io, ctx->pinned, (size_t)n_values * es, cudaMemcpyHostToDevice, ctx->stream));
-    cudaError_t e = launch_scatter_constants(pop->h.dtype, pop->d_tape, pop->d_const_pos, pop->d_gtape,
-                                             pop->d_gconst_pos, ctx->dev_io, n_values, ctx->stream);
+    cudaError_t e = launch_scatter_constants(pop->h.dtype, pop->d_tape, pop->d_const_pos, ctx->dev_io,
+                                             n_values, ctx->stream);
     if (e != cudaSuccess) return cuda_err(ctx, e, "scatter constants");
     ctx->launches += 1;
     CU(ctx, cudaStreamSynchronize(ctx->stream));  // pinned staging is reused by later calls
@@ -579,18 +572,21 @@ static int run_grad(dex_ctx* ctx, const dex_population* cpop, const void* X, int
         for (int32_t c : h.n_const_tree) ncmax = std::max(ncmax, c);
         Gmax = mode == DEX_GRAD_FEATURES ? F : mode == DEX_GRAD_CONSTANTS ? ncmax : F + ncmax;
     }
-    const int64_t n_tiles = grad_num_tiles(h.dtype, F, h.max_gstack, Gmax, N);
+    const int64_t n_tiles = grad_num_tiles(h.dtype, F, h.max_stack, Gmax, N);
     const int64_t want = (int64_t)ctx->sm_count * 8 * 4;
     int64_t n_chunks = std::max<int64_t>(1, (want + n_tiles - 1) / n_tiles);
+    n_chunks = std::max<int64_t>(n_chunks, ((int64_t)h.tape.size() + 127) / 128);
     n_chunks = std::min<int64_t>(n_chunks, std::min<int64_t>(h.n_trees, 65535));
     const int32_t* chunks = nullptr;
-    int rc = chunk_table(ctx, pop, (int32_t)n_chunks, &chunks, true);
+    int rc = chunk_table(ctx, pop, (int32_t)n_chunks, &chunks);
     if (rc) return rc;
+    if ((rc = ensure_xt(ctx, grad_xt_bytes(h.dtype, F, h.max_stack, Gmax, N)))) return rc;
     GradArgs a{};
     a.dtype = h.dtype;
-    a.gtape = pop->d_gtape; a.gtape_off = pop->d_gtape_off; a.const_off = pop->d_const_off;
-    a.n_trees = h.n_trees; a.max_gstack = h.max_gstack;
-    a.X = X; a.F = F; a.N = N; a.ldx = ldx; a.mode = mode; a.direction = direction;
+    a.tape = pop->d_tape; a.tape_off = pop->d_tape_off; a.const_ord = pop->d_const_ord;
+    a.const_off = pop->d_const_off;
+    a.n_trees = h.n_trees; a.max_stack = h.max_stack;
+    a.X = X; a.xt = ctx->xt; a.F = F; a.N = N; a.ldx = ldx; a.mode = mode; a.direction = direction;
     a.out = out; a.ldo = ldo; a.grad = grad; a.ok = ok; a.grad_off = nullptr;
     if (mode >= 0) {
         const size_t bytes = (size_t)(h.n_trees + 1) * sizeof(int64_t);

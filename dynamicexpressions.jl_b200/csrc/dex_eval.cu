@@ -548,8 +548,7 @@ __global__ void transpose_pad_kernel(const T* __restrict__ X, int64_t ldx, int F
 }
 
 template <typename T>
-__global__ void scatter_constants_kernel(Instr* tape, const int64_t* pos, GInstr* gtape,
-                                         const int64_t* gpos, const T* values, int64_t n) {
+__global__ void scatter_constants_kernel(Instr* tape, const int64_t* pos, const T* values, int64_t n) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const T v = values[i];
@@ -557,7 +556,6 @@ __global__ void scatter_constants_kernel(Instr* tape, const int64_t* pos, GInstr
     if (sizeof(T) == 4) { lo = __float_as_uint((float)v); hi = 0; }
     else { lo = (uint32_t)__double2loint((double)v); hi = (uint32_t)__double2hiint((double)v); }
     if (pos[i] >= 0) { tape[pos[i]].c_lo = lo; tape[pos[i]].c_hi = hi; }
-    if (gpos[i] >= 0) { gtape[gpos[i]].c_lo = lo; gtape[gpos[i]].c_hi = hi; }
 }
 
 __global__ void loss_reduce_kernel(const double* partial, int64_t n_tiles, int64_t n_trees,
@@ -672,15 +670,14 @@ cudaError_t launch_eval(const EvalArgs& e, cudaStream_t stream, int sm_count, in
     return err;
 }
 
-cudaError_t launch_scatter_constants(int dtype, Instr* tape, const int64_t* pos, GInstr* gtape,
-                                     const int64_t* gpos, const void* values, int64_t n,
-                                     cudaStream_t stream) {
+cudaError_t launch_scatter_constants(int dtype, Instr* tape, const int64_t* pos, const void* values,
+                                     int64_t n, cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
     const unsigned blocks = (unsigned)((n + 255) / 256);
     if (dtype == DEX_F32)
-        scatter_constants_kernel<float><<<blocks, 256, 0, stream>>>(tape, pos, gtape, gpos, static_cast<const float*>(values), n);
+        scatter_constants_kernel<float><<<blocks, 256, 0, stream>>>(tape, pos, static_cast<const float*>(values), n);
     else
-        scatter_constants_kernel<double><<<blocks, 256, 0, stream>>>(tape, pos, gtape, gpos, static_cast<const double*>(values), n);
+        scatter_constants_kernel<double><<<blocks, 256, 0, stream>>>(tape, pos, static_cast<const double*>(values), n);
     return cudaGetLastError();
 }
 

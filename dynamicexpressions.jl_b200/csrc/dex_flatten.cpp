@@ -34,7 +34,6 @@ struct Flattener {
     int64_t tree_index = 0;
     int64_t const_base = 0;  // global ordinal of this tree's first constant
     int max_slot = 0;        // slots used by the tree being emitted
-    int max_gslot = 0;
 
     Flattener(const OpTable& o, int dt, int pack_flags, PackedPopulation& p, std::string& e)
         : ops(o), dtype(dt), fused((pack_flags & DEX_PACK_FUSED) != 0),
@@ -463,6 +462,7 @@ struct Flattener {
             const int64_t idx = (int64_t)out.tape.size();
             if (e.a.src == SRC_CONST) { put_const(ins, e.a.c); if (e.a.cord >= 0) out.const_pos[const_base + e.a.cord] = idx; }
             if (e.b.src == SRC_CONST) { put_const(ins, e.b.c); if (e.b.cord >= 0) out.const_pos[const_base + e.b.cord] = idx; }
+            out.tape_const_ord.push_back(e.a.src == SRC_CONST ? e.a.cord : e.b.src == SRC_CONST ? e.b.cord : -1);
             if (h == H_GENERIC) ++out.n_generic;
             out.n_checks += ((ins.w0 & F_CHK_OUT) ? 1 : 0) + (e.a.chk ? 1 : 0) + (e.b.chk ? 1 : 0);
             out.tape.push_back(ins);
@@ -471,41 +471,8 @@ struct Flattener {
     std::vector<uint8_t> rebase;  // per tape instruction: bit0 rowA is a feature, bit1 rowB is a feature
     bool elide = true;
 
-    // ---- gradient tape -----------------------------------------------------------------
-    void gemit(uint32_t w0, uint32_t w1, double c) {
-        GInstr g{};
-        g.w0 = w0;
-        g.w1 = w1;
-        Instr tmp{};
-        put_const(tmp, c);
-        g.c_lo = tmp.c_lo;
-        g.c_hi = tmp.c_hi;
-        out.gtape.push_back(g);
-    }
-    int ggen(int64_t i, int dst, int rec) {
-        if (rec > MAX_RECURSION) return fail(DEX_ERR_UNSUPPORTED, "tree too deep");
-        if (dst >= 65535) return fail(DEX_ERR_UNSUPPORTED, "gradient stack too deep");
-        max_gslot = std::max(max_gslot, dst + 1);
-        const dex_node& x = nd[i];
-        if (x.degree == 0) {
-            uint32_t w1 = x.kind == DEX_LEAF_CONST ? (uint32_t)cord[i] : (uint32_t)x.feature;
-            if (x.kind == DEX_LEAF_CONST) out.gconst_pos[const_base + cord[i]] = (int64_t)out.gtape.size();
-            gemit(0u | ((uint32_t)x.kind << 8) | ((uint32_t)dst << 16), w1, x.val);
-            return DEX_OK;
-        }
-        int64_t c = i + 1;
-        for (int k = 0; k < x.degree; ++k) {
-            int rc = ggen(c, dst + k, rec + 1);
-            if (rc) return rc;
-            c += size[c];
-        }
-        gemit((uint32_t)opcode(i) | ((uint32_t)dst << 16), 0, 0.0);
-        return DEX_OK;
-    }
-
     int run(const dex_node* nodes, const int64_t* offsets, int64_t n_trees) {
         out.tape_off.assign(1, 0);
-        out.gtape_off.assign(1, 0);
         out.const_off.assign(1, 0);
         for (int64_t t = 0; t < n_trees; ++t) {
             tree_index = t;
@@ -527,9 +494,7 @@ struct Flattener {
                 if (nd[i].degree == 0 && nd[i].kind == DEX_LEAF_CONST) cord[i] = nc++;
             const_base = out.n_constants;
             out.const_pos.resize((size_t)(const_base + nc), -1);
-            out.gconst_pos.resize((size_t)(const_base + nc), -1);
             max_slot = 0;
-            max_gslot = 0;
             cur.clear();
             last = -1;
             if (nd[0].degree == 0) {
@@ -540,16 +505,13 @@ struct Flattener {
                 return rc;
             }
             lower_tree();
-            if ((rc = ggen(0, 0, 0))) return rc;
             out.max_stack = std::max(out.max_stack, max_slot);
-            out.max_gstack = std::max(out.max_gstack, max_gslot);
             out.n_constants += nc;
             out.n_nodes += n;
             out.n_nodes_tree.push_back((int32_t)n);
             out.n_const_tree.push_back(nc);
             out.const_off.push_back(out.n_constants);
             out.tape_off.push_back((int64_t)out.tape.size());
-            out.gtape_off.push_back((int64_t)out.gtape.size());
         }
         // rebase feature rows behind the stack rows
         const uint32_t base = (uint32_t)out.max_stack;

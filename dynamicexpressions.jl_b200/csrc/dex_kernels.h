@@ -47,12 +47,14 @@ int64_t eval_num_tiles(int dtype, int32_t F, int32_t max_stack, int64_t N, int* 
 
 struct GradArgs {
     int dtype;
-    const GInstr* gtape;        // device
-    const int64_t* gtape_off;   // device, n_trees + 1
+    const Instr* tape;          // device: the evaluation tape
+    const int64_t* tape_off;    // device, n_trees + 1
+    const int32_t* const_ord;   // device, per tape instruction: tree-local constant ordinal or -1
     const int64_t* const_off;   // device, n_trees + 1 (constant ordinal base per tree)
     int64_t n_trees;
-    int32_t max_gstack;
+    int32_t max_stack;
     const void* X;
+    void* xt;                   // device scratch >= grad_xt_bytes()
     int32_t F;
     int64_t N;
     int64_t ldx;
@@ -67,12 +69,12 @@ struct GradArgs {
 // chunk_start: device table of n_chunks + 1 tree indices; Gmax: largest gradient count of any tree
 cudaError_t launch_grad_ex(const GradArgs& a, const int32_t* chunk_start, int n_chunks, int Gmax,
                            cudaStream_t stream, int* launches);
-int64_t grad_num_tiles(int dtype, int F, int max_gstack, int Gmax, int64_t N);
+int64_t grad_num_tiles(int dtype, int F, int max_stack, int Gmax, int64_t N);
+size_t grad_xt_bytes(int dtype, int F, int max_stack, int Gmax, int64_t N);
 
 // tiny helpers
-cudaError_t launch_scatter_constants(int dtype, Instr* tape, const int64_t* pos, GInstr* gtape,
-                                     const int64_t* gpos, const void* values, int64_t n,
-                                     cudaStream_t stream);
+cudaError_t launch_scatter_constants(int dtype, Instr* tape, const int64_t* pos, const void* values,
+                                     int64_t n, cudaStream_t stream);
 cudaError_t launch_loss_reduce(const double* partial, int64_t n_tiles, int64_t n_trees,
                                double denom_inv, double* loss, cudaStream_t stream);
 

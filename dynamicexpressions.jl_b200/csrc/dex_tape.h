@@ -90,22 +90,6 @@ enum Handler : uint32_t {
     H__COUNT
 };
 
-// ---- gradient tape ---------------------------------------------------------------
-// Unfused post-order stack machine (the reference's derivative evaluator has no
-// fused kernels, /root/reference/src/EvaluateDerivative.jl:262-365): every leaf is
-// a LOAD that pushes (value, one-hot gradient seed), every operator pops its
-// operands and pushes (value, gradient).  16 bytes.
-//   w0 [ 7: 0] opcode (0 = LOAD)   [ 9: 8] leaf kind (LOAD only: 0 const, 1 feature, 2 parameter)
-//      [31:16] dst stack slot (operands of an n-ary op are slots dst .. dst+n-1)
-//   w1 leaf: feature / parameter index, or constant ordinal (0-based, leaf order)
-//   c  constant value
-struct GInstr {
-    uint32_t w0;
-    uint32_t w1;
-    uint32_t c_lo;
-    uint32_t c_hi;
-};
-
 // ---- host-side description of a packed population ----------------------------------
 struct OpTable {
     std::vector<int32_t> ops[3];  // builtin opcodes per degree
@@ -118,21 +102,18 @@ struct PackedPopulation {
     int64_t n_nodes = 0;
     int64_t n_constants = 0;
     int32_t max_stack = 0;       // eval tape stack rows
-    int32_t max_gstack = 0;      // grad tape stack slots
     int32_t max_feature = -1;
     int32_t max_parameter = -1;
     int64_t n_generic = 0;       // instructions that take the generic handler
     int64_t n_checks = 0;        // validity checks left after elision
     std::vector<Instr> tape;               // all trees, concatenated
     std::vector<int64_t> tape_off;         // n_trees + 1
-    std::vector<GInstr> gtape;
-    std::vector<int64_t> gtape_off;        // n_trees + 1
+    std::vector<int32_t> tape_const_ord;   // per instruction: tree-local ordinal of its inline constant, -1 if none
     std::vector<int32_t> n_nodes_tree;     // count_nodes per tree
     std::vector<int32_t> n_const_tree;     // count_constant_nodes per tree
     std::vector<int64_t> const_off;        // n_trees + 1 (prefix of n_const_tree)
-    // constant ordinal (global) -> instruction index in tape / gtape holding its value
+    // constant ordinal (global) -> instruction index in the tape holding its value
     std::vector<int64_t> const_pos;
-    std::vector<int64_t> gconst_pos;
 };
 
 // Flatten `n_trees` wire trees.  Returns 0 or a negative DEX_ERR_* code with a

@@ -219,8 +219,8 @@ int dexo_max_threads(void) {
 #endif
 }
 static int pick_threads(int nthreads) {
-    int m = dexo_max_threads();
-    return (nthreads <= 0 || nthreads > m) ? m : nthreads;
+    /* an explicit count wins (torchrun exports OMP_NUM_THREADS=1); <= 0 means the OpenMP default */
+    return nthreads > 0 ? nthreads : dexo_max_threads();
 }
 
 int dexo_eval_population(const dex_node* nodes, const int64_t* offsets, int64_t n_trees,
