@@ -60,6 +60,85 @@ template <typename T, int K> __device__ __forceinline__ void stv(T* p, const T (
 // how the derivative of an operand is obtained
 enum : int { DK_ACC = 0, DK_SLOT = 1, DK_LEAF = 2 };
 
+// d = p * x   and   d = d + p * x   over the K samples of a thread.  Products and the sum are
+// rounded separately, like the reference's `grad_1 * d_1 + grad_2 * d_2`; Float32 uses
+// Blackwell's packed FMUL2 / FADD2 / FFMA2 (two IEEE operations per instruction).
+template <typename T, int K> struct DOps {
+    static __device__ __forceinline__ void mul(T (&d)[K], const T (&p)[K], const T (&x)[K]) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) d[k] = p[k] * x[k];
+    }
+    static __device__ __forceinline__ void mul_add(T (&d)[K], const T (&p)[K], const T (&x)[K]) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) d[k] = d[k] + p[k] * x[k];
+    }
+    static __device__ __forceinline__ void check(T& nf, const T (&d)[K]) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) nf = m_fma(d[k], T(0), nf);
+    }
+};
+template <int K> struct DOps<float, K> {
+    static __device__ __forceinline__ void mul(float (&d)[K], const float (&p)[K], const float (&x)[K]) {
+#pragma unroll
+        for (int k = 0; k < K; k += 2) {
+            const float2 r = __fmul2_rn(make_float2(p[k], p[k + 1]), make_float2(x[k], x[k + 1]));
+            d[k] = r.x; d[k + 1] = r.y;
+        }
+    }
+    static __device__ __forceinline__ void mul_add(float (&d)[K], const float (&p)[K], const float (&x)[K]) {
+#pragma unroll
+        for (int k = 0; k < K; k += 2) {
+            const float2 m = __fmul2_rn(make_float2(p[k], p[k + 1]), make_float2(x[k], x[k + 1]));
+            const float2 r = __fadd2_rn(make_float2(d[k], d[k + 1]), m);
+            d[k] = r.x; d[k + 1] = r.y;
+        }
+    }
+    static __device__ __forceinline__ void check(float& nf, const float (&d)[K]) {
+        float2 acc = make_float2(nf, 0.f);
+#pragma unroll
+        for (int k = 0; k < K; k += 2) acc = __ffma2_rn(make_float2(d[k], d[k + 1]), make_float2(0.f, 0.f), acc);
+        nf = acc.x + acc.y;
+    }
+};
+
+// derivative row g of one operand
+template <typename T, int GC, int K, int KIND>
+__device__ __forceinline__ void dsrc(T (&x)[K], const T (&ad)[GC][K], const T* drow, int idx, int TILE, int g) {
+    if (KIND == DK_ACC) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) x[k] = ad[g][k];
+    } else if (KIND == DK_SLOT) {
+        ldv<T, K>(x, drow + (size_t)(1 + g) * TILE);
+    } else {   // one-hot / zero seed of a leaf
+        const T e = (g == idx) ? T(1) : T(0);
+#pragma unroll
+        for (int k = 0; k < K; ++k) x[k] = e;
+    }
+}
+
+// ad[g] <- p0 * dA[g] (+ p1 * dB[g] (+ p2 * ad[g]))  for every direction of the pass
+template <typename T, int GC, int K, int DEG, int KA, int KB>
+__device__ __forceinline__ void combine(T (&ad)[GC][K], const T (&p)[3][K], const T* const (&drow)[3],
+                                        const int (&idx)[3], int TILE, T& nf, bool chk) {
+#pragma unroll
+    for (int g = 0; g < GC; ++g) {
+        T d[K], x[K];
+        dsrc<T, GC, K, KA>(x, ad, drow[0], idx[0], TILE, g);
+        DOps<T, K>::mul(d, p[0], x);
+        if (DEG >= 2) {
+            dsrc<T, GC, K, KB>(x, ad, drow[1], idx[1], TILE, g);
+            DOps<T, K>::mul_add(d, p[1], x);
+        }
+        if (DEG >= 3) {   // third operand is always ACC
+            dsrc<T, GC, K, DK_ACC>(x, ad, drow[2], idx[2], TILE, g);
+            DOps<T, K>::mul_add(d, p[2], x);
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) ad[g][k] = d[k];
+        if (chk) DOps<T, K>::check(nf, d);
+    }
+}
+
 template <typename T, int GC>
 __global__ void __launch_bounds__(128) grad_kernel(const GK<T> a) {
     constexpr int K = 16 / (int)sizeof(T);
@@ -204,35 +283,30 @@ __global__ void __launch_bounds__(128) grad_kernel(const GK<T> a) {
                     } break;
                 }
                 // ---- d[g] = sum_i p_i * d_i[g]   (grad_degn_eval :355-361), left to right ------
-#pragma unroll
-                for (int g = 0; g < GC; ++g) {
-                    T d[K];
-#pragma unroll
-                    for (int i = 0; i < 3; ++i) {
-                        if (i >= deg) continue;
-                        T di[K];
-                        if (dk[i] == DK_ACC) {
-#pragma unroll
-                            for (int k = 0; k < K; ++k) di[k] = ad[g][k];
-                        } else if (dk[i] == DK_SLOT) {
-                            ldv<T, K>(di, drow[i] + (size_t)(1 + g) * TILE);
-                        } else {
-                            const T e = (g == idx[i]) ? T(1) : T(0);
-#pragma unroll
-                            for (int k = 0; k < K; ++k) di[k] = e;
-                        }
-#pragma unroll
-                        for (int k = 0; k < K; ++k) {
-                            const T term = p[i][k] * di[k];
-                            d[k] = i == 0 ? term : d[k] + term;
-                        }
+                // the operand kinds are hoisted out of the direction loop: one branch-free,
+                // fully unrolled instance of `combine` per (kind A, kind B) pair
+                const bool chk = mode >= 0;
+                if (deg == 1) {
+                    switch (dk[0]) {
+                        case DK_ACC: combine<T, GC, K, 1, DK_ACC, DK_ACC>(ad, p, drow, idx, TILE, nf, chk); break;
+                        case DK_SLOT: combine<T, GC, K, 1, DK_SLOT, DK_ACC>(ad, p, drow, idx, TILE, nf, chk); break;
+                        default: combine<T, GC, K, 1, DK_LEAF, DK_ACC>(ad, p, drow, idx, TILE, nf, chk); break;
                     }
-#pragma unroll
-                    for (int k = 0; k < K; ++k) ad[g][k] = d[k];
-                    if (mode >= 0) {
-#pragma unroll
-                        for (int k = 0; k < K; ++k) nf = m_fma(d[k], T(0), nf);
-                    }
+                } else {
+#define COMBINE_PAIR(DEG)                                                                               \
+    switch (dk[0] * 3 + dk[1]) {                                                                        \
+        case DK_ACC * 3 + DK_SLOT: combine<T, GC, K, DEG, DK_ACC, DK_SLOT>(ad, p, drow, idx, TILE, nf, chk); break;   \
+        case DK_ACC * 3 + DK_LEAF: combine<T, GC, K, DEG, DK_ACC, DK_LEAF>(ad, p, drow, idx, TILE, nf, chk); break;   \
+        case DK_SLOT * 3 + DK_ACC: combine<T, GC, K, DEG, DK_SLOT, DK_ACC>(ad, p, drow, idx, TILE, nf, chk); break;   \
+        case DK_SLOT * 3 + DK_SLOT: combine<T, GC, K, DEG, DK_SLOT, DK_SLOT>(ad, p, drow, idx, TILE, nf, chk); break; \
+        case DK_SLOT * 3 + DK_LEAF: combine<T, GC, K, DEG, DK_SLOT, DK_LEAF>(ad, p, drow, idx, TILE, nf, chk); break; \
+        case DK_LEAF * 3 + DK_ACC: combine<T, GC, K, DEG, DK_LEAF, DK_ACC>(ad, p, drow, idx, TILE, nf, chk); break;   \
+        case DK_LEAF * 3 + DK_SLOT: combine<T, GC, K, DEG, DK_LEAF, DK_SLOT>(ad, p, drow, idx, TILE, nf, chk); break; \
+        case DK_LEAF * 3 + DK_LEAF: combine<T, GC, K, DEG, DK_LEAF, DK_LEAF>(ad, p, drow, idx, TILE, nf, chk); break; \
+        default: combine<T, GC, K, DEG, DK_ACC, DK_ACC>(ad, p, drow, idx, TILE, nf, chk); break;        \
+    }
+                    if (deg == 2) { COMBINE_PAIR(2) } else { COMBINE_PAIR(3) }
+#undef COMBINE_PAIR
                 }
 #pragma unroll
                 for (int k = 0; k < K; ++k) av[k] = vo[k];
