@@ -34,8 +34,8 @@
 #ifndef DEX_EVAL_U
 #define DEX_EVAL_U 2
 #endif
-#ifndef DEX_TAIL_DUP
-#define DEX_TAIL_DUP 0
+#ifndef DEX_PTX_INTERP
+#define DEX_PTX_INTERP 1
 #endif
 #ifndef DEX_MIN_CTAS
 #define DEX_MIN_CTAS 3
@@ -49,9 +49,7 @@
 #ifndef DEX_SYNC_TREE
 #define DEX_SYNC_TREE 0
 #endif
-#ifndef DEX_SYNC_INSTR
-#define DEX_SYNC_INSTR 0
-#endif
+
 
 namespace dex {
 
@@ -311,15 +309,8 @@ __global__ void __launch_bounds__(DEX_MAX_THREADS, DEX_MIN_CTAS) eval_kernel(con
 #pragma unroll
         for (int k = 0; k < K; ++k) acc.v[k] = T(0);
 
-        uint4 ins = __ldg(ip);
-        for (int pc = 0; pc < n; ++pc) {
-            uint4 nxt = ins;
-            if (pc + 1 < n) nxt = __ldg(ip + pc + 1);  // prefetch the next instruction
-            // pull the tape line two lines (16 instructions) ahead into L1: with thousands of
-            // trees per CTA the tape no longer stays L1-resident and an L2 miss per line would
-            // otherwise be exposed (tapes of consecutive trees are contiguous; the buffer is
-            // padded, so running past this tree's end just prefetches the next tree)
-            if ((pc & 7) == 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(ip + pc + 16));
+        // one tape instruction, C++ form (all handlers + the generic path)
+        auto step = [&](const uint4& ins) {
             const uint32_t w0 = ins.x;
             const T* ra = my + (size_t)(ins.y & 0xfffu) * TILE;
             const T* rb = my + (size_t)((ins.y >> 12) & 0xfffu) * TILE;
@@ -330,19 +321,7 @@ __global__ void __launch_bounds__(DEX_MAX_THREADS, DEX_MIN_CTAS) eval_kernel(con
             if (w0 & F_PUSH) st_row<T, U>(my + (size_t)(ins.y >> 24) * TILE, CS, acc);
 
             const uint32_t h = FAST ? (w0 & 0xffu) : (uint32_t)H_GENERIC;
-#if DEX_TAIL_DUP
-// every specialised handler carries its own copy of the loop tail, so the accumulator is
-// updated in place and no register shuffling is needed at a shared merge point
-#define HANDLER_END                                   \
-    if (w0 & F_CHK_OUT) check<T, U>(nf, acc);         \
-    ins = nxt;                                        \
-    continue;
-#else
 #define HANDLER_END break;
-#endif
-#if DEX_SYNC_INSTR
-            __syncthreads();  // experiment: keep the warps of a CTA on the same handler
-#endif
             switch (h) {
                 // ---- specialised handlers: one indirect branch, no operand decoding ----
                 case H_LOAD_R: {
@@ -487,12 +466,47 @@ __global__ void __launch_bounds__(DEX_MAX_THREADS, DEX_MIN_CTAS) eval_kernel(con
                         for (int k = 0; k < K; ++k) r.v[k] = lr[k];
                     }
                     acc = r;
-                    if (!chk) goto next_instruction;  // CHK_OUT below is unconditional for FAST
+                    if (!chk) return;  // CHK_OUT below is unconditional for FAST
                 } break;
             }
             if (w0 & F_CHK_OUT) check<T, U>(nf, acc);
-        next_instruction:
-            ins = nxt;
+        };
+#undef HANDLER_END
+
+        if constexpr (DEX_PTX_INTERP && FAST && !PARAM && !LOSS && sizeof(T) == 4 && U == 2) {
+            // Float32 hot path: the instruction loop as one inline-PTX block with a real jump
+            // table (gen_interp_ptx.py).  It returns at the end of the tape or at the first
+            // instruction it does not implement natively, which `step` then executes.
+            const uint32_t my_s = (uint32_t)__cvta_generic_to_shared(my);
+            const uint32_t tile_b = (uint32_t)TILE * 4u, cs_b = (uint32_t)CS * 4u;
+            int pc = 0;
+            float* av = reinterpret_cast<float*>(acc.v);
+            float* nfv = reinterpret_cast<float*>(nf);
+            while (pc < n) {
+                asm volatile(
+#include "dex_interp_f32.inc"
+                    : "+r"(pc), "+f"(av[0]), "+f"(av[1]), "+f"(av[2]), "+f"(av[3]), "+f"(av[4]), "+f"(av[5]),
+                      "+f"(av[6]), "+f"(av[7]), "+f"(nfv[0]), "+f"(nfv[1])
+                    : "l"(ip), "r"(n), "r"(my_s), "r"(tile_b), "r"(cs_b)
+                    : "memory");
+                if (pc < n) {
+                    step(__ldg(ip + pc));
+                    ++pc;
+                }
+            }
+        } else {
+            uint4 ins = __ldg(ip);
+            for (int pc = 0; pc < n; ++pc) {
+                uint4 nxt = ins;
+                if (pc + 1 < n) nxt = __ldg(ip + pc + 1);  // prefetch the next instruction
+                // pull the tape line two lines (16 instructions) ahead into L1: with thousands of
+                // trees per CTA the tape no longer stays L1-resident and an L2 miss per line would
+                // otherwise be exposed (tapes of consecutive trees are contiguous; the buffer is
+                // padded, so running past this tree's end just prefetches the next tree)
+                if ((pc & 7) == 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(ip + pc + 16));
+                step(ins);
+                ins = nxt;
+            }
         }
 
         // ---- result row segment ----------------------------------------------------
