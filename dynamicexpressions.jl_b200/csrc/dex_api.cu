@@ -51,6 +51,7 @@ struct dex_population {
     int64_t* d_const_off = nullptr;
     int64_t* d_const_pos = nullptr;
     std::map<int32_t, int32_t*> chunk_tables;  // n_chunks -> device table
+    std::map<int32_t, std::vector<int32_t>> chunk_tables_host;
     std::map<std::string, int64_t*> grad_off_tables;
 };
 
@@ -164,6 +165,7 @@ int chunk_table(dex_ctx* ctx, dex_population* pop, int32_t n_chunks, const int32
     CU(ctx, cudaMemcpyAsync(d, tab.data(), tab.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));  // tab is a stack temporary
     pop->chunk_tables[key] = d;
+    pop->chunk_tables_host[key] = tab;
     *out = d;
     return DEX_OK;
 }
@@ -187,7 +189,8 @@ int check_eval_args(dex_ctx* ctx, const dex_population* pop, const void* X, int3
 int run_eval(dex_ctx* ctx, const dex_population* cpop, const void* X, int32_t F, int64_t N,
              int64_t ldx, void* out, int64_t ldo, uint8_t* ok, int eval_flags, const void* params,
              int32_t n_params, int32_t n_classes, const int32_t* classes, const void* y,
-             const void* w, double* loss_partial, int64_t* n_tiles_out) {
+             const void* w, double* loss_partial, int64_t* n_tiles_out, int n_slices = 1,
+             void* out_host = nullptr, int64_t ldo_host = 0) {
     dex_population* pop = const_cast<dex_population*>(cpop);
     const PackedPopulation& h = pop->h;
     if (h.n_trees == 0 || N == 0) return DEX_OK;
@@ -226,9 +229,36 @@ int run_eval(dex_ctx* ctx, const dex_population* cpop, const void* X, int32_t F,
     a.params = params; a.n_params = n_params; a.n_classes = n_classes; a.classes = classes;
     a.y = y; a.w = w; a.loss_partial = loss_partial;
     int launches = 0;
-    cudaError_t e = launch_eval(a, ctx->stream, ctx->sm_count, &launches);
+    if (n_slices <= 1 || !out_host) {
+        cudaError_t e = launch_eval(a, ctx->stream, ctx->sm_count, &launches);
+        ctx->launches += launches;
+        if (e != cudaSuccess) return cuda_err(ctx, e, "eval kernel launch");
+        return DEX_OK;
+    }
+    // Host-result pipeline: the population is evaluated in slices of consecutive tree chunks;
+    // the device->host copy of slice s (copy stream) overlaps the kernel of slice s+1.
+    const std::vector<int32_t>& tab = pop->chunk_tables_host[(int32_t)n_chunks];
+    const size_t es = h.dtype == DEX_F32 ? 4 : 8;
+    n_slices = (int)std::min<int64_t>(n_slices, n_chunks);
+    for (int sl = 0; sl < n_slices; ++sl) {
+        const int64_t c0 = n_chunks * sl / n_slices, c1 = n_chunks * (sl + 1) / n_slices;
+        EvalArgs b = a;
+        b.chunk_start = a.chunk_start + c0;
+        b.n_chunks = (int32_t)(c1 - c0);
+        b.skip_prepass = sl > 0;
+        cudaError_t e = launch_eval(b, ctx->stream, ctx->sm_count, &launches);
+        if (e != cudaSuccess) { ctx->launches += launches; return cuda_err(ctx, e, "eval kernel launch"); }
+        const int64_t t_lo = tab[(size_t)c0], t_hi = tab[(size_t)c1];
+        CU(ctx, cudaEventRecord(ctx->ev[sl & 1], ctx->stream));
+        CU(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev[sl & 1], 0));
+        if (t_hi > t_lo)
+            CU(ctx, cudaMemcpy2DAsync(static_cast<char*>(out_host) + (size_t)t_lo * (size_t)ldo_host * es,
+                                      (size_t)ldo_host * es,
+                                      static_cast<const char*>(out) + (size_t)t_lo * (size_t)ldo * es,
+                                      (size_t)ldo * es, (size_t)N * es, (size_t)(t_hi - t_lo),
+                                      cudaMemcpyDeviceToHost, ctx->copy_stream));
+    }
     ctx->launches += launches;
-    if (e != cudaSuccess) return cuda_err(ctx, e, "eval kernel launch");
     return DEX_OK;
 }
 
@@ -648,13 +678,17 @@ int dex_eval_host(dex_ctx* ctx, const dex_population* pop, const void* X_host, i
     CU(ctx, cudaMemcpyAsync(dX, X_host, xb, cudaMemcpyHostToDevice, ctx->stream));
     if ((rc = check_eval_args(ctx, pop, dX, nfeatures, N, ldx, dO, N, dK))) return rc;
     if (pop->h.max_parameter >= 0) return set_err(ctx, DEX_ERR_INVALID, "population has parameter leaves");
+    // results travel back slice by slice on the copy stream while the next slice computes
+    const int n_slices = (size_t)P * (size_t)N * es >= ((size_t)8 << 20) ? 8 : 1;
     if ((rc = run_eval(ctx, pop, dX, nfeatures, N, ldx, dO, N, dK, eval_flags, nullptr, 0, 0, nullptr,
-                       nullptr, nullptr, nullptr, nullptr)))
+                       nullptr, nullptr, nullptr, nullptr, n_slices, out_host, ldo)))
         return rc;
-    CU(ctx, cudaMemcpy2DAsync(out_host, (size_t)ldo * es, dO, (size_t)N * es, (size_t)N * es, (size_t)P,
-                              cudaMemcpyDeviceToHost, ctx->stream));
+    if (n_slices == 1)
+        CU(ctx, cudaMemcpy2DAsync(out_host, (size_t)ldo * es, dO, (size_t)N * es, (size_t)N * es, (size_t)P,
+                                  cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaMemcpyAsync(ok_host, dK, (size_t)P, cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->copy_stream));
     return DEX_OK;
 }
 

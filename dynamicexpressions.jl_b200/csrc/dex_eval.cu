@@ -666,15 +666,18 @@ cudaError_t launch_eval(const EvalArgs& e, cudaStream_t stream, int sm_count, in
     const int64_t tile = (int64_t)threads * (e.dtype == DEX_F32 ? 4 : 2) * EVAL_U;
     const int64_t Npad = n_tiles * tile;
     const int64_t cover = std::max<int64_t>(Npad, e.n_trees);
-    if (e.dtype == DEX_F32)
-        transpose_pad_kernel<float><<<(unsigned)((cover + 255) / 256), 256, 0, stream>>>(
-            static_cast<const float*>(e.X), e.ldx, e.F, e.N, static_cast<float*>(e.xt), Npad, e.ok, e.n_trees);
-    else
-        transpose_pad_kernel<double><<<(unsigned)((cover + 255) / 256), 256, 0, stream>>>(
-            static_cast<const double*>(e.X), e.ldx, e.F, e.N, static_cast<double*>(e.xt), Npad, e.ok, e.n_trees);
-    cudaError_t err = cudaGetLastError();
-    if (err != cudaSuccess) return err;
-    if (launches) *launches += 1;
+    cudaError_t err = cudaSuccess;
+    if (!e.skip_prepass) {
+        if (e.dtype == DEX_F32)
+            transpose_pad_kernel<float><<<(unsigned)((cover + 255) / 256), 256, 0, stream>>>(
+                static_cast<const float*>(e.X), e.ldx, e.F, e.N, static_cast<float*>(e.xt), Npad, e.ok, e.n_trees);
+        else
+            transpose_pad_kernel<double><<<(unsigned)((cover + 255) / 256), 256, 0, stream>>>(
+                static_cast<const double*>(e.X), e.ldx, e.F, e.N, static_cast<double*>(e.xt), Npad, e.ok, e.n_trees);
+        err = cudaGetLastError();
+        if (err != cudaSuccess) return err;
+        if (launches) *launches += 1;
+    }
     EvalArgs k = e;   // the interpreter reads the staged copy
     k.X = e.xt;
     k.ldx = Npad;

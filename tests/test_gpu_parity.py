@@ -441,23 +441,23 @@ def test_fused_loss_matches_materialised_results():
     np.testing.assert_allclose(got[good], want[good], rtol=1e-10)
 
 
-def test_host_entry_point_matches_device_entry_point():
+@pytest.mark.parametrize("P_,N", [(64, 4096), (400, 8192)])   # the second takes the sliced D2H pipeline
+def test_host_entry_point_matches_device_entry_point(P_, N):
     import torch
     ops = dexb200.OperatorEnum(treegen.OPSET_A)
-    nodes, offsets = treegen.gen_population(64, 6, 2, 4, 5, seed=61)
-    N = 4096
+    nodes, offsets = treegen.gen_population(P_, 6, 2, 4, 5, seed=61)
     Xh = torch.from_numpy(np.random.default_rng(10).standard_normal((N, 5)).astype(np.float32)).pin_memory()
     pop = D.Population(None, ops, np.float32, wire=(nodes, offsets))
-    out_h = torch.empty((64, N), dtype=torch.float32).pin_memory()
-    ok_h = torch.empty(64, dtype=torch.uint8).pin_memory()
+    out_h = torch.empty((P_, N), dtype=torch.float32).pin_memory()
+    ok_h = torch.empty(P_, dtype=torch.uint8).pin_memory()
     pop.eval_host(Xh, out_h, ok_h)
     out_d, ok_d = pop.eval(Xh.cuda().T)
     a, b = out_h.numpy(), out_d.cpu().numpy()
     assert ((a == b) | (np.isnan(a) & np.isnan(b))).all()
     assert (ok_h.numpy() == ok_d.cpu().numpy()).all()
     # pageable numpy buffers work too
-    out_n = np.empty((64, N), np.float32)
-    ok_n = np.empty(64, np.uint8)
+    out_n = np.empty((P_, N), np.float32)
+    ok_n = np.empty(P_, np.uint8)
     pop.eval_host(Xh.numpy().copy(), out_n, ok_n)
     assert ((out_n == b) | (np.isnan(out_n) & np.isnan(b))).all()
 
