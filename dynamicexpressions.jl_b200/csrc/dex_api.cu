@@ -196,11 +196,12 @@ int run_eval(dex_ctx* ctx, const dex_population* cpop, const void* X, int32_t F,
     if (h.n_trees == 0 || N == 0) return DEX_OK;
     int threads;
     size_t smem;
-    const int64_t n_tiles = eval_num_tiles(h.dtype, F, h.max_stack, N, &threads, &smem);
+    const int32_t front_rows = h.max_stack + h.n_param_rows;
+    const int64_t n_tiles = eval_num_tiles(h.dtype, F, front_rows, N, &threads, &smem);
     if (n_tiles_out) *n_tiles_out = n_tiles;
     if (smem > 227 * 1024)
         return set_err(ctx, DEX_ERR_UNSUPPORTED,
-                       "nfeatures + stack rows = " + std::to_string(F + h.max_stack) +
+                       "nfeatures + stack rows = " + std::to_string(F + front_rows) +
                            " do not fit in shared memory");
     // Chunking policy.  (a) enough CTAs for ~4 waves of 8 resident CTAs per SM; (b) chunks of at
     // most ~chunk_instr tape instructions: CTAs are dispatched tile-fastest, so with short
@@ -222,7 +223,8 @@ int run_eval(dex_ctx* ctx, const dex_population* cpop, const void* X, int32_t F,
     if (rc) return rc;
     a.n_chunks = (int32_t)n_chunks;
     a.max_stack = h.max_stack;
-    if ((rc = ensure_xt(ctx, eval_xt_bytes(h.dtype, F, h.max_stack, N)))) return rc;
+    a.n_param_rows = h.n_param_rows;
+    if ((rc = ensure_xt(ctx, eval_xt_bytes(h.dtype, F, front_rows, N)))) return rc;
     a.X = X; a.F = F; a.N = N; a.ldx = ldx; a.xt = ctx->xt;
     a.out = out; a.ldo = ldo; a.ok = ok;
     a.early_exit = (eval_flags & DEX_EVAL_EARLY_EXIT) ? 1 : 0;
@@ -562,7 +564,7 @@ int dex_eval_loss(dex_ctx* ctx, const dex_population* pop, const void* X_dev, in
     if (pop->h.max_parameter >= 0) return set_err(ctx, DEX_ERR_INVALID, "population has parameter leaves");
     if (pop->h.n_trees == 0) return DEX_OK;
     int threads; size_t smem;
-    const int64_t n_tiles = eval_num_tiles(pop->h.dtype, nfeatures, pop->h.max_stack, std::max<int64_t>(nsamples, 1), &threads, &smem);
+    const int64_t n_tiles = eval_num_tiles(pop->h.dtype, nfeatures, pop->h.max_stack + pop->h.n_param_rows, std::max<int64_t>(nsamples, 1), &threads, &smem);
     if ((rc = ensure_scratch(ctx, (size_t)n_tiles * (size_t)pop->h.n_trees * sizeof(double)))) return rc;
     double* partial = static_cast<double*>(ctx->scratch);
     if ((rc = run_eval(ctx, pop, X_dev, nfeatures, nsamples, ldx, nullptr, 0, ok_dev, eval_flags, nullptr, 0,

@@ -172,7 +172,7 @@ template <typename T> struct KArgs {
     const T* w;
     double* loss_partial;
     int64_t N, ldx, ldo, n_trees;
-    int32_t F, max_stack, early_exit, n_params, n_classes;
+    int32_t F, max_stack, n_param_rows, early_exit, n_params, n_classes;
 };
 
 // A row vector of one thread: U chunks of C elements.
@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(DEX_MAX_THREADS, DEX_MIN_CTAS) eval_kernel(con
     // async copies (TMA, cp.async.bulk -> SASS UBLKCP) that complete on an mbarrier.
     __shared__ __align__(8) unsigned long long stage_bar;
     {
-        T* xs = rows + (size_t)a.max_stack * TILE;
+        T* xs = rows + (size_t)(a.max_stack + a.n_param_rows) * TILE;
         const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&stage_bar);
         const uint32_t row_bytes = (uint32_t)TILE * (uint32_t)sizeof(T);
         if (tid == 0) {
@@ -304,6 +304,17 @@ __global__ void __launch_bounds__(DEX_MAX_THREADS, DEX_MIN_CTAS) eval_kernel(con
         const int n = (int)(a.tape_off[t + 1] - off);
         const uint4* ip = a.tape + off;
         const T* ptree = PARAM ? a.params + (size_t)t * a.n_params * a.n_classes : nullptr;
+        if (PARAM) {
+            // ParametricExpression: gather this tree's per-sample parameters
+            // parameters[p, classes[j]] (src/ParametricExpression.jl:380-384) into the parameter
+            // rows; each thread fills and later reads only its own columns, so no barrier
+            for (int p = 0; p < a.n_param_rows; ++p) {
+                V pv;
+#pragma unroll
+                for (int k = 0; k < K; ++k) pv.v[k] = __ldg(ptree + cls[k] + p);
+                st_row<T, U>(my + (size_t)(a.max_stack + p) * TILE, CS, pv);
+            }
+        }
         V acc;
         T nf[2] = {T(0), T(0)};
 #pragma unroll
@@ -473,7 +484,7 @@ __global__ void __launch_bounds__(DEX_MAX_THREADS, DEX_MIN_CTAS) eval_kernel(con
         };
 #undef HANDLER_END
 
-        if constexpr (DEX_PTX_INTERP && FAST && !PARAM && !LOSS && sizeof(T) == 4 && U == 2) {
+        if constexpr (DEX_PTX_INTERP && FAST && sizeof(T) == 4 && U == 2) {
             // Float32 hot path: the instruction loop as one inline-PTX block with a real jump
             // table (gen_interp_ptx.py).  It returns at the end of the tape or at the first
             // instruction it does not implement natively, which `step` then executes.
@@ -599,7 +610,7 @@ cudaError_t launch_typed(const EvalArgs& e, cudaStream_t stream, int threads, si
     a.w = static_cast<const T*>(e.w);
     a.loss_partial = e.loss_partial;
     a.N = e.N; a.ldx = e.ldx; a.ldo = e.ldo; a.n_trees = e.n_trees;
-    a.F = e.F; a.max_stack = e.max_stack; a.early_exit = e.early_exit;
+    a.F = e.F; a.max_stack = e.max_stack; a.n_param_rows = e.n_param_rows; a.early_exit = e.early_exit;
     a.n_params = e.n_params; a.n_classes = e.n_classes;
     dim3 grid((unsigned)n_tiles, (unsigned)e.n_chunks);
     const bool param = e.params != nullptr, loss = e.y != nullptr, fast = e.early_exit != 0;
@@ -660,7 +671,7 @@ cudaError_t launch_eval(const EvalArgs& e, cudaStream_t stream, int sm_count, in
     (void)sm_count;
     int threads;
     size_t smem;
-    const int64_t n_tiles = eval_num_tiles(e.dtype, e.F, e.max_stack, e.N, &threads, &smem);
+    const int64_t n_tiles = eval_num_tiles(e.dtype, e.F, e.max_stack + e.n_param_rows, e.N, &threads, &smem);
     if (smem > SMEM_LIMIT) return cudaErrorInvalidConfiguration;
     if (e.n_trees == 0 || e.N == 0) return cudaSuccess;
     const int64_t tile = (int64_t)threads * (e.dtype == DEX_F32 ? 4 : 2) * EVAL_U;

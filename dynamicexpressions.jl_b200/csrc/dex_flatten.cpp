@@ -106,6 +106,7 @@ struct Flattener {
         uint32_t src = SRC_ACC;
         uint32_t row = 0;   // stack slot (SRC_ROW, is_feature=false), feature idx, or param idx
         bool is_feature = false;
+        bool is_param = false;  // a parameter row (gathered per tree into shared memory), rebased like features
         double c = 0.0;
         int32_t cord = -1;
         bool chk = false;
@@ -135,7 +136,10 @@ struct Flattener {
             o.row = x.feature;
             o.chk = bumper ? false : (feature_checked || const_mode);
         } else {
-            o.src = SRC_PARAM;
+            // a ParametricExpression parameter: the kernel gathers parameters[p, classes[:]] of
+            // the current tree into a shared-memory row, so the operand is an ordinary ROW
+            o.src = SRC_ROW;
+            o.is_param = true;
             o.row = x.feature;
             o.chk = bumper ? false : (feature_checked || const_mode);
         }
@@ -458,7 +462,8 @@ struct Flattener {
             // bit 31/30 of the scratch word c_hi-independent marker is kept in `rebase`
             uint32_t ra = e.a.row, rb = e.b.row;
             ins.w1 = (ra & 0xfffu) | ((rb & 0xfffu) << 12) | (push_row << 24);
-            rebase.push_back((uint8_t)((e.a.is_feature ? 1 : 0) | (e.b.is_feature ? 2 : 0)));
+            rebase.push_back((uint8_t)((e.a.is_feature ? 1 : 0) | (e.b.is_feature ? 2 : 0) |
+                                       (e.a.is_param ? 4 : 0) | (e.b.is_param ? 8 : 0)));
             const int64_t idx = (int64_t)out.tape.size();
             if (e.a.src == SRC_CONST) { put_const(ins, e.a.c); if (e.a.cord >= 0) out.const_pos[const_base + e.a.cord] = idx; }
             if (e.b.src == SRC_CONST) { put_const(ins, e.b.c); if (e.b.cord >= 0) out.const_pos[const_base + e.b.cord] = idx; }
@@ -513,8 +518,10 @@ struct Flattener {
             out.const_off.push_back(out.n_constants);
             out.tape_off.push_back((int64_t)out.tape.size());
         }
-        // rebase feature rows behind the stack rows
-        const uint32_t base = (uint32_t)out.max_stack;
+        // row layout: [0, max_stack) operand stack, then one row per parameter, then the features
+        out.n_param_rows = out.max_parameter + 1;
+        const uint32_t pbase = (uint32_t)out.max_stack;
+        const uint32_t base = pbase + (uint32_t)out.n_param_rows;
         if (out.max_feature >= 0 && (int64_t)out.max_feature + base > MAX_ROWS)
             return fail(DEX_ERR_UNSUPPORTED, "feature index " + std::to_string(out.max_feature) +
                                                  " + stack rows exceed the device row limit " + std::to_string(MAX_ROWS));
@@ -523,6 +530,8 @@ struct Flattener {
             uint32_t ra = ins.w1 & 0xfffu, rb = (ins.w1 >> 12) & 0xfffu;
             if (rebase[k] & 1) ra += base;
             if (rebase[k] & 2) rb += base;
+            if (rebase[k] & 4) ra += pbase;
+            if (rebase[k] & 8) rb += pbase;
             ins.w1 = (ins.w1 & 0xff000000u) | ra | (rb << 12);
         }
         out.n_trees = n_trees;

@@ -15,7 +15,8 @@ struct EvalArgs {
     int64_t n_trees;
     const int32_t* chunk_start; // device, n_chunks + 1 (tree index ranges, balanced by tape length)
     int32_t n_chunks;
-    int32_t max_stack;          // stack rows in front of the feature rows
+    int32_t max_stack;          // stack rows in front of the parameter and feature rows
+    int32_t n_param_rows;       // rows between the stack rows and the feature rows
     const void* X;              // device, column-major F x N, leading dimension ldx
     void* xt;                   // device scratch >= eval_xt_bytes(): feature-major padded copy of X
     int32_t F;
@@ -43,6 +44,7 @@ struct EvalArgs {
 cudaError_t launch_eval(const EvalArgs& a, cudaStream_t stream, int sm_count, int* launches);
 size_t eval_xt_bytes(int dtype, int32_t F, int32_t max_stack, int64_t N);
 // number of sample tiles launch_eval will use for (dtype, F, max_stack, N)
+// `max_stack` here = stack rows + parameter rows (every row in front of the features)
 int64_t eval_num_tiles(int dtype, int32_t F, int32_t max_stack, int64_t N, int* threads_out,
                        size_t* smem_out);
 

@@ -9,9 +9,10 @@
 // accumulator operand) — this is the device analogue of the reference's fused
 // 2-/3-node kernels (/root/reference/src/Evaluate.jl:693-993).
 //
-// Stack slots and feature rows are ABSOLUTE shared-memory row indices fixed at pack
-// time: rows [0, max_stack) are the operand stack, rows [max_stack, max_stack+F)
-// are the features, so the interpreter never maintains a stack pointer.
+// Stack slots, parameter rows and feature rows are ABSOLUTE shared-memory row indices
+// fixed at pack time: rows [0, max_stack) are the operand stack, the next n_param_rows
+// rows hold the current tree's per-sample parameters (ParametricExpression), the features
+// follow, so the interpreter never maintains a stack pointer.
 //
 // Every instruction also carries a HANDLER id: the index of a code path in the
 // interpreter that is specialised for (operator, operand sources), so that the hot
@@ -104,6 +105,7 @@ struct PackedPopulation {
     int32_t max_stack = 0;       // eval tape stack rows
     int32_t max_feature = -1;
     int32_t max_parameter = -1;
+    int32_t n_param_rows = 0;    // shared-memory rows reserved for parameters (max_parameter + 1)
     int64_t n_generic = 0;       // instructions that take the generic handler
     int64_t n_checks = 0;        // validity checks left after elision
     std::vector<Instr> tape;               // all trees, concatenated

@@ -22,13 +22,17 @@ def handler_name(h):
     return s.decode() if s else None
 
 
-def run_tape(ins, X, max_stack, opcode_info, dtype, early_exit=True, params=None, classes0=None):
-    """ins: uint32[n, 4] of one tree; X: (F, N).  Returns (out[N], ok)."""
+def run_tape(ins, X, max_stack, opcode_info, dtype, early_exit=True, params=None, classes0=None,
+             n_param_rows=0):
+    """ins: uint32[n, 4] of one tree; X: (F, N).  Returns (out[N], ok).
+    Row layout (csrc/dex_tape.h): stack rows, parameter rows, feature rows."""
     u, b, t = _np_ops()
     sym2code = {v[0]: k for k, v in opcode_info.items()}
     F, N = X.shape
-    rows = np.zeros((max_stack + F, N), dtype=dtype)
-    rows[max_stack:] = X
+    rows = np.zeros((max_stack + n_param_rows + F, N), dtype=dtype)
+    rows[max_stack + n_param_rows:] = X
+    for p_ in range(n_param_rows):
+        rows[max_stack + p_] = np.asarray(params, dtype=dtype)[p_, classes0]
     acc = np.zeros(N, dtype=dtype)
     ok = True
 

@@ -118,7 +118,8 @@ def test_flattened_tape_matches_oracle_on_golden_cases(case, oracle):
                                use_fused=c.get("use_fused", True))
             ins, off = pop.tape()
             y, ok = run_tape(ins, X, pop.info["max_stack"], dexb200.OPCODE_INFO, dtype,
-                             early_exit=c.get("early_exit", True), params=P, classes0=cls0)
+                             early_exit=c.get("early_exit", True), params=P, classes0=cls0,
+                             n_param_rows=pop.info["max_parameter"] + 1)
             if P is not None:
                 ry, rok = oracle.eval_parametric(wire, ops.opcodes, X, P, cls0, _flags(oracle, c))
             else:
