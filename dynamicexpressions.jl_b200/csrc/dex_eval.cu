@@ -215,7 +215,9 @@ __device__ __forceinline__ void check(float (&nf)[2], const Vec<float, U>& r) {
 }
 #endif
 
-template <typename T, int U, bool FAST, bool PARAM, bool LOSS>
+// NT: CTA size fixed at compile time (the full-size 256-thread launch: row and chunk strides
+// become immediates of the shared-memory accesses) or 0 = read blockDim.x.
+template <typename T, int U, bool FAST, bool PARAM, bool LOSS, int NT = 0>
 __global__ void __launch_bounds__(DEX_MAX_THREADS, DEX_MIN_CTAS) eval_kernel(const KArgs<T> a) {
     using V = Vec<T, U>;
     constexpr int C = V::C;
@@ -223,7 +225,7 @@ __global__ void __launch_bounds__(DEX_MAX_THREADS, DEX_MIN_CTAS) eval_kernel(con
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* rows = reinterpret_cast<T*>(smem_raw);
     const int tid = threadIdx.x;
-    const int nthr = blockDim.x;
+    const int nthr = NT ? NT : (int)blockDim.x;
     const int TILE = nthr * K;          // samples per CTA = row stride in elements
     const int CS = nthr * C;            // chunk stride in elements
     const int64_t s0 = (int64_t)blockIdx.x * TILE;
@@ -323,15 +325,15 @@ __global__ void __launch_bounds__(DEX_MAX_THREADS, DEX_MIN_CTAS) eval_kernel(con
         // one tape instruction, C++ form (all handlers + the generic path)
         auto step = [&](const uint4& ins) {
             const uint32_t w0 = ins.x;
-            const T* ra = my + (size_t)(ins.y & 0xfffu) * TILE;
-            const T* rb = my + (size_t)((ins.y >> 12) & 0xfffu) * TILE;
+            const T* ra = my + (size_t)row_a(ins.y) * TILE;
+            const T* rb = my + (size_t)row_b(ins.y) * TILE;
             const T c = const_of<T>(ins);
             V cv;  // the inline constant broadcast over the K samples
 #pragma unroll
             for (int k = 0; k < K; ++k) cv.v[k] = c;
-            if (w0 & F_PUSH) st_row<T, U>(my + (size_t)(ins.y >> 24) * TILE, CS, acc);
+            if (w0 & F_PUSH) st_row<T, U>(my + (size_t)push_row(w0) * TILE, CS, acc);
 
-            const uint32_t h = FAST ? (w0 & 0xffu) : (uint32_t)H_GENERIC;
+            const uint32_t h = FAST ? (w0 & HANDLER_MASK) : (uint32_t)H_GENERIC;
 #define HANDLER_END break;
             switch (h) {
                 // ---- specialised handlers: one indirect branch, no operand decoding ----
@@ -423,7 +425,7 @@ __global__ void __launch_bounds__(DEX_MAX_THREADS, DEX_MIN_CTAS) eval_kernel(con
                             for (int k = 0; k < K; ++k) va.v[k] = c;
                         } else if (PARAM && src == SRC_PARAM) {
 #pragma unroll
-                            for (int k = 0; k < K; ++k) va.v[k] = __ldg(ptree + cls[k] + (ins.y & 0xfffu));
+                            for (int k = 0; k < K; ++k) va.v[k] = __ldg(ptree + cls[k] + row_a(ins.y));
                         } else va = acc;
                     }
                     {
@@ -434,7 +436,7 @@ __global__ void __launch_bounds__(DEX_MAX_THREADS, DEX_MIN_CTAS) eval_kernel(con
                             for (int k = 0; k < K; ++k) vb.v[k] = c;
                         } else if (PARAM && src == SRC_PARAM) {
 #pragma unroll
-                            for (int k = 0; k < K; ++k) vb.v[k] = __ldg(ptree + cls[k] + ((ins.y >> 12) & 0xfffu));
+                            for (int k = 0; k < K; ++k) vb.v[k] = __ldg(ptree + cls[k] + row_b(ins.y));
                         } else vb = acc;
                     }
                     const bool chk = early || (w0 & F_ALWAYS);
@@ -615,7 +617,11 @@ cudaError_t launch_typed(const EvalArgs& e, cudaStream_t stream, int threads, si
     dim3 grid((unsigned)n_tiles, (unsigned)e.n_chunks);
     const bool param = e.params != nullptr, loss = e.y != nullptr, fast = e.early_exit != 0;
     void (*kern)(const KArgs<T>);
-    if (fast) {
+    if (fast && threads == DEX_MAX_THREADS && sizeof(T) == 4) {
+        constexpr int NT = sizeof(T) == 4 ? DEX_MAX_THREADS : 0;
+        kern = loss ? (param ? eval_kernel<T, U, true, true, true, NT> : eval_kernel<T, U, true, false, true, NT>)
+                    : (param ? eval_kernel<T, U, true, true, false, NT> : eval_kernel<T, U, true, false, false, NT>);
+    } else if (fast) {
         kern = loss ? (param ? eval_kernel<T, U, true, true, true> : eval_kernel<T, U, true, false, true>)
                     : (param ? eval_kernel<T, U, true, true, false> : eval_kernel<T, U, true, false, false>);
     } else {

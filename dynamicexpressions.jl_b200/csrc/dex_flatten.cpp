@@ -456,12 +456,11 @@ struct Flattener {
             if (e.a.chk) ins.w0 |= F_CHK_A;
             if (e.b.chk) ins.w0 |= F_CHK_B;
             if ((e.a.chk && e.a.src == SRC_CONST) || (e.b.chk && e.b.src == SRC_CONST)) ins.w0 |= F_CHK_CONST;
-            uint32_t push_row = 0;
-            if (e.push_slot >= 0) { ins.w0 |= F_PUSH; push_row = (uint32_t)e.push_slot; }
+            if (e.push_slot >= 0) ins.w0 |= F_PUSH | HANDLER_PUSH | ((uint32_t)e.push_slot << PUSH_ROW_SHIFT);
             // feature rows are rebased behind the stack rows once max_stack is known:
             // bit 31/30 of the scratch word c_hi-independent marker is kept in `rebase`
             uint32_t ra = e.a.row, rb = e.b.row;
-            ins.w1 = (ra & 0xfffu) | ((rb & 0xfffu) << 12) | (push_row << 24);
+            ins.w1 = (ra & 0xffffu) | (rb << 16);
             rebase.push_back((uint8_t)((e.a.is_feature ? 1 : 0) | (e.b.is_feature ? 2 : 0) |
                                        (e.a.is_param ? 4 : 0) | (e.b.is_param ? 8 : 0)));
             const int64_t idx = (int64_t)out.tape.size();
@@ -527,12 +526,12 @@ struct Flattener {
                                                  " + stack rows exceed the device row limit " + std::to_string(MAX_ROWS));
         for (size_t k = 0; k < out.tape.size(); ++k) {
             Instr& ins = out.tape[k];
-            uint32_t ra = ins.w1 & 0xfffu, rb = (ins.w1 >> 12) & 0xfffu;
+            uint32_t ra = row_a(ins.w1), rb = row_b(ins.w1);
             if (rebase[k] & 1) ra += base;
             if (rebase[k] & 2) rb += base;
             if (rebase[k] & 4) ra += pbase;
             if (rebase[k] & 8) rb += pbase;
-            ins.w1 = (ins.w1 & 0xff000000u) | ra | (rb << 12);
+            ins.w1 = ra | (rb << 16);
         }
         out.n_trees = n_trees;
         return DEX_OK;

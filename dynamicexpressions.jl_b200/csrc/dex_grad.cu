@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(128) grad_kernel(const GK<T> a) {
                 const uint32_t op = (w0 >> 8) & 0xffu;
                 const T c = gconst_of<T>(ins);
                 if (w0 & F_PUSH) {
-                    T* dst = my + (size_t)(ins.y >> 24) * (1 + GC) * TILE;
+                    T* dst = my + (size_t)push_row(w0) * (1 + GC) * TILE;
                     stv<T, K>(dst, av);
 #pragma unroll
                     for (int g = 0; g < GC; ++g) stv<T, K>(dst + (size_t)(1 + g) * TILE, ad[g]);
@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(128) grad_kernel(const GK<T> a) {
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
                     const uint32_t src = (w0 >> (16 + 2 * i)) & 3u;
-                    const int row = (int)((ins.y >> (12 * i)) & 0xfffu);
+                    const int row = (int)((ins.y >> (16 * i)) & 0xffffu);
                     dk[i] = DK_LEAF; idx[i] = -1; drow[i] = my;
                     if (i >= deg) {
 #pragma unroll

@@ -27,7 +27,9 @@ namespace dex {
 
 // ---- evaluation tape -------------------------------------------------------------
 // 16 bytes, fetched as one uint4 (x=w0, y=w1, z/w = constant).
-//   w0 [ 7: 0] handler  HANDLER id (H_*), 0 = generic
+//   w0 [ 5: 0] handler  HANDLER id (H_*), 0 = generic
+//      [ 6]    copy of PUSH: the Float32 jump table has one entry per (handler, PUSH)
+//              so that the push costs nothing when it does not happen; bit 7 is zero
 //      [15: 8] opcode   builtin opcode of include/dex_ops.def (IDENTITY doubles as LOAD)
 //      [17:16] srcA     SRC_*
 //      [19:18] srcB     SRC_*   (ternary: third operand is always ACC)
@@ -41,9 +43,10 @@ namespace dex {
 //                       (/root/reference/src/Evaluate.jl:722, 737, 754, 787)
 //      [26]    CHK_CONST  the inline constant participates (= CHK_A/CHK_B of the
 //                       constant operand; what the specialised handlers test)
-//   w1 [11: 0] rowA  (ROW: smem row; PARAM: parameter index)
-//      [23:12] rowB
-//      [31:24] push_row
+//      [31:27] push_row  stack slot the PUSH stores to (a tree of n nodes needs about
+//                       log2(n) slots in Sethi-Ullman order, so five bits are ample)
+//   w1 [15: 0] rowA  (ROW: smem row; PARAM: parameter index)
+//      [31:16] rowB
 //   c  inline constant: float in .z (F32) or double in .z/.w (F64)
 struct Instr {
     uint32_t w0;
@@ -63,8 +66,17 @@ enum : uint32_t {
     F_GUARD = 1u << 25,
     F_CHK_CONST = 1u << 26,
 };
-constexpr int MAX_STACK_ROWS = 250;  // push_row is 8 bits
-constexpr int MAX_ROWS = 4095;       // row fields are 12 bits
+constexpr int MAX_STACK_ROWS = 31;   // push_row is 5 bits
+constexpr int MAX_ROWS = 65535;      // row fields are 16 bits
+constexpr int PUSH_ROW_SHIFT = 27;
+#if defined(__CUDACC__)
+#define DEX_HD __host__ __device__ __forceinline__
+#else
+#define DEX_HD inline
+#endif
+DEX_HD uint32_t row_a(uint32_t w1) { return w1 & 0xffffu; }
+DEX_HD uint32_t row_b(uint32_t w1) { return w1 >> 16; }
+DEX_HD uint32_t push_row(uint32_t w0) { return w0 >> PUSH_ROW_SHIFT; }
 
 // Operators with specialised handlers.  Unary: operand in ACC (_A) or in a ROW (_R).
 // Commutative binary: (ACC,ROW) (ACC,CONST) (ROW,ROW) (ROW,CONST) — the flattener swaps
@@ -90,6 +102,8 @@ enum Handler : uint32_t {
 #undef X
     H__COUNT
 };
+constexpr uint32_t HANDLER_MASK = 63u, HANDLER_PUSH = 64u;
+static_assert(H__COUNT <= HANDLER_PUSH - 1, "handler ids must fit six bits (one slot is reserved)");
 
 // ---- host-side description of a packed population ----------------------------------
 struct OpTable {

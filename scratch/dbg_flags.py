@@ -22,6 +22,6 @@ for t in bad[:3]:
     j = np.nonzero(~np.isfinite(out[t]) | ~np.isfinite(ref[t]))[0][:5]
     print(" nonfinite idx", j, out[t][j], ref[t][j])
     for w in ins[off[t]:off[t+1]]:
-        w0=int(w[0]); print("   ", D.lib().dex_handler_name(w0&0xff).decode(), dexb200.OPCODE_INFO[(w0>>8)&0xff][0], "src", (w0>>16)&3, (w0>>18)&3, "flags", [n for n,b in [("PUSH",20),("OUT",21),("A",22),("B",23),("ALW",24),("GRD",25),("CC",26)] if w0&(1<<b)], "rows", int(w[1])&0xfff, (int(w[1])>>12)&0xfff, int(w[1])>>24, np.array([w[2]],dtype=np.uint32).view(np.float32)[0])
+        w0=int(w[0]); print("   ", D.lib().dex_handler_name(w0&0x3f).decode(), dexb200.OPCODE_INFO[(w0>>8)&0xff][0], "src", (w0>>16)&3, (w0>>18)&3, "flags", [n for n,b in [("PUSH",20),("OUT",21),("A",22),("B",23),("ALW",24),("GRD",25),("CC",26)] if w0&(1<<b)], "rows", int(w[1])&0xffff, int(w[1])>>16, w0>>27, np.array([w[2]],dtype=np.uint32).view(np.float32)[0])
     # elementwise compare
     d = np.abs(out[t]-ref[t]); print(" max abs diff", np.nanmax(d))

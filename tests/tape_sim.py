@@ -46,12 +46,12 @@ def run_tape(ins, X, max_stack, opcode_info, dtype, early_exit=True, params=None
 
     for w in ins:
         w0, w1 = int(w[0]), int(w[1])
-        rowA, rowB, push_row = w1 & 0xFFF, (w1 >> 12) & 0xFFF, w1 >> 24
+        rowA, rowB, push_row = w1 & 0xFFFF, w1 >> 16, w0 >> 27
         if w0 & F_PUSH:
             rows[push_row] = acc
         c = const_of(w)
         cvec = np.full(N, c, dtype=dtype)
-        h = (w0 & 0xFF) if early_exit else 0          # early_exit off => generic kernel
+        h = (w0 & 0x3F) if early_exit else 0          # early_exit off => generic kernel
         code = (w0 >> 8) & 0xFF
         if h != 0:
             name = handler_name(h)
