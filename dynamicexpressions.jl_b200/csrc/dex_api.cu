@@ -50,6 +50,13 @@ struct dex_population {
     int32_t* d_const_ord = nullptr;
     int64_t* d_const_off = nullptr;
     int64_t* d_const_pos = nullptr;
+    // folded image (h.folded): what dex_eval* run
+    Instr* d_ftape = nullptr;
+    int64_t* d_ftape_off = nullptr;
+    int64_t* d_fconst_pos = nullptr;
+    Instr* d_ctape = nullptr;
+    int64_t* d_seg = nullptr;
+    int64_t* d_seg_off = nullptr;
     std::map<int32_t, int32_t*> chunk_tables;  // n_chunks -> device table
     std::map<int32_t, std::vector<int32_t>> chunk_tables_host;
     std::map<std::string, int64_t*> grad_off_tables;
@@ -147,7 +154,7 @@ int chunk_table(dex_ctx* ctx, dex_population* pop, int32_t n_chunks, const int32
     const int32_t key = n_chunks;
     auto it = pop->chunk_tables.find(key);
     if (it != pop->chunk_tables.end()) { *out = it->second; return DEX_OK; }
-    const PackedPopulation& h = pop->h;
+    const PackedPopulation& h = *pop->h.folded;
     std::vector<int32_t> tab((size_t)n_chunks + 1, 0);
     // cost of trees [0, t) = tape instructions + a fixed per-tree cost of one
     const std::vector<int64_t>& toff = h.tape_off;
@@ -192,7 +199,7 @@ int run_eval(dex_ctx* ctx, const dex_population* cpop, const void* X, int32_t F,
              const void* w, double* loss_partial, int64_t* n_tiles_out, int n_slices = 1,
              void* out_host = nullptr, int64_t ldo_host = 0) {
     dex_population* pop = const_cast<dex_population*>(cpop);
-    const PackedPopulation& h = pop->h;
+    const PackedPopulation& h = *pop->h.folded;   // evaluation runs the folded image
     if (h.n_trees == 0 || N == 0) return DEX_OK;
     int threads;
     size_t smem;
@@ -216,8 +223,9 @@ int run_eval(dex_ctx* ctx, const dex_population* cpop, const void* X, int32_t F,
     n_chunks = std::min<int64_t>(n_chunks, std::min<int64_t>(h.n_trees, 65535));
     EvalArgs a{};
     a.dtype = h.dtype;
-    a.tape = pop->d_tape;
-    a.tape_off = pop->d_tape_off;
+    a.tape = pop->d_ftape;
+    a.tape_off = pop->d_ftape_off;
+    if (!h.seg.empty()) { a.ctape = pop->d_ctape; a.seg = pop->d_seg; a.seg_off = pop->d_seg_off; }
     a.n_trees = h.n_trees;
     int rc = chunk_table(ctx, pop, (int32_t)n_chunks, &a.chunk_start);
     if (rc) return rc;
@@ -415,6 +423,13 @@ int dex_population_pack(dex_ctx* ctx, const dex_optable* ops, const dex_node* no
         if (!rc) rc = upload(ctx, &pop->d_const_ord, pop->h.tape_const_ord);
         if (!rc) rc = upload(ctx, &pop->d_const_off, pop->h.const_off);
         if (!rc) rc = upload(ctx, &pop->d_const_pos, pop->h.const_pos);
+        const PackedPopulation& f = *pop->h.folded;
+        if (!rc) rc = upload(ctx, &pop->d_ftape, f.tape);
+        if (!rc) rc = upload(ctx, &pop->d_ftape_off, f.tape_off);
+        if (!rc) rc = upload(ctx, &pop->d_fconst_pos, f.const_pos);
+        if (!rc) rc = upload(ctx, &pop->d_ctape, f.ctape);
+        if (!rc) rc = upload(ctx, &pop->d_seg, f.seg);
+        if (!rc) rc = upload(ctx, &pop->d_seg_off, f.seg_off);
         if (!rc && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = set_err(ctx, DEX_ERR_CUDA, "tape upload failed");
         if (rc) { dex_population_destroy(pop); return rc; }
     }
@@ -428,6 +443,8 @@ int dex_population_destroy(dex_population* pop) {
         cudaSetDevice(pop->device);
         cudaFree(pop->d_tape); cudaFree(pop->d_tape_off); cudaFree(pop->d_const_ord);
         cudaFree(pop->d_const_off); cudaFree(pop->d_const_pos);
+        cudaFree(pop->d_ftape); cudaFree(pop->d_ftape_off); cudaFree(pop->d_fconst_pos);
+        cudaFree(pop->d_ctape); cudaFree(pop->d_seg); cudaFree(pop->d_seg_off);
         for (auto& kv : pop->chunk_tables) cudaFree(kv.second);
         for (auto& kv : pop->grad_off_tables) cudaFree(kv.second);
     }
@@ -447,6 +464,10 @@ int dex_population_get_info(const dex_population* pop, dex_population_info* info
     info->dtype = pop->h.dtype;
     info->n_generic = pop->h.n_generic;
     info->n_checks = pop->h.n_checks;
+    info->n_folded_instructions = (int64_t)pop->h.folded->tape.size();
+    info->n_scalar_instructions = (int64_t)pop->h.folded->ctape.size();
+    info->n_folded_subtrees = (int64_t)pop->h.folded->seg.size() / 3;
+    info->folded_max_stack = pop->h.folded->max_stack;
     return DEX_OK;
 }
 
@@ -483,6 +504,19 @@ int64_t dex_population_copy_tape(const dex_population* pop, void* instrs, int64_
     return n;
 }
 
+// the folded image: main tape, scalar tape, segment table (3 int64 per folded subtree)
+int dex_population_copy_folded(const dex_population* pop, void* instrs, int64_t* offsets,
+                               void* scalar_instrs, int64_t* segs, int64_t* seg_offsets) {
+    if (!pop) return DEX_ERR_INVALID;
+    const PackedPopulation& f = *pop->h.folded;
+    if (instrs) std::memcpy(instrs, f.tape.data(), f.tape.size() * sizeof(Instr));
+    if (offsets) std::copy(f.tape_off.begin(), f.tape_off.end(), offsets);
+    if (scalar_instrs) std::memcpy(scalar_instrs, f.ctape.data(), f.ctape.size() * sizeof(Instr));
+    if (segs) std::copy(f.seg.begin(), f.seg.end(), segs);
+    if (seg_offsets) std::copy(f.seg_off.begin(), f.seg_off.end(), seg_offsets);
+    return DEX_OK;
+}
+
 int dex_population_get_constants(dex_ctx* ctx, const dex_population* pop, void* values_host,
                                  int64_t n_values) {
     if (!ctx || !pop || (!values_host && n_values > 0)) return DEX_ERR_INVALID;
@@ -505,6 +539,11 @@ int dex_population_set_constants(dex_ctx* ctx, dex_population* pop, const void* 
         Instr& ins = pop->h.tape[(size_t)pop->h.const_pos[(size_t)k]];
         if (es == 4) { std::memcpy(&ins.c_lo, static_cast<const float*>(values_host) + k, 4); ins.c_hi = 0; }
         else { uint64_t u; std::memcpy(&u, static_cast<const double*>(values_host) + k, 8); ins.c_lo = (uint32_t)u; ins.c_hi = (uint32_t)(u >> 32); }
+        PackedPopulation& f = *pop->h.folded;
+        const int64_t fp = f.const_pos[(size_t)k];
+        Instr& fi = fp >= 0 ? f.tape[(size_t)fp] : f.ctape[(size_t)(-(fp + 1))];
+        fi.c_lo = ins.c_lo;
+        fi.c_hi = ins.c_hi;
     }
     if (pop->device < 0 || n_values == 0) return DEX_OK;
     int rc = ensure_device(ctx);
@@ -513,10 +552,13 @@ int dex_population_set_constants(dex_ctx* ctx, dex_population* pop, const void* 
     if ((rc = ensure_dev_io(ctx, (size_t)n_values * es))) return rc;
     std::memcpy(ctx->pinned, values_host, (size_t)n_values * es);
     CU(ctx, cudaMemcpyAsync(ctx->dev_io, ctx->pinned, (size_t)n_values * es, cudaMemcpyHostToDevice, ctx->stream));
-    cudaError_t e = launch_scatter_constants(pop->h.dtype, pop->d_tape, pop->d_const_pos, ctx->dev_io,
+    cudaError_t e = launch_scatter_constants(pop->h.dtype, pop->d_tape, nullptr, pop->d_const_pos, ctx->dev_io,
                                              n_values, ctx->stream);
+    if (e == cudaSuccess)
+        e = launch_scatter_constants(pop->h.dtype, pop->d_ftape, pop->d_ctape, pop->d_fconst_pos, ctx->dev_io,
+                                     n_values, ctx->stream);
     if (e != cudaSuccess) return cuda_err(ctx, e, "scatter constants");
-    ctx->launches += 1;
+    ctx->launches += 2;
     CU(ctx, cudaStreamSynchronize(ctx->stream));  // pinned staging is reused by later calls
     return DEX_OK;
 }
@@ -564,7 +606,7 @@ int dex_eval_loss(dex_ctx* ctx, const dex_population* pop, const void* X_dev, in
     if (pop->h.max_parameter >= 0) return set_err(ctx, DEX_ERR_INVALID, "population has parameter leaves");
     if (pop->h.n_trees == 0) return DEX_OK;
     int threads; size_t smem;
-    const int64_t n_tiles = eval_num_tiles(pop->h.dtype, nfeatures, pop->h.max_stack + pop->h.n_param_rows, std::max<int64_t>(nsamples, 1), &threads, &smem);
+    const int64_t n_tiles = eval_num_tiles(pop->h.dtype, nfeatures, pop->h.folded->max_stack + pop->h.n_param_rows, std::max<int64_t>(nsamples, 1), &threads, &smem);
     if ((rc = ensure_scratch(ctx, (size_t)n_tiles * (size_t)pop->h.n_trees * sizeof(double)))) return rc;
     double* partial = static_cast<double*>(ctx->scratch);
     if ((rc = run_eval(ctx, pop, X_dev, nfeatures, nsamples, ldx, nullptr, 0, ok_dev, eval_flags, nullptr, 0,

@@ -561,28 +561,86 @@ __global__ void __launch_bounds__(DEX_MAX_THREADS, DEX_MIN_CTAS) eval_kernel(con
     }
 }
 
+// Constant-subtree folding of tree t: runs the scalar segments of the tree (dex_tape.h,
+// PackedPopulation::ctape) and stores each result into the inline-constant slot of the
+// instruction that consumes it.  Same operator code as the sample loop.  Returns false when
+// a value the reference's scalar walk checks is not finite (_eval_constant_tree returns
+// ResultOk(.., false), /root/reference/src/Evaluate.jl:1059-1114) — whatever early_exit says.
+template <typename T>
+__device__ bool fold_tree(Instr* tape, const Instr* ctape, const int64_t* seg, const int64_t* seg_off, int64_t t) {
+    bool ok = true;
+    T st[MAX_STACK_ROWS + 1];
+    for (int64_t sg = seg_off[t]; sg < seg_off[t + 1]; ++sg) {
+        const int64_t begin = seg[3 * sg], end = seg[3 * sg + 1], target = seg[3 * sg + 2];
+        T acc = T(0);
+        for (int64_t pc = begin; pc < end; ++pc) {
+            const uint4 ins = *reinterpret_cast<const uint4*>(ctape + pc);
+            const uint32_t w0 = ins.x;
+            const T c = const_of<T>(ins);
+            if (w0 & F_PUSH) st[push_row(w0)] = acc;
+            const uint32_t sa = (w0 >> 16) & 3u, sb = (w0 >> 18) & 3u;
+            const T x = sa == SRC_ROW ? st[row_a(ins.y)] : (sa == SRC_CONST ? c : acc);
+            const T y = sb == SRC_ROW ? st[row_b(ins.y)] : (sb == SRC_CONST ? c : acc);
+            const T z = acc;
+            if ((w0 & F_CHK_A) && !t_finite(x)) ok = false;
+            if ((w0 & F_CHK_B) && !t_finite(y)) ok = false;
+            T v;
+            switch ((w0 >> 8) & 0xffu) {
+#define U_CASE(SYM, VEXPR, GEXPR) case DEX_OP_##SYM: v = (VEXPR); break;
+                DEX_UNARY_OPS(U_CASE)
+#undef U_CASE
+#define B_CASE(SYM, VEXPR, G0, G1) case DEX_OP_##SYM: v = (VEXPR); break;
+                DEX_BINARY_OPS(B_CASE)
+#undef B_CASE
+#define T_CASE(SYM, VEXPR, G0, G1, G2) case DEX_OP_##SYM: v = (VEXPR); break;
+                DEX_TERNARY_OPS(T_CASE)
+#undef T_CASE
+                default: v = t_nan<T>(); break;
+            }
+            (void)y; (void)z;
+            if ((w0 & F_CHK_OUT) && !t_finite(v)) ok = false;
+            acc = v;
+        }
+        if (target >= 0) {
+            uint32_t lo, hi;
+            if (sizeof(T) == 4) { lo = __float_as_uint((float)acc); hi = 0; }
+            else { lo = (uint32_t)__double2loint((double)acc); hi = (uint32_t)__double2hiint((double)acc); }
+            tape[target].c_lo = lo;
+            tape[target].c_hi = hi;
+        }
+    }
+    return ok;
+}
+
 // Pre-pass: XT[f][s] = X[f, min(s, N-1)] for s < Npad — the feature-major, tile-padded image
-// of the caller's column-major X that the interpreter stages with bulk async copies.  Also
-// presets ok[] to 1.  X is tiny next to the results (F*N vs P*N elements).
+// of the caller's column-major X that the interpreter stages with bulk async copies.  The
+// first n_trees threads also fold the constant subtrees of one tree each and preset ok[] to
+// the outcome (1 unless a folded constant is invalid).  X is tiny next to the results (F*N vs
+// P*N elements), the scalar tape tiny next to the sample loop.
 template <typename T>
 __global__ void transpose_pad_kernel(const T* __restrict__ X, int64_t ldx, int F, int64_t N,
-                                     T* __restrict__ XT, int64_t Npad, uint8_t* ok, int64_t n_trees) {
+                                     T* __restrict__ XT, int64_t Npad, uint8_t* ok, int64_t n_trees,
+                                     Instr* tape, const Instr* ctape, const int64_t* seg,
+                                     const int64_t* seg_off) {
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s < n_trees) ok[s] = 1;
-    if (s >= Npad) return;
-    const T* col = X + (s < N ? s : N - 1) * ldx;
-    for (int f = 0; f < F; ++f) XT[(size_t)f * Npad + s] = __ldg(col + f);
+    if (s < Npad) {
+        const T* col = X + (s < N ? s : N - 1) * ldx;
+        for (int f = 0; f < F; ++f) XT[(size_t)f * Npad + s] = __ldg(col + f);
+    }
+    if (s < n_trees) ok[s] = (!seg_off || fold_tree<T>(tape, ctape, seg, seg_off, s)) ? 1 : 0;
 }
 
 template <typename T>
-__global__ void scatter_constants_kernel(Instr* tape, const int64_t* pos, const T* values, int64_t n) {
+__global__ void scatter_constants_kernel(Instr* tape, Instr* scalar_tape, const int64_t* pos, const T* values, int64_t n) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const T v = values[i];
     uint32_t lo, hi;
     if (sizeof(T) == 4) { lo = __float_as_uint((float)v); hi = 0; }
     else { lo = (uint32_t)__double2loint((double)v); hi = (uint32_t)__double2hiint((double)v); }
-    if (pos[i] >= 0) { tape[pos[i]].c_lo = lo; tape[pos[i]].c_hi = hi; }
+    const int64_t p = pos[i];
+    Instr* dst = p >= 0 ? tape + p : (scalar_tape ? scalar_tape - (p + 1) : nullptr);
+    if (dst) { dst->c_lo = lo; dst->c_hi = hi; }
 }
 
 __global__ void loss_reduce_kernel(const double* partial, int64_t n_tiles, int64_t n_trees,
@@ -687,10 +745,12 @@ cudaError_t launch_eval(const EvalArgs& e, cudaStream_t stream, int sm_count, in
     if (!e.skip_prepass) {
         if (e.dtype == DEX_F32)
             transpose_pad_kernel<float><<<(unsigned)((cover + 255) / 256), 256, 0, stream>>>(
-                static_cast<const float*>(e.X), e.ldx, e.F, e.N, static_cast<float*>(e.xt), Npad, e.ok, e.n_trees);
+                static_cast<const float*>(e.X), e.ldx, e.F, e.N, static_cast<float*>(e.xt), Npad, e.ok, e.n_trees,
+                const_cast<Instr*>(e.tape), e.ctape, e.seg, e.seg_off);
         else
             transpose_pad_kernel<double><<<(unsigned)((cover + 255) / 256), 256, 0, stream>>>(
-                static_cast<const double*>(e.X), e.ldx, e.F, e.N, static_cast<double*>(e.xt), Npad, e.ok, e.n_trees);
+                static_cast<const double*>(e.X), e.ldx, e.F, e.N, static_cast<double*>(e.xt), Npad, e.ok, e.n_trees,
+                const_cast<Instr*>(e.tape), e.ctape, e.seg, e.seg_off);
         err = cudaGetLastError();
         if (err != cudaSuccess) return err;
         if (launches) *launches += 1;
@@ -704,14 +764,14 @@ cudaError_t launch_eval(const EvalArgs& e, cudaStream_t stream, int sm_count, in
     return err;
 }
 
-cudaError_t launch_scatter_constants(int dtype, Instr* tape, const int64_t* pos, const void* values,
-                                     int64_t n, cudaStream_t stream) {
+cudaError_t launch_scatter_constants(int dtype, Instr* tape, Instr* scalar_tape, const int64_t* pos,
+                                     const void* values, int64_t n, cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
     const unsigned blocks = (unsigned)((n + 255) / 256);
     if (dtype == DEX_F32)
-        scatter_constants_kernel<float><<<blocks, 256, 0, stream>>>(tape, pos, static_cast<const float*>(values), n);
+        scatter_constants_kernel<float><<<blocks, 256, 0, stream>>>(tape, scalar_tape, pos, static_cast<const float*>(values), n);
     else
-        scatter_constants_kernel<double><<<blocks, 256, 0, stream>>>(tape, pos, static_cast<const double*>(values), n);
+        scatter_constants_kernel<double><<<blocks, 256, 0, stream>>>(tape, scalar_tape, pos, static_cast<const double*>(values), n);
     return cudaGetLastError();
 }
 

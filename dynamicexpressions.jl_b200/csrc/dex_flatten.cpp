@@ -10,6 +10,7 @@
 
 #include <algorithm>
 #include <cstring>
+#include <limits>
 
 #include "../../include/dexb200.h"
 
@@ -25,6 +26,8 @@ struct Flattener {
     int64_t n = 0;
     int dtype;
     bool fused, bumper;
+    bool fold = false;             // emit the folded image (constant subtrees -> scalar tape)
+    bool in_fold = false;          // currently generating a scalar segment
     std::vector<int32_t> size;     // subtree sizes
     std::vector<uint8_t> isconst;  // subtree has no feature/parameter leaf
     std::vector<int32_t> need;     // stack slots needed with ACC free
@@ -35,9 +38,9 @@ struct Flattener {
     int64_t const_base = 0;  // global ordinal of this tree's first constant
     int max_slot = 0;        // slots used by the tree being emitted
 
-    Flattener(const OpTable& o, int dt, int pack_flags, PackedPopulation& p, std::string& e)
+    Flattener(const OpTable& o, int dt, int pack_flags, bool fold_, PackedPopulation& p, std::string& e)
         : ops(o), dtype(dt), fused((pack_flags & DEX_PACK_FUSED) != 0),
-          bumper((pack_flags & DEX_PACK_BUMPER) != 0), out(p), err(e) {}
+          bumper((pack_flags & DEX_PACK_BUMPER) != 0), fold(fold_), out(p), err(e) {}
 
     int fail(int code, const std::string& msg) {
         err = "tree " + std::to_string(tree_index) + ": " + msg;
@@ -79,7 +82,10 @@ struct Flattener {
         if (x.degree == 1) {
             need[i] = need[ch[0]];
         } else if (x.degree == 2) {
-            bool ll = nd[ch[0]].degree == 0, rl = nd[ch[1]].degree == 0;
+            // a folded constant subtree is an inline constant of its consumer, like a leaf
+            const bool fl = fold && !bumper;
+            bool ll = nd[ch[0]].degree == 0 || (fl && isconst[ch[0]]);
+            bool rl = nd[ch[1]].degree == 0 || (fl && isconst[ch[1]]);
             if (ll && rl) need[i] = 0;
             else if (ll) need[i] = need[ch[1]];
             else if (rl) need[i] = need[ch[0]];
@@ -110,6 +116,7 @@ struct Flattener {
         double c = 0.0;
         int32_t cord = -1;
         bool chk = false;
+        int64_t fold = -1;  // index (in out.seg) of the scalar segment that produces this constant
     };
     // one instruction before lowering
     struct EIns {
@@ -225,6 +232,50 @@ struct Flattener {
         return f;
     }
 
+    // ---- constant-subtree folding ---------------------------------------------------------
+    bool foldable(int64_t i, bool allow_fold = true) const {
+        return fold && !bumper && !in_fold && allow_fold && nd[i].degree > 0 && isconst[i];
+    }
+    // Generates the scalar segment of constant subtree i and returns the inline-constant
+    // operand that stands for it.  Its validity (every value the reference's scalar walk
+    // checks) is reported by the fold pass per tree, not by a check in the sample loop.
+    int fold_operand(int64_t i, int rec, Opnd& o) {
+        std::vector<EIns> saved;
+        saved.swap(cur);
+        const int saved_last = last, saved_slots = max_slot;
+        max_slot = 0;
+        in_fold = true;
+        int rc = gen(i, -1, 0, true, false, rec + 1);
+        in_fold = false;
+        if (!rc) {
+            const int64_t begin = (int64_t)out.ctape.size();
+            lower(cur, true);
+            o = Opnd();
+            o.src = SRC_CONST;
+            o.c = std::numeric_limits<double>::quiet_NaN();   // overwritten by the fold pass
+            o.fold = (int64_t)out.seg.size() / 3;
+            out.seg.push_back(begin);
+            out.seg.push_back((int64_t)out.ctape.size());
+            out.seg.push_back(-1);
+            scalar_slots = std::max(scalar_slots, max_slot);
+        }
+        cur.swap(saved);
+        last = saved_last;
+        max_slot = saved_slots;
+        return rc;
+    }
+    int scalar_slots = 0;
+    // folded subtree -> ACC
+    int emit_load_fold(int64_t i, int push_slot, int rec) {
+        Opnd a;
+        if (int rc = fold_operand(i, rec, a)) return rc;
+        const bool keep = elide;
+        elide = false;
+        emit(DEX_OP_IDENTITY, a, acc(), 0u, push_slot);
+        elide = keep;
+        return DEX_OK;
+    }
+
     // Materialise a leaf into ACC (LOAD = IDENTITY with the leaf as operand A).
     int emit_load(int64_t i, bool feature_checked, bool const_mode, int push_slot) {
         Opnd a = leaf_operand(i, feature_checked, const_mode);
@@ -247,6 +298,7 @@ struct Flattener {
             bool allow_fold = true) {
         if (rec > MAX_RECURSION) return fail(DEX_ERR_UNSUPPORTED, "tree too deep");
         if (depth >= MAX_STACK_ROWS) return fail(DEX_ERR_UNSUPPORTED, "operand stack deeper than " + std::to_string(MAX_STACK_ROWS));
+        if (foldable(i, allow_fold) && !const_mode) return emit_load_fold(i, push_slot, rec);
         const dex_node& x = nd[i];
         const int op = opcode(i);
         // constant subtrees are folded by _eval_tree_array (src/Evaluate.jl:347-354) — but the
@@ -298,6 +350,12 @@ struct Flattener {
                 const dex_node& L = nd[l];
                 bool branch0 = fused2 && L.degree == 2 && leaf(child(l, 0)) && leaf(child(l, 1));
                 if (branch0) chk = true;  // branch0 :left, x3 checked (:799)
+                if (foldable(l, !branch0) && !const_mode && nd[r].kind != DEX_LEAF_CONST) {
+                    Opnd a;
+                    if ((rc = fold_operand(l, rec, a))) return rc;
+                    emit(op, a, leaf_operand(r, chk, const_mode), out_flags(const_mode, false), push_slot);
+                    return DEX_OK;
+                }
                 if ((rc = gen(l, push_slot, depth, const_mode, false, rec + 1, !branch0))) return rc;
                 const int ci = last;
                 const int p = emit(op, acc(), leaf_operand(r, chk, const_mode), out_flags(const_mode, false), -1);
@@ -309,13 +367,32 @@ struct Flattener {
                 const dex_node& R = nd[r];
                 bool branch0 = fused2 && R.degree == 2 && leaf(child(r, 0)) && leaf(child(r, 1));
                 if (branch0) chk = true;  // branch0 :right, x1 checked (:810)
+                if (foldable(r, !branch0) && !const_mode && nd[l].kind != DEX_LEAF_CONST) {
+                    Opnd b;
+                    if ((rc = fold_operand(r, rec, b))) return rc;
+                    emit(op, leaf_operand(l, chk, const_mode), b, out_flags(const_mode, false), push_slot);
+                    return DEX_OK;
+                }
                 if ((rc = gen(r, push_slot, depth, const_mode, false, rec + 1, !branch0))) return rc;
                 const int ci = last;
                 const int p = emit(op, leaf_operand(l, chk, const_mode), acc(), out_flags(const_mode, false), -1);
                 elide_result(ci, p, 1);
                 return DEX_OK;
             }
-            // both children are operators: evaluate the one needing more stack first
+            // both children are operators; one of them may be a folded constant subtree, which
+            // the other one's consumer takes as its inline constant
+            if (!const_mode && (foldable(l) != foldable(r))) {
+                const bool lf = foldable(l);
+                if ((rc = gen(lf ? r : l, push_slot, depth, const_mode, false, rec + 1))) return rc;
+                const int ci = last;
+                Opnd k;
+                if ((rc = fold_operand(lf ? l : r, rec, k))) return rc;
+                const int p = lf ? emit(op, k, acc(), out_flags(const_mode, false), -1)
+                                 : emit(op, acc(), k, out_flags(const_mode, false), -1);
+                elide_result(ci, p, lf ? 1 : 0);
+                return DEX_OK;
+            }
+            // evaluate the one needing more stack first
             bool left_first = need[l] >= need[r];
             int64_t first = left_first ? l : r, second = left_first ? r : l;
             if ((rc = gen(first, push_slot, depth, const_mode, false, rec + 1))) return rc;
@@ -427,13 +504,15 @@ struct Flattener {
         }
     }
 
-    void lower_tree() {
+    // scalar == true: a folded constant subtree; its instructions go to the scalar tape, which
+    // a one-thread interpreter runs (generic decode, no rows to rebase)
+    void lower(const std::vector<EIns>& list, bool scalar) {
         // unary operator on an inline constant (only inside constant subtrees): split into
         // LOAD_C + OP_A so that both halves take specialised handlers
         std::vector<EIns> split;
-        split.reserve(cur.size());
-        for (const EIns& e : cur) {
-            if (e.op < 64 && e.op != DEX_OP_IDENTITY && e.a.src == SRC_CONST && fast_unary(e.op)) {
+        split.reserve(list.size());
+        for (const EIns& e : list) {
+            if (!scalar && e.op < 64 && e.op != DEX_OP_IDENTITY && e.a.src == SRC_CONST && fast_unary(e.op)) {
                 EIns ld{DEX_OP_IDENTITY, e.a, acc(), e.flags & F_ALWAYS, e.push_slot};
                 EIns op{e.op, acc(), acc(), e.flags, -1};
                 split.push_back(ld);
@@ -442,6 +521,7 @@ struct Flattener {
                 split.push_back(e);
             }
         }
+        std::vector<Instr>& tape = scalar ? out.ctape : out.tape;
         for (EIns e : split) {
             // commutative operators: bring the operands into (ACC|ROW, ROW|CONST) order
             if (commutative(e.op)) {
@@ -451,25 +531,31 @@ struct Flattener {
             Instr ins{};
             const bool a_chk_row = e.a.chk && e.a.src != SRC_CONST && e.a.src != SRC_ACC;
             const bool b_chk_row = e.b.chk && e.b.src != SRC_CONST && e.b.src != SRC_ACC;
-            const uint32_t h = pick_handler(e, a_chk_row, b_chk_row);
+            const uint32_t h = scalar ? (uint32_t)H_GENERIC : pick_handler(e, a_chk_row, b_chk_row);
             ins.w0 = h | ((uint32_t)e.op << 8) | (e.a.src << 16) | (e.b.src << 18) | e.flags;
             if (e.a.chk) ins.w0 |= F_CHK_A;
             if (e.b.chk) ins.w0 |= F_CHK_B;
             if ((e.a.chk && e.a.src == SRC_CONST) || (e.b.chk && e.b.src == SRC_CONST)) ins.w0 |= F_CHK_CONST;
             if (e.push_slot >= 0) ins.w0 |= F_PUSH | HANDLER_PUSH | ((uint32_t)e.push_slot << PUSH_ROW_SHIFT);
-            // feature rows are rebased behind the stack rows once max_stack is known:
-            // bit 31/30 of the scratch word c_hi-independent marker is kept in `rebase`
+            // feature and parameter rows are rebased behind the stack rows once max_stack is known
             uint32_t ra = e.a.row, rb = e.b.row;
             ins.w1 = (ra & 0xffffu) | (rb << 16);
-            rebase.push_back((uint8_t)((e.a.is_feature ? 1 : 0) | (e.b.is_feature ? 2 : 0) |
-                                       (e.a.is_param ? 4 : 0) | (e.b.is_param ? 8 : 0)));
-            const int64_t idx = (int64_t)out.tape.size();
-            if (e.a.src == SRC_CONST) { put_const(ins, e.a.c); if (e.a.cord >= 0) out.const_pos[const_base + e.a.cord] = idx; }
-            if (e.b.src == SRC_CONST) { put_const(ins, e.b.c); if (e.b.cord >= 0) out.const_pos[const_base + e.b.cord] = idx; }
-            out.tape_const_ord.push_back(e.a.src == SRC_CONST ? e.a.cord : e.b.src == SRC_CONST ? e.b.cord : -1);
-            if (h == H_GENERIC) ++out.n_generic;
-            out.n_checks += ((ins.w0 & F_CHK_OUT) ? 1 : 0) + (e.a.chk ? 1 : 0) + (e.b.chk ? 1 : 0);
-            out.tape.push_back(ins);
+            const int64_t idx = (int64_t)tape.size();
+            const int64_t pos = scalar ? -(1 + idx) : idx;
+            for (const Opnd* o : {&e.a, &e.b}) {
+                if (o->src != SRC_CONST) continue;
+                put_const(ins, o->c);
+                if (o->cord >= 0) out.const_pos[const_base + o->cord] = pos;
+                if (o->fold >= 0) out.seg[(size_t)o->fold * 3 + 2] = idx;   // the fold pass stores here
+            }
+            if (!scalar) {
+                rebase.push_back((uint8_t)((e.a.is_feature ? 1 : 0) | (e.b.is_feature ? 2 : 0) |
+                                           (e.a.is_param ? 4 : 0) | (e.b.is_param ? 8 : 0)));
+                out.tape_const_ord.push_back(e.a.src == SRC_CONST ? e.a.cord : e.b.src == SRC_CONST ? e.b.cord : -1);
+                if (h == H_GENERIC) ++out.n_generic;
+                out.n_checks += ((ins.w0 & F_CHK_OUT) ? 1 : 0) + (e.a.chk ? 1 : 0) + (e.b.chk ? 1 : 0);
+            }
+            tape.push_back(ins);
         }
     }
     std::vector<uint8_t> rebase;  // per tape instruction: bit0 rowA is a feature, bit1 rowB is a feature
@@ -478,6 +564,7 @@ struct Flattener {
     int run(const dex_node* nodes, const int64_t* offsets, int64_t n_trees) {
         out.tape_off.assign(1, 0);
         out.const_off.assign(1, 0);
+        out.seg_off.assign(1, 0);
         for (int64_t t = 0; t < n_trees; ++t) {
             tree_index = t;
             nd = nodes + offsets[t];
@@ -508,7 +595,8 @@ struct Flattener {
             } else if ((rc = gen(0, -1, 0, false, false, 0))) {
                 return rc;
             }
-            lower_tree();
+            lower(cur, false);
+            out.seg_off.push_back((int64_t)out.seg.size() / 3);
             out.max_stack = std::max(out.max_stack, max_slot);
             out.n_constants += nc;
             out.n_nodes += n;
@@ -546,9 +634,17 @@ int flatten_population(const OpTable& ops, const void* nodes, const int64_t* off
     out = PackedPopulation();
     out.dtype = dtype;
     out.pack_flags = pack_flags;
-    Flattener f(ops, dtype, pack_flags, out, err);
+    Flattener f(ops, dtype, pack_flags, false, out, err);
     int rc = f.run(reinterpret_cast<const dex_node*>(nodes), offsets, n_trees);
     if (rc) return rc;
+    // second image for evaluation: constant subtrees folded into the scalar tape
+    auto folded = std::make_shared<PackedPopulation>();
+    folded->dtype = dtype;
+    folded->pack_flags = pack_flags;
+    Flattener g(ops, dtype, pack_flags, true, *folded, err);
+    rc = g.run(reinterpret_cast<const dex_node*>(nodes), offsets, n_trees);
+    if (rc) return rc;
+    out.folded = folded;
     return DEX_OK;
 }
 

@@ -12,6 +12,11 @@ struct EvalArgs {
     int dtype;                  // DEX_F32 / DEX_F64
     const Instr* tape;          // device
     const int64_t* tape_off;    // device, n_trees + 1
+    // constant-subtree folding (null seg_off => nothing to fold): the prepass runs the scalar
+    // tape and stores the results into the constant slots of `tape`
+    const Instr* ctape;         // device
+    const int64_t* seg;         // device, 3 per folded subtree: ctape begin, end, target in `tape`
+    const int64_t* seg_off;     // device, n_trees + 1
     int64_t n_trees;
     const int32_t* chunk_start; // device, n_chunks + 1 (tree index ranges, balanced by tape length)
     int32_t n_chunks;
@@ -76,8 +81,9 @@ int64_t grad_num_tiles(int dtype, int F, int max_stack, int Gmax, int64_t N);
 size_t grad_xt_bytes(int dtype, int F, int max_stack, int Gmax, int64_t N);
 
 // tiny helpers
-cudaError_t launch_scatter_constants(int dtype, Instr* tape, const int64_t* pos, const void* values,
-                                     int64_t n, cudaStream_t stream);
+// pos[i] >= 0: tape[pos[i]]; pos[i] < 0: scalar_tape[-(1 + pos[i])] (folded image)
+cudaError_t launch_scatter_constants(int dtype, Instr* tape, Instr* scalar_tape, const int64_t* pos,
+                                     const void* values, int64_t n, cudaStream_t stream);
 cudaError_t launch_loss_reduce(const double* partial, int64_t n_tiles, int64_t n_trees,
                                double denom_inv, double* loss, cudaStream_t stream);
 

@@ -20,6 +20,7 @@
 // generic path (any operator, any operand source, every flag).
 #pragma once
 #include <cstdint>
+#include <memory>
 #include <vector>
 #include <string>
 
@@ -128,8 +129,21 @@ struct PackedPopulation {
     std::vector<int32_t> n_nodes_tree;     // count_nodes per tree
     std::vector<int32_t> n_const_tree;     // count_constant_nodes per tree
     std::vector<int64_t> const_off;        // n_trees + 1 (prefix of n_const_tree)
-    // constant ordinal (global) -> instruction index in the tape holding its value
+    // constant ordinal (global) -> instruction index in the tape holding its value; in a
+    // folded image a constant that lives in the scalar tape is stored as -(1 + ctape index)
     std::vector<int64_t> const_pos;
+
+    // ---- folded image (evaluation only) ------------------------------------------------
+    // The reference evaluates every maximal constant subtree as a scalar and fills the result
+    // (_eval_constant_tree, /root/reference/src/Evaluate.jl:347-354, 1059-1114).  Device
+    // analogue: `folded` is a second flattening of the same trees in which such a subtree is
+    // ONE inline constant of its consumer; its operators live in the scalar tape `ctape`,
+    // which the prepass kernel runs once per evaluation call (one thread per tree) and whose
+    // results it stores into the constant slots of `folded->tape`.
+    std::vector<Instr> ctape;        // scalar instructions of all folded subtrees
+    std::vector<int64_t> seg;        // per subtree: ctape begin, ctape end, target instruction
+    std::vector<int64_t> seg_off;    // n_trees + 1: subtrees of tree t are seg_off[t]..seg_off[t+1]
+    std::shared_ptr<PackedPopulation> folded;   // only set on the outer (unfolded) image
 };
 
 // Flatten `n_trees` wire trees.  Returns 0 or a negative DEX_ERR_* code with a

@@ -61,6 +61,7 @@ ABI = {
     "dex_host_free": (C.c_int, [_P]),
     "dex_ctx_launch_count": (_I64, [_P]),
     "dex_population_copy_tape": (_I64, [_P, _P, _I64, _P]),
+    "dex_population_copy_folded": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "dex_handler_name": (C.c_char_p, [C.c_int]),
 }
 
@@ -74,7 +75,9 @@ class DexError(RuntimeError):
 class _Info(C.Structure):
     _fields_ = [("n_trees", _I64), ("n_nodes", _I64), ("n_instructions", _I64),
                 ("n_constants", _I64), ("max_stack", _I32), ("max_feature", _I32),
-                ("max_parameter", _I32), ("dtype", _I32), ("n_generic", _I64), ("n_checks", _I64)]
+                ("max_parameter", _I32), ("dtype", _I32), ("n_generic", _I64), ("n_checks", _I64),
+                ("n_folded_instructions", _I64), ("n_scalar_instructions", _I64),
+                ("n_folded_subtrees", _I64), ("folded_max_stack", _I32), ("reserved0", _I32)]
 
 
 _lib = None
@@ -290,6 +293,18 @@ class Population:
         off = np.zeros(self.n_trees + 1, dtype=np.int64)
         lib().dex_population_copy_tape(self.h, _ptr(ins), n, _ptr(off))
         return ins, off
+
+    def folded(self):
+        """Host copy of the image dex_eval* run: dict(tape, offsets, scalar_tape, segs, seg_offsets);
+        segs[k] = (scalar begin, scalar end, target instruction in `tape`)."""
+        nf, ns, nk = (self.info[k] for k in ("n_folded_instructions", "n_scalar_instructions", "n_folded_subtrees"))
+        ins = np.zeros((nf, 4), dtype=np.uint32)
+        off = np.zeros(self.n_trees + 1, dtype=np.int64)
+        sc = np.zeros((ns, 4), dtype=np.uint32)
+        segs = np.zeros((nk, 3), dtype=np.int64)
+        soff = np.zeros(self.n_trees + 1, dtype=np.int64)
+        lib().dex_population_copy_folded(self.h, _ptr(ins), _ptr(off), _ptr(sc), _ptr(segs), _ptr(soff))
+        return dict(tape=ins, offsets=off, scalar_tape=sc, segs=segs, seg_offsets=soff)
 
     # -- evaluation ------------------------------------------------------------------
     def _outputs(self, N, out, ok):

@@ -124,6 +124,12 @@ typedef struct dex_population_info {
     int32_t dtype;
     int64_t n_generic;        /* instructions executed by the generic (non-specialised) handler */
     int64_t n_checks;         /* validity checks left after host-side elision                   */
+    /* the image dex_eval* run: constant subtrees (Evaluate.jl:347-354) folded into scalars   */
+    int64_t n_folded_instructions;  /* sample-loop instructions after folding                  */
+    int64_t n_scalar_instructions;  /* instructions of the folded subtrees (run once per call)  */
+    int64_t n_folded_subtrees;
+    int32_t folded_max_stack;       /* operand-stack rows of the folded image                   */
+    int32_t reserved0;
 } dex_population_info;
 int dex_population_get_info(const dex_population* pop, dex_population_info* info);
 /* per-tree count_constant_nodes (/root/reference/src/NodeUtils.jl:43-51); counts[n_trees] */
@@ -197,6 +203,13 @@ const char* dex_handler_name(int handler);
  * returns the instruction count; offsets (n_trees+1) may be NULL */
 int64_t dex_population_copy_tape(const dex_population* pop, void* instrs, int64_t capacity,
                                  int64_t* offsets);
+/* host image of what dex_eval* execute: the folded tape (n_folded_instructions, offsets
+ * n_trees+1), the scalar tape (n_scalar_instructions) and its segment table — per folded
+ * subtree three int64: scalar-tape begin, end, and the folded-tape instruction whose inline
+ * constant receives the result; seg_offsets (n_trees+1) delimits the subtrees of each tree.
+ * Any pointer may be NULL. */
+int dex_population_copy_folded(const dex_population* pop, void* instrs, int64_t* offsets,
+                               void* scalar_instrs, int64_t* segs, int64_t* seg_offsets);
 
 #ifdef __cplusplus
 }

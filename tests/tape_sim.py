@@ -122,3 +122,28 @@ def run_tape(ins, X, max_stack, opcode_info, dtype, early_exit=True, params=None
         if chk and (w0 & F_CHK_OUT) and bad(r):
             ok = False
     return acc, ok
+
+
+def run_folded(img, t, X, max_stack, opcode_info, dtype, early_exit=True, params=None, classes0=None,
+               n_param_rows=0):
+    """What dex_eval* execute for tree t of Population.folded(): the scalar segments of its
+    constant subtrees first (prepass kernel, csrc/dex_eval.cu fold_tree: every check applies,
+    whatever early_exit says), their results stored into the constant slots of the folded
+    tape, then the folded tape over the samples."""
+    off = img["offsets"]
+    main = img["tape"][off[t]:off[t + 1]].copy()
+    ok = True
+    empty = np.zeros((0, 1), dtype=dtype)
+    for k in range(img["seg_offsets"][t], img["seg_offsets"][t + 1]):
+        b, e, target = (int(v) for v in img["segs"][k])
+        assert off[t] <= target < off[t + 1], "segment target outside its tree"
+        val, sok = run_tape(img["scalar_tape"][b:e], empty, 32, opcode_info, dtype, early_exit=True)
+        ok = ok and sok
+        w = main[target - off[t]]
+        assert ((int(w[0]) >> 16) & 3) == SRC_CONST or ((int(w[0]) >> 18) & 3) == SRC_CONST
+        raw = np.asarray(val[:1], dtype=dtype).view(np.uint32)
+        w[2] = raw[0]
+        w[3] = raw[1] if dtype == np.float64 else 0
+    y, mok = run_tape(main, X, max_stack, opcode_info, dtype, early_exit=early_exit, params=params,
+                      classes0=classes0, n_param_rows=n_param_rows)
+    return y, (ok and mok)

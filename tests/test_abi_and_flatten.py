@@ -13,7 +13,7 @@ import dexb200
 from dexb200 import device as D
 from dexb200 import treegen
 from tests.golden_util import (CONTEXTS, load_cases, make_matrix, make_operators, make_tree)
-from tests.tape_sim import run_tape
+from tests.tape_sim import run_folded, run_tape
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -116,20 +116,25 @@ def test_flattened_tape_matches_oracle_on_golden_cases(case, oracle):
             c = CONTEXTS[cname]
             pop = D.Population([tree], ops, dtype, ctx=hctx, bumper=c.get("bumper", False),
                                use_fused=c.get("use_fused", True))
-            ins, off = pop.tape()
-            y, ok = run_tape(ins, X, pop.info["max_stack"], dexb200.OPCODE_INFO, dtype,
-                             early_exit=c.get("early_exit", True), params=P, classes0=cls0,
-                             n_param_rows=pop.info["max_parameter"] + 1)
             if P is not None:
                 ry, rok = oracle.eval_parametric(wire, ops.opcodes, X, P, cls0, _flags(oracle, c))
             else:
                 ry, rok = oracle.eval_tree_array(wire, ops.opcodes, X, _flags(oracle, c))
-            assert ok == rok, (case["id"], dt, cname)
-            if rok:
-                tol = 1e-4 if dtype == np.float32 else 1e-9
-                fin = np.isfinite(ry)
-                np.testing.assert_allclose(y[fin], ry[fin], rtol=tol, atol=tol)
-                assert (np.isfinite(y) == fin).all()
+            # the full tape (gradients) and the folded image (evaluation) must both agree
+            ins, off = pop.tape()
+            full = run_tape(ins, X, pop.info["max_stack"], dexb200.OPCODE_INFO, dtype,
+                            early_exit=c.get("early_exit", True), params=P, classes0=cls0,
+                            n_param_rows=pop.info["max_parameter"] + 1)
+            fold = run_folded(pop.folded(), 0, X, pop.info["folded_max_stack"], dexb200.OPCODE_INFO, dtype,
+                              early_exit=c.get("early_exit", True), params=P, classes0=cls0,
+                              n_param_rows=pop.info["max_parameter"] + 1)
+            for which, (y, ok) in (("full", full), ("folded", fold)):
+                assert ok == rok, (case["id"], dt, cname, which)
+                if rok:
+                    tol = 1e-4 if dtype == np.float32 else 1e-9
+                    fin = np.isfinite(ry)
+                    np.testing.assert_allclose(y[fin], ry[fin], rtol=tol, atol=tol)
+                    assert (np.isfinite(y) == fin).all()
 
 
 def _nonfinite_X(rng, F, N, dtype):
@@ -154,7 +159,7 @@ def test_flattened_tape_matches_oracle_on_random_trees(seed, cname, oracle):
     ops = dexb200.OperatorEnum(spec)
     c = CONTEXTS[cname]
     F, N = 4, 24
-    n_checked = 0
+    n_checked = n_folded = 0
     for k in range(60):
         w = _random_wire(rng, ops, F, max_nodes=int(rng.integers(1, 40)))
         dtype = np.float32 if k % 2 else np.float64
@@ -162,16 +167,21 @@ def test_flattened_tape_matches_oracle_on_random_trees(seed, cname, oracle):
         pop = D.Population(None, ops, dtype, ctx=hctx, wire=(w, np.array([0, len(w)])),
                            bumper=c.get("bumper", False), use_fused=c.get("use_fused", True))
         ins, _ = pop.tape()
-        y, ok = run_tape(ins, X, pop.info["max_stack"], dexb200.OPCODE_INFO, dtype,
-                         early_exit=c.get("early_exit", True))
         ry, rok = oracle.eval_tree_array(w, ops.opcodes, X, _flags(oracle, c))
-        assert ok == rok, (seed, k, cname, dexb200.string_tree(dexb200.from_wire(w), ops))
-        if rok:
-            n_checked += 1
-            tol = 2e-4 if dtype == np.float32 else 1e-8
-            fin = np.isfinite(ry) & (np.abs(ry) < 1e30)
-            np.testing.assert_allclose(y[fin], ry[fin], rtol=tol, atol=tol)
+        full = run_tape(ins, X, pop.info["max_stack"], dexb200.OPCODE_INFO, dtype,
+                        early_exit=c.get("early_exit", True))
+        fold = run_folded(pop.folded(), 0, X, pop.info["folded_max_stack"], dexb200.OPCODE_INFO, dtype,
+                          early_exit=c.get("early_exit", True))
+        n_folded += pop.info["n_folded_subtrees"]
+        for which, (y, ok) in (("full", full), ("folded", fold)):
+            assert ok == rok, (seed, k, cname, which, dexb200.string_tree(dexb200.from_wire(w), ops))
+            if rok:
+                tol = 2e-4 if dtype == np.float32 else 1e-8
+                fin = np.isfinite(ry) & (np.abs(ry) < 1e30)
+                np.testing.assert_allclose(y[fin], ry[fin], rtol=tol, atol=tol)
+        n_checked += bool(rok)
     assert n_checked > 5
+    assert n_folded > 0 or c.get("bumper")       # the Bumper evaluator does not fold
 
 
 def _random_wire(rng, ops, F, max_nodes):
