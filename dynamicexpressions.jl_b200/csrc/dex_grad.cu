@@ -8,25 +8,57 @@
 // stack in shared memory, and nothing but X in and (value, gradient) out touches HBM.
 //
 // The kernel interprets the SAME fused tape as dex_eval.cu (leaves folded into their
-// consumer, Sethi-Ullman order, absolute stack rows): an operand is ACC, a stack slot, a
-// feature row, or an inline constant, and a leaf's derivative is a one-hot (or zero) vector
-// that is never materialised in memory.
+// consumer, Sethi-Ullman order, absolute stack rows, handler ids): an operand is ACC, a
+// stack slot, a feature row, or an inline constant, and a leaf's derivative is a one-hot (or
+// zero) vector that is never materialised in memory.
 //
 // Mapping
-//   grid.x  sample tiles of blockDim.x * K samples (K = 16 bytes / sizeof(T))
+//   grid.x  sample tiles of TILE = blockDim.x * K samples
 //   grid.y  chunks of trees
-//   thread  K consecutive samples; ACC = (1 + GC) * K registers
+//   thread  K = U * C samples as U 16-byte chunks (C = 4 floats / 2 doubles; chunk u of
+//           thread t covers samples u*(blockDim.x*C) + t*C ..), ACC = (1 + GC) * K registers
 //   smem    stack slot s component c: row s * (1 + GC) + c;  features behind the stack rows
 //   GC      compile-time number of directions per pass (1..8); trees with more directions
 //           (many constants) take several passes, recomputing the primal per pass
-// Semantics: every value and every gradient component of every node, leaves included, must
-// be finite for `complete` (:238-243) — including products with the zeros of a one-hot
-// (Inf * 0 = NaN is a failure in the reference, and here); eval_diff never checks (:68-85).
+//
+// One tape instruction runs in two stages, each entered through one warp-uniform switch:
+//   stage 1 (by HANDLER id = operator x operand forms): fetch the operand values, compute the
+//           value v and the partials p0, p1, note where each operand's derivative lives
+//           (ACC registers / stack slot rows / one-hot leaf) and the coefficient class;
+//   stage 2 (by coefficient class x operand kinds): d[g] = p0 * dA[g] + p1 * dB[g] for the GC
+//           directions, fully unrolled and branch-free.  Classes: ADD (1, 1), SUB (1, -1),
+//           VAR (partials that are finite whenever the node values are: *, max, min, exp,
+//           sin, ...) and GEN (anything: /, sqrt, log, ...).  For ADD/SUB/VAR a one-hot leaf
+//           contributes nothing to the directions it does not own, so those products are
+//           skipped; for GEN they are computed, because an infinite partial times a zero
+//           seed is NaN in the reference (`grad * d_cumulator`, :355-361) and must fail here
+//           too (sqrt(x1) at x1 = 0).
+//
+// Semantics: every VALUE of every node, leaves included, must be finite for `complete`
+// (:238-243) and so must every gradient component.  A non-finite derivative component can
+// never become finite again on its way to the root (d_parent[g] = sum_i p_i * d_i[g]; a
+// non-finite factor makes the product non-finite and a non-finite term makes the sum
+// non-finite), so derivatives are checked once, at the root; values are checked at every
+// node.  eval_diff never checks (:68-85) and takes the GEN class everywhere, so that its
+// non-finite patterns are those of the reference's arithmetic.
 #include "dex_kernels.h"
 #include "dex_ops.cuh"
 #include "../../include/dexb200.h"
 
 #include <algorithm>
+
+#ifndef DEX_GRAD_U
+#define DEX_GRAD_U 1
+#endif
+#ifndef DEX_GRAD_PTX
+#define DEX_GRAD_PTX 1
+#endif
+#ifndef DEX_GRAD_MIN_CTAS
+#define DEX_GRAD_MIN_CTAS 4
+#endif
+#ifndef DEX_GRAD_THREADS
+#define DEX_GRAD_THREADS 128
+#endif
 
 namespace dex {
 namespace {
@@ -42,7 +74,7 @@ template <typename T> struct GK {
     T* grad;
     const int64_t* grad_off;
     uint8_t* ok;
-    int64_t N, ldx, ldo;
+    int64_t N, ldx, ldo, n_trees;
     int32_t F, max_stack, mode, direction;
 };
 
@@ -50,132 +82,335 @@ template <typename T> __device__ __forceinline__ T gconst_of(const uint4& ins);
 template <> __device__ __forceinline__ float gconst_of<float>(const uint4& ins) { return __uint_as_float(ins.z); }
 template <> __device__ __forceinline__ double gconst_of<double>(const uint4& ins) { return __hiloint2double((int)ins.w, (int)ins.z); }
 
-template <typename T, int K> __device__ __forceinline__ void ldv(T (&v)[K], const T* p) {
-    *reinterpret_cast<uint4*>(v) = *reinterpret_cast<const uint4*>(p);
-}
-template <typename T, int K> __device__ __forceinline__ void stv(T* p, const T (&v)[K]) {
-    *reinterpret_cast<uint4*>(p) = *reinterpret_cast<const uint4*>(v);
-}
-
-// how the derivative of an operand is obtained
-enum : int { DK_ACC = 0, DK_SLOT = 1, DK_LEAF = 2 };
-
-// d = p * x   and   d = d + p * x   over the K samples of a thread.  Products and the sum are
-// rounded separately, like the reference's `grad_1 * d_1 + grad_2 * d_2`; Float32 uses
-// Blackwell's packed FMUL2 / FADD2 / FFMA2 (two IEEE operations per instruction).
-template <typename T, int K> struct DOps {
-    static __device__ __forceinline__ void mul(T (&d)[K], const T (&p)[K], const T (&x)[K]) {
+// ---- K-vectors of one thread ------------------------------------------------------------
+template <typename T, int U> struct VK {
+    static constexpr int C = 16 / (int)sizeof(T);
+    static constexpr int K = U * C;
+    static __device__ __forceinline__ void ld(T (&v)[K], const T* p, int CS) {
 #pragma unroll
-        for (int k = 0; k < K; ++k) d[k] = p[k] * x[k];
+        for (int u = 0; u < U; ++u)
+            *reinterpret_cast<uint4*>(&v[u * C]) = *reinterpret_cast<const uint4*>(p + u * CS);
     }
-    static __device__ __forceinline__ void mul_add(T (&d)[K], const T (&p)[K], const T (&x)[K]) {
+    static __device__ __forceinline__ void st(T* p, int CS, const T (&v)[K]) {
 #pragma unroll
-        for (int k = 0; k < K; ++k) d[k] = d[k] + p[k] * x[k];
-    }
-    static __device__ __forceinline__ void check(T& nf, const T (&d)[K]) {
-#pragma unroll
-        for (int k = 0; k < K; ++k) nf = m_fma(d[k], T(0), nf);
+        for (int u = 0; u < U; ++u)
+            *reinterpret_cast<uint4*>(p + u * CS) = *reinterpret_cast<const uint4*>(&v[u * C]);
     }
 };
-template <int K> struct DOps<float, K> {
-    static __device__ __forceinline__ void mul(float (&d)[K], const float (&p)[K], const float (&x)[K]) {
+
+// element-wise arithmetic; every operation rounds once, like the reference's scalar code.
+// Float32 uses Blackwell's packed FMUL2 / FADD2 / FFMA2 (two IEEE operations per instruction).
+template <typename T, int K> struct VA {
+    static __device__ __forceinline__ void mul(T (&d)[K], const T (&a)[K], const T (&b)[K]) {
 #pragma unroll
-        for (int k = 0; k < K; k += 2) {
-            const float2 r = __fmul2_rn(make_float2(p[k], p[k + 1]), make_float2(x[k], x[k + 1]));
-            d[k] = r.x; d[k + 1] = r.y;
-        }
+        for (int k = 0; k < K; ++k) d[k] = a[k] * b[k];
     }
-    static __device__ __forceinline__ void mul_add(float (&d)[K], const float (&p)[K], const float (&x)[K]) {
+    static __device__ __forceinline__ void muls(T (&d)[K], const T (&a)[K], T s) {
 #pragma unroll
-        for (int k = 0; k < K; k += 2) {
-            const float2 m = __fmul2_rn(make_float2(p[k], p[k + 1]), make_float2(x[k], x[k + 1]));
-            const float2 r = __fadd2_rn(make_float2(d[k], d[k + 1]), m);
-            d[k] = r.x; d[k + 1] = r.y;
-        }
+        for (int k = 0; k < K; ++k) d[k] = a[k] * s;
     }
-    static __device__ __forceinline__ void check(float& nf, const float (&d)[K]) {
+    static __device__ __forceinline__ void add(T (&d)[K], const T (&a)[K], const T (&b)[K]) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) d[k] = a[k] + b[k];
+    }
+    static __device__ __forceinline__ void adds(T (&d)[K], const T (&a)[K], T s) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) d[k] = a[k] + s;
+    }
+    static __device__ __forceinline__ void sub(T (&d)[K], const T (&a)[K], const T (&b)[K]) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) d[k] = a[k] - b[k];
+    }
+    static __device__ __forceinline__ void neg(T (&d)[K], const T (&a)[K]) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) d[k] = -a[k];
+    }
+    static __device__ __forceinline__ void check(T& nf, const T (&a)[K]) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) nf = m_fma(a[k], T(0), nf);
+    }
+};
+template <int K> struct VA<float, K> {
+    static __device__ __forceinline__ float2 f2(const float* p) { return make_float2(p[0], p[1]); }
+    static __device__ __forceinline__ void mul(float (&d)[K], const float (&a)[K], const float (&b)[K]) {
+#pragma unroll
+        for (int k = 0; k < K; k += 2) { const float2 r = __fmul2_rn(f2(a + k), f2(b + k)); d[k] = r.x; d[k + 1] = r.y; }
+    }
+    static __device__ __forceinline__ void muls(float (&d)[K], const float (&a)[K], float s) {
+        const float2 ss = make_float2(s, s);
+#pragma unroll
+        for (int k = 0; k < K; k += 2) { const float2 r = __fmul2_rn(f2(a + k), ss); d[k] = r.x; d[k + 1] = r.y; }
+    }
+    static __device__ __forceinline__ void add(float (&d)[K], const float (&a)[K], const float (&b)[K]) {
+#pragma unroll
+        for (int k = 0; k < K; k += 2) { const float2 r = __fadd2_rn(f2(a + k), f2(b + k)); d[k] = r.x; d[k + 1] = r.y; }
+    }
+    static __device__ __forceinline__ void adds(float (&d)[K], const float (&a)[K], float s) {
+        const float2 ss = make_float2(s, s);
+#pragma unroll
+        for (int k = 0; k < K; k += 2) { const float2 r = __fadd2_rn(f2(a + k), ss); d[k] = r.x; d[k + 1] = r.y; }
+    }
+    // a - b as fma(b, -1, a): the product is exact, one rounding — identical to a + (-b)
+    static __device__ __forceinline__ void sub(float (&d)[K], const float (&a)[K], const float (&b)[K]) {
+        const float2 m1 = make_float2(-1.f, -1.f);
+#pragma unroll
+        for (int k = 0; k < K; k += 2) { const float2 r = __ffma2_rn(f2(b + k), m1, f2(a + k)); d[k] = r.x; d[k + 1] = r.y; }
+    }
+    static __device__ __forceinline__ void neg(float (&d)[K], const float (&a)[K]) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) d[k] = -a[k];
+    }
+    static __device__ __forceinline__ void check(float& nf, const float (&a)[K]) {
         float2 acc = make_float2(nf, 0.f);
 #pragma unroll
-        for (int k = 0; k < K; k += 2) acc = __ffma2_rn(make_float2(d[k], d[k + 1]), make_float2(0.f, 0.f), acc);
+        for (int k = 0; k < K; k += 2) acc = __ffma2_rn(f2(a + k), make_float2(0.f, 0.f), acc);
         nf = acc.x + acc.y;
     }
 };
 
-// derivative row g of one operand
-template <typename T, int GC, int K, int KIND>
-__device__ __forceinline__ void dsrc(T (&x)[K], const T (&ad)[GC][K], const T* drow, int idx, int TILE, int g) {
+// ---- operators: value and partials as compile-time functors --------------------------------
+template <int OPC, typename T> struct G1;
+template <int OPC, typename T> struct G2;
+#define X1(SYM, VEXPR, GEXPR)                                                        \
+    template <typename T> struct G1<DEX_OP_##SYM, T> {                               \
+        static __device__ __forceinline__ void f(T x, T& vo, T& p0) {                \
+            const T v = (VEXPR);                                                     \
+            p0 = (GEXPR);                                                            \
+            vo = v;                                                                  \
+        }                                                                            \
+    };
+DEX_UNARY_OPS(X1)
+#undef X1
+#define X2(SYM, VEXPR, GA, GB)                                                       \
+    template <typename T> struct G2<DEX_OP_##SYM, T> {                               \
+        static __device__ __forceinline__ void f(T x, T y, T& vo, T& p0, T& p1) {    \
+            const T v = (VEXPR);                                                     \
+            p0 = (GA);                                                               \
+            p1 = (GB);                                                               \
+            vo = v;                                                                  \
+        }                                                                            \
+    };
+DEX_BINARY_OPS(X2)
+#undef X2
+// x / y: the quotient and 1/y are IEEE divisions; d/dy = -(v/y) is taken as -(v * (1/y)), one
+// multiplication instead of a third division (<= 1 ulp from the quotient; when 1/y overflows
+// the tree fails through p0 either way).
+template <> struct G2<DEX_OP_DIV, float> {
+    static __device__ __forceinline__ void f(float x, float y, float& vo, float& p0, float& p1) {
+        const float r = 1.0f / y;
+        vo = x / y;
+        p0 = r;
+        p1 = -(vo * r);
+    }
+};
+
+// where the derivative of an operand lives
+enum : int { DK_ACC = 0, DK_SLOT = 1, DK_LEAF = 2 };
+// coefficient classes (see the header comment)
+enum : int { CL_ADD = 0, CL_SUB = 1, CL_VAR = 2, CL_GEN = 3 };      // binary: (p0, p1)
+enum : int { UL_ONE = 0, UL_NEG = 1, UL_VAR = 2, UL_GEN = 3 };      // unary: p0
+// stage-2 selector: binary cls*9 + ka*3 + kb in [0, 36); unary 36 + ucls*3 + ka in [36, 48)
+constexpr int SEL_UNARY = 36, SEL_NONE = 48;
+
+template <int OPC> struct BinClass { static constexpr int v = CL_GEN; };
+template <> struct BinClass<DEX_OP_ADD> { static constexpr int v = CL_ADD; };
+template <> struct BinClass<DEX_OP_SUB> { static constexpr int v = CL_SUB; };
+template <> struct BinClass<DEX_OP_MUL> { static constexpr int v = CL_VAR; };
+template <> struct BinClass<DEX_OP_MAX> { static constexpr int v = CL_VAR; };
+template <> struct BinClass<DEX_OP_MIN> { static constexpr int v = CL_VAR; };
+template <int OPC> struct UnClass { static constexpr int v = UL_GEN; };
+template <> struct UnClass<DEX_OP_NEG> { static constexpr int v = UL_NEG; };
+#define UVAR(S) template <> struct UnClass<DEX_OP_##S> { static constexpr int v = UL_VAR; };
+UVAR(ABS) UVAR(SQUARE) UVAR(CUBE) UVAR(EXP) UVAR(SIN) UVAR(COS) UVAR(TANH) UVAR(RELU)
+#undef UVAR
+
+// dense index over the operators with an unrolled stage-1 code path; everything else is
+// FO_GENERIC.  The handler id of a tape instruction (operator x operand forms) maps to it.
+enum : int {
+    FO_GENERIC = 0,
+    FO_LOAD,
+#define X(S) FO_##S,
+    DEX_FAST_UNARY(X) DEX_FAST_BIN_COMM(X) DEX_FAST_BIN_NC(X)
+#undef X
+    FO__COUNT
+};
+struct FastOpTable { uint8_t v[64]; };
+constexpr FastOpTable make_fast_op_table() {
+    FastOpTable t{};
+    t.v[H_LOAD_R] = FO_LOAD;
+    t.v[H_LOAD_C] = FO_LOAD;
+#define X(S) t.v[H_##S##_A] = FO_##S; t.v[H_##S##_R] = FO_##S;
+    DEX_FAST_UNARY(X)
+#undef X
+#define X(S) t.v[H_##S##_AR] = FO_##S; t.v[H_##S##_AC] = FO_##S; t.v[H_##S##_RR] = FO_##S; t.v[H_##S##_RC] = FO_##S;
+    DEX_FAST_BIN_COMM(X)
+#undef X
+#define X(S)                                                                                         \
+    t.v[H_##S##_AR] = FO_##S; t.v[H_##S##_RA] = FO_##S; t.v[H_##S##_AC] = FO_##S; t.v[H_##S##_CA] = FO_##S; \
+    t.v[H_##S##_RR] = FO_##S; t.v[H_##S##_RC] = FO_##S; t.v[H_##S##_CR] = FO_##S;
+    DEX_FAST_BIN_NC(X)
+#undef X
+    return t;
+}
+__constant__ FastOpTable c_fast_op_table = make_fast_op_table();
+
+// ---- stage 2 ----------------------------------------------------------------------------------
+// dA[g] of a densely evaluated operand
+template <typename T, int GC, int U, int KIND>
+__device__ __forceinline__ void dsrc(T (&x)[VK<T, U>::K], const T (&adg)[VK<T, U>::K], const T* slot, int g,
+                                     int idx, int TILE, int CS) {
+    constexpr int K = VK<T, U>::K;
     if (KIND == DK_ACC) {
 #pragma unroll
-        for (int k = 0; k < K; ++k) x[k] = ad[g][k];
+        for (int k = 0; k < K; ++k) x[k] = adg[k];
     } else if (KIND == DK_SLOT) {
-        ldv<T, K>(x, drow + (size_t)(1 + g) * TILE);
-    } else {   // one-hot / zero seed of a leaf
+        VK<T, U>::ld(x, slot + (size_t)(1 + g) * TILE, CS);
+    } else {
         const T e = (g == idx) ? T(1) : T(0);
 #pragma unroll
         for (int k = 0; k < K; ++k) x[k] = e;
     }
 }
 
-// ad[g] <- p0 * dA[g] (+ p1 * dB[g] (+ p2 * ad[g]))  for every direction of the pass
-template <typename T, int GC, int K, int DEG, int KA, int KB>
-__device__ __forceinline__ void combine(T (&ad)[GC][K], const T (&p)[3][K], const T* const (&drow)[3],
-                                        const int (&idx)[3], int TILE, T& nf, bool chk) {
+template <typename T, int GC, int U, int CLS, int KA, int KB>
+__device__ __forceinline__ void combine_bin(T (&ad)[GC][VK<T, U>::K], const T (&p0)[VK<T, U>::K],
+                                            const T (&p1)[VK<T, U>::K], const T* sa, const T* sb, int ia,
+                                            int ib, int TILE, int CS) {
+    constexpr int K = VK<T, U>::K;
+    using A = VA<T, K>;
+    constexpr bool spA = (KA == DK_LEAF) && (CLS != CL_GEN);   // one-hot operand, skippable zeros
+    constexpr bool spB = (KB == DK_LEAF) && (CLS != CL_GEN);
 #pragma unroll
     for (int g = 0; g < GC; ++g) {
-        T d[K], x[K];
-        dsrc<T, GC, K, KA>(x, ad, drow[0], idx[0], TILE, g);
-        DOps<T, K>::mul(d, p[0], x);
-        if (DEG >= 2) {
-            dsrc<T, GC, K, KB>(x, ad, drow[1], idx[1], TILE, g);
-            DOps<T, K>::mul_add(d, p[1], x);
-        }
-        if (DEG >= 3) {   // third operand is always ACC
-            dsrc<T, GC, K, DK_ACC>(x, ad, drow[2], idx[2], TILE, g);
-            DOps<T, K>::mul_add(d, p[2], x);
+        T a[K], b[K], d[K];
+        if (!spA) dsrc<T, GC, U, KA>(a, ad[g], sa, g, ia, TILE, CS);
+        if (!spB) dsrc<T, GC, U, KB>(b, ad[g], sb, g, ib, TILE, CS);
+        if (CLS == CL_ADD) {
+            if (!spA && !spB) A::add(d, a, b);
+            else if (!spA) { A::adds(d, a, (g == ib) ? T(1) : T(0)); }
+            else if (!spB) { A::adds(d, b, (g == ia) ? T(1) : T(0)); }
+            else {
+                const T e = ((g == ia) ? T(1) : T(0)) + ((g == ib) ? T(1) : T(0));
+#pragma unroll
+                for (int k = 0; k < K; ++k) d[k] = e;
+            }
+        } else if (CLS == CL_SUB) {
+            if (!spA && !spB) A::sub(d, a, b);
+            else if (!spA) { A::adds(d, a, (g == ib) ? T(-1) : T(0)); }
+            else if (!spB) { A::neg(d, b); A::adds(d, d, (g == ia) ? T(1) : T(0)); }
+            else {
+                const T e = ((g == ia) ? T(1) : T(0)) - ((g == ib) ? T(1) : T(0));
+#pragma unroll
+                for (int k = 0; k < K; ++k) d[k] = e;
+            }
+        } else if (CLS == CL_VAR) {
+            if (!spA && !spB) { T t[K]; A::mul(d, p0, a); A::mul(t, p1, b); A::add(d, d, t); }
+            else if (!spA) { A::mul(d, p0, a); if (g == ib) A::add(d, d, p1); }
+            else if (!spB) { A::mul(d, p1, b); if (g == ia) A::add(d, p0, d); }
+            else {
+#pragma unroll
+                for (int k = 0; k < K; ++k) d[k] = T(0);
+                if (g == ia) A::add(d, d, p0);
+                if (g == ib) A::add(d, d, p1);
+            }
+        } else {   // CL_GEN: every product is formed, also with the zeros of a one-hot
+            T t[K];
+            A::mul(d, p0, a);
+            A::mul(t, p1, b);
+            A::add(d, d, t);
         }
 #pragma unroll
         for (int k = 0; k < K; ++k) ad[g][k] = d[k];
-        if (chk) DOps<T, K>::check(nf, d);
     }
 }
 
-template <typename T, int GC>
-__global__ void __launch_bounds__(128) grad_kernel(const GK<T> a) {
-    constexpr int K = 16 / (int)sizeof(T);
+template <typename T, int GC, int U, int CLS, int KA>
+__device__ __forceinline__ void combine_un(T (&ad)[GC][VK<T, U>::K], const T (&p0)[VK<T, U>::K], const T* sa,
+                                           int ia, int TILE, int CS) {
+    constexpr int K = VK<T, U>::K;
+    using A = VA<T, K>;
+#pragma unroll
+    for (int g = 0; g < GC; ++g) {
+        T a[K], d[K];
+        if (KA == DK_LEAF && CLS != UL_GEN) {
+            const bool hit = (g == ia);
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+                d[k] = CLS == UL_ONE ? (hit ? T(1) : T(0)) : CLS == UL_NEG ? (hit ? T(-1) : T(0)) : (hit ? p0[k] : T(0));
+        } else {
+            dsrc<T, GC, U, KA>(a, ad[g], sa, g, ia, TILE, CS);
+            if (CLS == UL_ONE) {
+#pragma unroll
+                for (int k = 0; k < K; ++k) d[k] = a[k];
+            } else if (CLS == UL_NEG) A::neg(d, a);
+            else A::mul(d, p0, a);
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) ad[g][k] = d[k];
+    }
+}
+
+#if DEX_GRAD_PTX
+#include "dex_grad_f32.inc"
+#endif
+
+// DIFF: eval_diff_tree_array (one direction, no validity checks, GEN class everywhere)
+template <typename T, int GC, int U, bool DIFF>
+__global__ void __launch_bounds__(DEX_GRAD_THREADS, DEX_GRAD_MIN_CTAS) grad_kernel(const GK<T> a) {
+    using V = VK<T, U>;
+    using A = VA<T, V::K>;
+    constexpr int C = V::C;
+    constexpr int K = V::K;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* rows = reinterpret_cast<T*>(smem_raw);
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int TILE = nthr * K;
+    const int CS = nthr * C;
     const int S = a.max_stack;
     T* xs = rows + (size_t)S * (1 + GC) * TILE;   // feature rows
     const int64_t s0 = (int64_t)blockIdx.x * TILE;
 
     // stage the feature rows of this tile (XT is tile-padded: always in range, 16 B aligned)
-    for (int idx = tid; idx < a.F * nthr; idx += nthr) {
-        const int f = idx / nthr, t = idx - f * nthr;
-        *reinterpret_cast<uint4*>(xs + (size_t)f * TILE + t * K) =
-            __ldg(reinterpret_cast<const uint4*>(a.X + (size_t)f * a.ldx + s0 + t * K));
+    for (int idx = tid; idx < a.F * (TILE / C); idx += nthr) {
+        const int f = idx / (TILE / C), q = idx - f * (TILE / C);
+        *reinterpret_cast<uint4*>(xs + (size_t)f * TILE + q * C) =
+            __ldg(reinterpret_cast<const uint4*>(a.X + (size_t)f * a.ldx + s0 + q * C));
     }
     __syncthreads();
 
-    T* my = rows + tid * K;
-    const T* myx = xs + tid * K;
+    T* my = rows + tid * C;
+    const T* myx = xs + tid * C;
     const int t0 = a.chunk_start[blockIdx.y], t1 = a.chunk_start[blockIdx.y + 1];
     const int mode = a.mode;
     const bool full_tile = (s0 + TILE <= a.N);
+    const int NEVER = -(1 << 20);   // one-hot index that matches no direction
 
+    // Per-tree metadata is loaded one tree ahead (the loads of tree t + 1 are issued while tree t
+    // runs) and the first instruction of a tree arrives as the prefetch of its predecessor's last
+    // one (tapes are contiguous), so no tree starts with a chain of dependent global loads.
+    int64_t off = a.tape_off[t0], off_next = a.tape_off[t0 + 1];
+    int64_t co = a.const_off[t0], co_next = a.const_off[t0 + 1];
+    int64_t go = (!DIFF && a.grad_off) ? a.grad_off[t0] : 0;
+    uint4 ins = __ldg(a.tape + off);
     for (int t = t0; t < t1; ++t) {
-        const int64_t off = a.tape_off[t];
-        const int n = (int)(a.tape_off[t + 1] - off);
+        const int n = (int)(off_next - off);
         const uint4* ip = a.tape + off;
         const int32_t* ordp = a.const_ord + off;
-        const int nconst = (int)(a.const_off[t + 1] - a.const_off[t]);
-        const int G = mode < 0 ? 1 : mode == DEX_GRAD_FEATURES ? a.F
+        const int nconst = (int)(co_next - co);
+        const int64_t goff = go;
+        // next tree (the tables carry slack past their last entry, dex_api.cu upload())
+        const int64_t off_next2 = a.tape_off[t + 2];
+        const int64_t co_next2 = a.const_off[t + 2];
+        if (!DIFF && a.grad_off) go = a.grad_off[t + 1 < (int)a.n_trees ? t + 1 : t];
+        const int G = DIFF ? 1 : mode == DEX_GRAD_FEATURES ? a.F
                     : mode == DEX_GRAD_CONSTANTS ? nconst : a.F + nconst;
         T nf = T(0);
         const int npass = G > 0 ? (G + GC - 1) / GC : 1;
         for (int pass = 0; pass < npass; ++pass) {
             const int g0 = pass * GC;
+            // one-hot index of feature f: f + foff; of the constant with ordinal o: o + coff
+            const int foff = DIFF ? -a.direction : (mode == DEX_GRAD_CONSTANTS ? NEVER : -g0);
+            const int coff = DIFF ? NEVER : mode == DEX_GRAD_CONSTANTS ? -g0 : mode == DEX_GRAD_BOTH ? a.F - g0 : NEVER;
             T av[K], ad[GC][K];   // accumulator dual
 #pragma unroll
             for (int k = 0; k < K; ++k) av[k] = T(0);
@@ -184,180 +419,243 @@ __global__ void __launch_bounds__(128) grad_kernel(const GK<T> a) {
 #pragma unroll
                 for (int k = 0; k < K; ++k) ad[g][k] = T(0);
 
-            for (int pc = 0; pc < n; ++pc) {
-                const uint4 ins = __ldg(ip + pc);
+            // one tape instruction, C++ form (every handler, generic operators included)
+            auto step = [&](const uint4& ins, const int pc) {
                 const uint32_t w0 = ins.x;
-                const uint32_t op = (w0 >> 8) & 0xffu;
                 const T c = gconst_of<T>(ins);
                 if (w0 & F_PUSH) {
                     T* dst = my + (size_t)push_row(w0) * (1 + GC) * TILE;
-                    stv<T, K>(dst, av);
+                    V::st(dst, CS, av);
 #pragma unroll
-                    for (int g = 0; g < GC; ++g) stv<T, K>(dst + (size_t)(1 + g) * TILE, ad[g]);
+                    for (int g = 0; g < GC; ++g) V::st(dst + (size_t)(1 + g) * TILE, CS, ad[g]);
                 }
-                // ---- operands: value, derivative source, one-hot index --------------------
-                T xv[3][K];
-                int dk[3], idx[3];
-                const T* drow[3];
-                const int deg = op >= 128u ? 3 : (op >= 64u ? 2 : 1);
+                T x[K], y[K], vo[K], p0[K], p1[K];
+                const T* sa = my;
+                const T* sb = my;
+                int ia = NEVER, ib = NEVER, ka = DK_LEAF, kb = DK_LEAF, sel = SEL_NONE;
+                const uint32_t op = (w0 >> 8) & 0xffu;
+
+                // ---- stage 0: operand values; where their derivatives live -------------------
+                // ROW is a stack slot (dual in shared memory) or a feature leaf (one-hot
+                // derivative, value checked: grad_deg0_eval :387-399)
+                auto fetch = [&](uint32_t src, uint32_t row, T (&v)[K], const T*& sp, int& idx, int& kind) {
+                    if (src == SRC_ACC) {
 #pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    const uint32_t src = (w0 >> (16 + 2 * i)) & 3u;
-                    const int row = (int)((ins.y >> (16 * i)) & 0xffffu);
-                    dk[i] = DK_LEAF; idx[i] = -1; drow[i] = my;
-                    if (i >= deg) {
-#pragma unroll
-                        for (int k = 0; k < K; ++k) xv[i][k] = T(0);
-                    } else if (src == SRC_ACC) {
-#pragma unroll
-                        for (int k = 0; k < K; ++k) xv[i][k] = av[k];
-                        dk[i] = DK_ACC;
-                    } else if (src == SRC_ROW && row < S) {
-                        drow[i] = my + (size_t)row * (1 + GC) * TILE;
-                        ldv<T, K>(xv[i], drow[i]);
-                        dk[i] = DK_SLOT;
-                    } else if (src == SRC_ROW) {   // feature leaf: grad_deg0_eval :387-399
-                        const int f = row - S;
-                        ldv<T, K>(xv[i], myx + (size_t)f * TILE);
-                        if (mode == DEX_GRAD_FEATURES || mode == DEX_GRAD_BOTH) idx[i] = f - g0;
-                        else if (mode < 0 && f == a.direction) idx[i] = 0;
-                    } else {                        // constant leaf
-#pragma unroll
-                        for (int k = 0; k < K; ++k) xv[i][k] = c;
-                        const int ord = __ldg(ordp + pc);
-                        if (mode == DEX_GRAD_CONSTANTS) idx[i] = ord - g0;
-                        else if (mode == DEX_GRAD_BOTH) idx[i] = a.F + ord - g0;
-                    }
-                }
-                // third operand of a ternary operator is always ACC
-                dk[2] = DK_ACC; idx[2] = -1; drow[2] = my;
-#pragma unroll
-                for (int k = 0; k < K; ++k) xv[2][k] = av[k];
-                if (mode >= 0) {   // leaf values take part in the validity check (:238-243)
-#pragma unroll
-                    for (int i = 0; i < 2; ++i)
-                        if (i < deg && dk[i] == DK_LEAF) {
-#pragma unroll
-                            for (int k = 0; k < K; ++k) nf = m_fma(xv[i][k], T(0), nf);
+                        for (int k = 0; k < K; ++k) v[k] = av[k];
+                        kind = DK_ACC;
+                    } else if (src == SRC_ROW) {
+                        if ((int)row < S) {
+                            sp = my + (size_t)row * (1 + GC) * TILE;
+                            V::ld(v, sp, CS);
+                            kind = DK_SLOT;
+                        } else {
+                            const int f = (int)row - S;
+                            V::ld(v, myx + (size_t)f * TILE, CS);
+                            idx = f + foff;
+                            if (!DIFF) A::check(nf, v);
                         }
-                }
-                // ---- value and partials -------------------------------------------------------
-                T vo[K], p[3][K];
-                switch (op) {
-#define U_CASE(SYM, VEXPR, GEXPR)                                                       \
-    case DEX_OP_##SYM: {                                                                \
-        _Pragma("unroll") for (int k = 0; k < K; ++k) {                                 \
-            const T x = xv[0][k];                                                       \
-            const T v = (VEXPR);                                                        \
-            p[0][k] = (GEXPR);                                                          \
-            vo[k] = v; p[1][k] = T(0); p[2][k] = T(0);                                  \
-        }                                                                               \
-    } break;
-                    DEX_UNARY_OPS(U_CASE)
-#undef U_CASE
-#define B_CASE(SYM, VEXPR, G0, G1)                                                      \
-    case DEX_OP_##SYM: {                                                                \
-        _Pragma("unroll") for (int k = 0; k < K; ++k) {                                 \
-            const T x = xv[0][k], y = xv[1][k];                                         \
-            const T v = (VEXPR);                                                        \
-            p[0][k] = (G0); p[1][k] = (G1);                                             \
-            vo[k] = v; p[2][k] = T(0);                                                  \
-        }                                                                               \
-    } break;
-                    DEX_BINARY_OPS(B_CASE)
-#undef B_CASE
-#define T_CASE(SYM, VEXPR, G0, G1, G2)                                                  \
-    case DEX_OP_##SYM: {                                                                \
-        _Pragma("unroll") for (int k = 0; k < K; ++k) {                                 \
-            const T x = xv[0][k], y = xv[1][k], z = xv[2][k];                           \
-            const T v = (VEXPR);                                                        \
-            p[0][k] = (G0); p[1][k] = (G1); p[2][k] = (G2);                             \
-            vo[k] = v; (void)z;                                                         \
-        }                                                                               \
-    } break;
-                    DEX_TERNARY_OPS(T_CASE)
-#undef T_CASE
-                    default: {
+                    } else {   // inline constant
 #pragma unroll
-                        for (int k = 0; k < K; ++k) { vo[k] = t_nan<T>(); p[0][k] = p[1][k] = p[2][k] = t_nan<T>(); }
+                        for (int k = 0; k < K; ++k) v[k] = c;
+                        if (!DIFF) {
+                            nf = m_fma(c, T(0), nf);
+                            if (mode != DEX_GRAD_FEATURES) idx = __ldg(ordp + pc) + coff;
+                        }
+                    }
+                };
+                fetch((w0 >> 16) & 3u, row_a(ins.y), x, sa, ia, ka);
+                if (op >= 64u) fetch((w0 >> 18) & 3u, row_b(ins.y), y, sb, ib, kb);
+
+                // ---- stage 1: value and partials, by operator ----------------------------------
+                // c_fast_op maps the handler id (operator x operand forms, csrc/dex_tape.h) to a
+                // dense index over the operators that have an unrolled code path here
+                switch ((int)c_fast_op_table.v[w0 & HANDLER_MASK]) {
+                    case FO_LOAD: {
+#pragma unroll
+                        for (int k = 0; k < K; ++k) { vo[k] = x[k]; p0[k] = T(1); }
+                        sel = SEL_UNARY + (DIFF ? UL_GEN : UL_ONE) * 3 + ka;
+                    } break;
+#define UN_CASE(S)                                                                          \
+    case FO_##S: {                                                                          \
+        _Pragma("unroll") for (int k = 0; k < K; ++k) G1<DEX_OP_##S, T>::f(x[k], vo[k], p0[k]); \
+        sel = SEL_UNARY + (DIFF ? UL_GEN : UnClass<DEX_OP_##S>::v) * 3 + ka;                \
+    } break;
+                    DEX_FAST_UNARY(UN_CASE)
+#undef UN_CASE
+#define BIN_CASE(S)                                                                         \
+    case FO_##S: {                                                                          \
+        _Pragma("unroll") for (int k = 0; k < K; ++k) G2<DEX_OP_##S, T>::f(x[k], y[k], vo[k], p0[k], p1[k]); \
+        sel = (DIFF ? CL_GEN : BinClass<DEX_OP_##S>::v) * 9 + ka * 3 + kb;                  \
+    } break;
+                    DEX_FAST_BIN_COMM(BIN_CASE)
+                    DEX_FAST_BIN_NC(BIN_CASE)
+#undef BIN_CASE
+                    // ---- generic: any operator -------------------------------------------------
+                    default: {
+                        const int deg = op >= 128u ? 3 : (op >= 64u ? 2 : 1);
+                        T p2[K];
+                        {
+                            // rolled over the samples, operands in local memory: this rarely taken
+                            // path stays small and keeps the hot code in the instruction cache
+                            T lx[K], ly[K], lz[K], lv[K], l0[K], l1[K], l2[K];
+#pragma unroll
+                            for (int k = 0; k < K; ++k) { lx[k] = x[k]; ly[k] = deg >= 2 ? y[k] : T(0); lz[k] = av[k]; }
+#pragma unroll 1
+                            for (int k = 0; k < K; ++k) {
+                                const T xx = lx[k], yy = ly[k], zz = lz[k];
+                                T v_, q0 = T(0), q1 = T(0), q2 = T(0);
+                                switch (op) {
+#define U_CASE(SYM, VEXPR, GEXPR) \
+    case DEX_OP_##SYM: { const T x = xx; const T v = (VEXPR); q0 = (GEXPR); v_ = v; } break;
+                                    DEX_UNARY_OPS(U_CASE)
+#undef U_CASE
+#define B_CASE(SYM, VEXPR, GA, GB) \
+    case DEX_OP_##SYM: { const T x = xx, y = yy; const T v = (VEXPR); q0 = (GA); q1 = (GB); v_ = v; } break;
+                                    DEX_BINARY_OPS(B_CASE)
+#undef B_CASE
+#define T_CASE(SYM, VEXPR, GA, GB, GZ) \
+    case DEX_OP_##SYM: { const T x = xx, y = yy, z = zz; const T v = (VEXPR); q0 = (GA); q1 = (GB); q2 = (GZ); v_ = v; (void)z; } break;
+                                    DEX_TERNARY_OPS(T_CASE)
+#undef T_CASE
+                                    default: v_ = q0 = q1 = q2 = t_nan<T>(); break;
+                                }
+                                lv[k] = v_; l0[k] = q0; l1[k] = q1; l2[k] = q2;
+                            }
+#pragma unroll
+                            for (int k = 0; k < K; ++k) { vo[k] = lv[k]; p0[k] = l0[k]; p1[k] = l1[k]; p2[k] = l2[k]; }
+                        }
+                        if (deg == 1) sel = SEL_UNARY + UL_GEN * 3 + ka;
+                        else if (deg == 2) sel = CL_GEN * 9 + ka * 3 + kb;
+                        else {
+                            // ternary: d = p0 dA + p1 dB + p2 dACC (third operand is always ACC)
+#pragma unroll
+                            for (int g = 0; g < GC; ++g) {
+                                T da[K], db[K], d[K], tt[K];
+                                if (ka == DK_ACC) dsrc<T, GC, U, DK_ACC>(da, ad[g], sa, g, ia, TILE, CS);
+                                else if (ka == DK_SLOT) dsrc<T, GC, U, DK_SLOT>(da, ad[g], sa, g, ia, TILE, CS);
+                                else dsrc<T, GC, U, DK_LEAF>(da, ad[g], sa, g, ia, TILE, CS);
+                                if (kb == DK_ACC) dsrc<T, GC, U, DK_ACC>(db, ad[g], sb, g, ib, TILE, CS);
+                                else if (kb == DK_SLOT) dsrc<T, GC, U, DK_SLOT>(db, ad[g], sb, g, ib, TILE, CS);
+                                else dsrc<T, GC, U, DK_LEAF>(db, ad[g], sb, g, ib, TILE, CS);
+                                A::mul(d, p0, da);
+                                A::mul(tt, p1, db);
+                                A::add(d, d, tt);
+                                A::mul(tt, p2, ad[g]);
+                                A::add(d, d, tt);
+#pragma unroll
+                                for (int k = 0; k < K; ++k) ad[g][k] = d[k];
+                            }
+                            sel = SEL_NONE;
+                        }
                     } break;
                 }
-                // ---- d[g] = sum_i p_i * d_i[g]   (grad_degn_eval :355-361), left to right ------
-                // the operand kinds are hoisted out of the direction loop: one branch-free,
-                // fully unrolled instance of `combine` per (kind A, kind B) pair
-                const bool chk = mode >= 0;
-                if (deg == 1) {
-                    switch (dk[0]) {
-                        case DK_ACC: combine<T, GC, K, 1, DK_ACC, DK_ACC>(ad, p, drow, idx, TILE, nf, chk); break;
-                        case DK_SLOT: combine<T, GC, K, 1, DK_SLOT, DK_ACC>(ad, p, drow, idx, TILE, nf, chk); break;
-                        default: combine<T, GC, K, 1, DK_LEAF, DK_ACC>(ad, p, drow, idx, TILE, nf, chk); break;
-                    }
-                } else {
-#define COMBINE_PAIR(DEG)                                                                               \
-    switch (dk[0] * 3 + dk[1]) {                                                                        \
-        case DK_ACC * 3 + DK_SLOT: combine<T, GC, K, DEG, DK_ACC, DK_SLOT>(ad, p, drow, idx, TILE, nf, chk); break;   \
-        case DK_ACC * 3 + DK_LEAF: combine<T, GC, K, DEG, DK_ACC, DK_LEAF>(ad, p, drow, idx, TILE, nf, chk); break;   \
-        case DK_SLOT * 3 + DK_ACC: combine<T, GC, K, DEG, DK_SLOT, DK_ACC>(ad, p, drow, idx, TILE, nf, chk); break;   \
-        case DK_SLOT * 3 + DK_SLOT: combine<T, GC, K, DEG, DK_SLOT, DK_SLOT>(ad, p, drow, idx, TILE, nf, chk); break; \
-        case DK_SLOT * 3 + DK_LEAF: combine<T, GC, K, DEG, DK_SLOT, DK_LEAF>(ad, p, drow, idx, TILE, nf, chk); break; \
-        case DK_LEAF * 3 + DK_ACC: combine<T, GC, K, DEG, DK_LEAF, DK_ACC>(ad, p, drow, idx, TILE, nf, chk); break;   \
-        case DK_LEAF * 3 + DK_SLOT: combine<T, GC, K, DEG, DK_LEAF, DK_SLOT>(ad, p, drow, idx, TILE, nf, chk); break; \
-        case DK_LEAF * 3 + DK_LEAF: combine<T, GC, K, DEG, DK_LEAF, DK_LEAF>(ad, p, drow, idx, TILE, nf, chk); break; \
-        default: combine<T, GC, K, DEG, DK_ACC, DK_ACC>(ad, p, drow, idx, TILE, nf, chk); break;        \
-    }
-                    if (deg == 2) { COMBINE_PAIR(2) } else { COMBINE_PAIR(3) }
-#undef COMBINE_PAIR
+
+                // ---- stage 2: derivative combination ---------------------------------------------
+                switch (sel) {
+#define CB(CLS, KA, KB) \
+    case (CLS) * 9 + (KA) * 3 + (KB): combine_bin<T, GC, U, CLS, KA, KB>(ad, p0, p1, sa, sb, ia, ib, TILE, CS); break;
+#define CB_ALL(CLS)                                                                                   \
+    CB(CLS, DK_ACC, DK_SLOT) CB(CLS, DK_ACC, DK_LEAF) CB(CLS, DK_SLOT, DK_ACC) CB(CLS, DK_SLOT, DK_SLOT) \
+    CB(CLS, DK_SLOT, DK_LEAF) CB(CLS, DK_LEAF, DK_ACC) CB(CLS, DK_LEAF, DK_SLOT) CB(CLS, DK_LEAF, DK_LEAF)
+                    CB_ALL(CL_ADD) CB_ALL(CL_SUB) CB_ALL(CL_VAR) CB_ALL(CL_GEN)
+                    CB(CL_GEN, DK_ACC, DK_ACC)   // generic path only (never emitted by the flattener)
+#undef CB_ALL
+#undef CB
+#define CU1(CLS, KA) \
+    case SEL_UNARY + (CLS) * 3 + (KA): combine_un<T, GC, U, CLS, KA>(ad, p0, sa, ia, TILE, CS); break;
+#define CU_ALL(CLS) CU1(CLS, DK_ACC) CU1(CLS, DK_SLOT) CU1(CLS, DK_LEAF)
+                    CU_ALL(UL_ONE) CU_ALL(UL_NEG) CU_ALL(UL_VAR) CU_ALL(UL_GEN)
+#undef CU_ALL
+#undef CU1
+                    default: break;
                 }
 #pragma unroll
                 for (int k = 0; k < K; ++k) av[k] = vo[k];
-                if (mode >= 0) {
-#pragma unroll
-                    for (int k = 0; k < K; ++k) nf = m_fma(vo[k], T(0), nf);
+                if (!DIFF) A::check(nf, vo);
+            };
+            // single call site of `step` (so that it is inlined and the dual accumulator stays in
+            // registers): the Float32 128-thread launch runs the instruction loop as one inline-PTX
+            // block with jump-table dispatch (gen_grad_ptx.py), which returns at the end of the tape
+            // or at the first instruction it does not implement natively; `step` executes that one.
+            constexpr bool HAS_PTX = DEX_GRAD_PTX && sizeof(T) == 4 && U == 1 && !DIFF;
+            const bool use_ptx = HAS_PTX && nthr == 128;
+            if (pass > 0) ins = __ldg(ip);
+            int pc = 0;
+            while (pc < n) {
+#if DEX_GRAD_PTX
+                if constexpr (HAS_PTX) {
+                    if (use_ptx) {
+                        const uint32_t my_s = (uint32_t)__cvta_generic_to_shared(my);
+                        float nfa[2] = {nf, 0.f};
+                        GradLoopF32<GC>::run(pc, av, ad, nfa, ins, ip, n, my_s, S, S * GC, foff - S, coff, ordp,
+                                             mode != DEX_GRAD_FEATURES ? 1 : 0);
+                        nf = nfa[0] + nfa[1];
+                        if (pc < n) ins = __ldg(ip + pc);   // early exit: `ins` is two instructions ahead
+                    }
                 }
+#endif
+                if (pc < n) {
+                    const uint4 nxt = __ldg(ip + pc + 1);
+                    step(ins, pc);
+                    ins = nxt;
+                    ++pc;
+                }
+            }
+            // root derivative check (see the header comment: non-finite components propagate)
+            if (!DIFF) {   // padded directions (g0 + g >= G) are not part of the gradient
+#pragma unroll
+                for (int g = 0; g < GC; ++g)
+                    if (g0 + g < G) A::check(nf, ad[g]);
             }
             // ---- outputs of this pass -----------------------------------------------------
-            const int64_t sbase = s0 + (int64_t)tid * K;
-            if (pass == 0) {
-                T* o = a.out + (size_t)t * a.ldo + sbase;
-                if (full_tile && (a.ldo % K) == 0 && (reinterpret_cast<uintptr_t>(a.out) & 15) == 0) stv<T, K>(o, av);
-                else {
 #pragma unroll
-                    for (int k = 0; k < K; ++k) if (sbase + k < a.N) o[k] = av[k];
+            for (int u = 0; u < U; ++u) {
+                const int64_t sbase = s0 + (int64_t)u * CS + (int64_t)tid * C;
+                if (pass == 0) {
+                    T* o = a.out + (size_t)t * a.ldo + sbase;
+                    if (full_tile && (a.ldo % C) == 0 && (reinterpret_cast<uintptr_t>(a.out) & 15) == 0)
+                        *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(&av[u * C]);
+                    else {
+#pragma unroll
+                        for (int k = 0; k < C; ++k) if (sbase + k < a.N) o[k] = av[u * C + k];
+                    }
                 }
-            }
-            if (mode < 0) {   // eval_diff: one derivative row per tree, laid out like `out`
-                T* o = a.grad + (size_t)t * a.ldo + sbase;
+                if (DIFF) {   // eval_diff: one derivative row per tree, laid out like `out`
+                    T* o = a.grad + (size_t)t * a.ldo + sbase;
 #pragma unroll
-                for (int k = 0; k < K; ++k) if (sbase + k < a.N) o[k] = ad[0][k];
-            } else if (G > 0) {
-                // (G x N) column-major block: element (g, s) at s * G + g
-                T* gout = a.grad + a.grad_off[t] + sbase * G + g0;
-                const int gc = min(GC, G - g0);
-                if (gc == GC && G == GC && full_tile && ((reinterpret_cast<uintptr_t>(gout) & 15) == 0)) {
-                    // the thread's K samples x GC directions are K*GC contiguous elements
-                    T flat[K * GC];
+                    for (int k = 0; k < C; ++k) if (sbase + k < a.N) o[k] = ad[0][u * C + k];
+                } else if (G > 0) {
+                    // (G x N) column-major block: element (g, s) at s * G + g
+                    T* gout = a.grad + goff + sbase * G + g0;
+                    const int gc = min(GC, G - g0);
+                    if (gc == GC && G == GC && full_tile && ((reinterpret_cast<uintptr_t>(gout) & 15) == 0)) {
+                        // the thread's C samples x GC directions are C*GC contiguous elements
+                        T flat[C * GC];
 #pragma unroll
-                    for (int k = 0; k < K; ++k)
+                        for (int k = 0; k < C; ++k)
 #pragma unroll
-                        for (int g = 0; g < GC; ++g) flat[k * GC + g] = ad[g][k];
+                            for (int g = 0; g < GC; ++g) flat[k * GC + g] = ad[g][u * C + k];
 #pragma unroll
-                    for (int q = 0; q < K * GC; q += K)
-                        *reinterpret_cast<uint4*>(gout + q) = *reinterpret_cast<const uint4*>(flat + q);
-                } else {
+                        for (int q = 0; q < C * GC; q += C)
+                            *reinterpret_cast<uint4*>(gout + q) = *reinterpret_cast<const uint4*>(flat + q);
+                    } else {
 #pragma unroll
-                    for (int k = 0; k < K; ++k)
-                        if (sbase + k < a.N) {
+                        for (int k = 0; k < C; ++k)
+                            if (sbase + k < a.N) {
 #pragma unroll
-                            for (int g = 0; g < GC; ++g)
-                                if (g < gc) gout[(size_t)k * G + g] = ad[g][k];
-                        }
+                                for (int g = 0; g < GC; ++g)
+                                    if (g < gc) gout[(size_t)k * G + g] = ad[g][u * C + k];
+                            }
+                    }
                 }
             }
         }
-        if (mode >= 0) {
+        if (!DIFF) {
             const bool bad = nf != nf;
             if (__any_sync(0xffffffffu, bad) && (tid & 31) == 0) a.ok[t] = 0;
         }
+        off = off_next; off_next = off_next2;
+        co = co_next; co_next = co_next2;
     }
 }
 
@@ -372,14 +670,15 @@ __global__ void gtranspose_pad_kernel(const T* __restrict__ X, int64_t ldx, int 
 }
 
 constexpr size_t G_SMEM_LIMIT = 227 * 1024;
+constexpr int GRAD_U = DEX_GRAD_U;
 
 struct GradShape { int threads; int GC; size_t smem; int64_t tile; };
 
 GradShape pick_shape(int dtype, int F, int max_stack, int Gmax) {
     const size_t es = dtype == DEX_F32 ? 4 : 8;
-    const int K = dtype == DEX_F32 ? 4 : 2;
+    const int K = (dtype == DEX_F32 ? 4 : 2) * GRAD_U;
     GradShape s;
-    s.threads = 128;
+    s.threads = DEX_GRAD_THREADS;
     s.GC = std::max(1, std::min(Gmax, 8));
     if (dtype == DEX_F64) {   // instantiated: 1, 2, 4, 8
         s.GC = s.GC <= 1 ? 1 : s.GC <= 2 ? 2 : s.GC <= 4 ? 4 : 8;
@@ -396,12 +695,13 @@ GradShape pick_shape(int dtype, int F, int max_stack, int Gmax) {
     return s;
 }
 
-template <typename T, int GC>
+template <typename T, int GC, bool DIFF>
 cudaError_t launch_one(const GK<T>& a, const GradShape& sh, int64_t n_tiles, int n_chunks, cudaStream_t stream) {
-    cudaError_t err = cudaFuncSetAttribute(grad_kernel<T, GC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh.smem);
+    auto kern = grad_kernel<T, GC, GRAD_U, DIFF>;
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh.smem);
     if (err != cudaSuccess) return err;
     dim3 grid((unsigned)n_tiles, (unsigned)n_chunks);
-    grad_kernel<T, GC><<<grid, sh.threads, sh.smem, stream>>>(a);
+    kern<<<grid, sh.threads, sh.smem, stream>>>(a);
     return cudaGetLastError();
 }
 
@@ -418,7 +718,7 @@ GK<T> make_args(const GradArgs& g, const int32_t* chunk_start, int64_t Npad) {
     a.grad = static_cast<T*>(g.grad);
     a.grad_off = g.grad_off;
     a.ok = g.ok;
-    a.N = g.N; a.ldx = Npad; a.ldo = g.ldo;
+    a.N = g.N; a.ldx = Npad; a.ldo = g.ldo; a.n_trees = g.n_trees;
     a.F = g.F; a.max_stack = g.max_stack; a.mode = g.mode; a.direction = g.direction;
     return a;
 }
@@ -453,24 +753,27 @@ cudaError_t launch_grad_ex(const GradArgs& g, const int32_t* chunk_start, int n_
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return err;
     if (launches) *launches += 1;
+    const bool diff = g.mode < 0;
     if (g.dtype == DEX_F32) {
         const GK<float> a = make_args<float>(g, chunk_start, Npad);
-        switch (sh.GC) {
-            case 1: err = launch_one<float, 1>(a, sh, n_tiles, n_chunks, stream); break;
-            case 2: err = launch_one<float, 2>(a, sh, n_tiles, n_chunks, stream); break;
-            case 3: err = launch_one<float, 3>(a, sh, n_tiles, n_chunks, stream); break;
-            case 4: err = launch_one<float, 4>(a, sh, n_tiles, n_chunks, stream); break;
-            case 5: err = launch_one<float, 5>(a, sh, n_tiles, n_chunks, stream); break;
-            case 6: err = launch_one<float, 6>(a, sh, n_tiles, n_chunks, stream); break;
-            default: err = launch_one<float, 8>(a, sh, n_tiles, n_chunks, stream); break;
+        if (diff) err = launch_one<float, 1, true>(a, sh, n_tiles, n_chunks, stream);
+        else switch (sh.GC) {
+            case 1: err = launch_one<float, 1, false>(a, sh, n_tiles, n_chunks, stream); break;
+            case 2: err = launch_one<float, 2, false>(a, sh, n_tiles, n_chunks, stream); break;
+            case 3: err = launch_one<float, 3, false>(a, sh, n_tiles, n_chunks, stream); break;
+            case 4: err = launch_one<float, 4, false>(a, sh, n_tiles, n_chunks, stream); break;
+            case 5: err = launch_one<float, 5, false>(a, sh, n_tiles, n_chunks, stream); break;
+            case 6: err = launch_one<float, 6, false>(a, sh, n_tiles, n_chunks, stream); break;
+            default: err = launch_one<float, 8, false>(a, sh, n_tiles, n_chunks, stream); break;
         }
     } else {
         const GK<double> a = make_args<double>(g, chunk_start, Npad);
-        switch (sh.GC) {
-            case 1: err = launch_one<double, 1>(a, sh, n_tiles, n_chunks, stream); break;
-            case 2: err = launch_one<double, 2>(a, sh, n_tiles, n_chunks, stream); break;
-            case 4: err = launch_one<double, 4>(a, sh, n_tiles, n_chunks, stream); break;
-            default: err = launch_one<double, 8>(a, sh, n_tiles, n_chunks, stream); break;
+        if (diff) err = launch_one<double, 1, true>(a, sh, n_tiles, n_chunks, stream);
+        else switch (sh.GC) {
+            case 1: err = launch_one<double, 1, false>(a, sh, n_tiles, n_chunks, stream); break;
+            case 2: err = launch_one<double, 2, false>(a, sh, n_tiles, n_chunks, stream); break;
+            case 4: err = launch_one<double, 4, false>(a, sh, n_tiles, n_chunks, stream); break;
+            default: err = launch_one<double, 8, false>(a, sh, n_tiles, n_chunks, stream); break;
         }
     }
     if (err == cudaSuccess && launches) *launches += 1;
