@@ -65,12 +65,42 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
+        # NVML / nvidia-smi enumerate physical GPUs: honour CUDA_VISIBLE_DEVICES when it is a list of indices
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        try:
+            ids = [int(v) for v in vis.split(",") if v.strip() != ""]
+            if ids and index < len(ids):
+                index = ids[index]
+        except ValueError:
+            pass
         self.index = index
         self.rows = []
         self.stop = threading.Event()
         self.th = threading.Thread(target=self.run, daemon=True)
 
     def run(self):
+        # NVML in-process (sub-millisecond per sample) so that even a 20-step timed region of a
+        # few milliseconds is sampled many times; nvidia-smi (the recipe's clocks line) as fallback
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            R = {"hw_slowdown": pynvml.nvmlClocksThrottleReasonHwSlowdown,
+                 "hw_thermal_slowdown": pynvml.nvmlClocksThrottleReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": pynvml.nvmlClocksThrottleReasonSwThermalSlowdown,
+                 "sw_power_cap": pynvml.nvmlClocksThrottleReasonSwPowerCap}
+            while not self.stop.is_set():
+                sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                mask = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                row = [str(self.index), str(sm), str(mx), "", ""]
+                row += ["Active" if (mask & R[nm]) else "Not Active"
+                        for nm in ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")]
+                self.rows.append(row)
+                self.stop.wait(0.002)
+            return
+        except Exception:
+            pass
         while not self.stop.is_set():
             try:
                 o = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
