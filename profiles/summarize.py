@@ -10,7 +10,8 @@ import sys
 
 tag = sys.argv[1]
 pre = sys.argv[2] if len(sys.argv) > 2 else "r01"
-rep = f"gpurun_out/prof_eval_{tag}.ncu-rep"
+kind = sys.argv[3] if len(sys.argv) > 3 else "eval"      # "eval" | "grad": which kernel's capture
+rep = f"gpurun_out/prof_{kind}_{tag}.ncu-rep"
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units, vals = rows[0], rows[1], rows[2]
@@ -39,7 +40,14 @@ keys = [
 ]
 out = {"source": rep, "kernel": d.get("Kernel Name", ("", ""))[1]}
 out.update({k: {"unit": d[k][0], "value": d[k][1]} for k in keys if k in d})
-json.dump(out, open(f"profiles/{pre}_eval_kernel_ncu_metrics.json", "w"), indent=1)
+keys_extra = ["l1tex__t_sectors_pipe_lsu_mem_local_op_ld.sum", "l1tex__t_sectors_pipe_lsu_mem_local_op_st.sum",
+              "l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_st.sum"]
+out.update({k: {"unit": d[k][0], "value": d[k][1]} for k in keys_extra if k in d})
+json.dump(out, open(f"profiles/{pre}_{kind}_kernel_ncu_metrics.json", "w"), indent=1)
+if kind != "eval":
+    for k in ("gpu__time_duration.sum", "smsp__inst_executed.sum", "sm__issue_active.avg.pct_of_peak_sustained_elapsed"):
+        print(k, d[k])
+    sys.exit(0)
 scale = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1}
 rd = float(d["dram__bytes_read.sum"][1]) * scale[d["dram__bytes_read.sum"][0]]
 wr = float(d["dram__bytes_write.sum"][1]) * scale[d["dram__bytes_write.sum"][0]]
