@@ -646,20 +646,32 @@ static int run_grad(dex_ctx* ctx, const dex_population* cpop, const void* X, int
         for (int32_t c : h.n_const_tree) ncmax = std::max(ncmax, c);
         Gmax = mode == DEX_GRAD_FEATURES ? F : mode == DEX_GRAD_CONSTANTS ? ncmax : F + ncmax;
     }
-    const int64_t n_tiles = grad_num_tiles(h.dtype, F, h.max_stack, Gmax, N);
+    // d/dX only (variable = Val(true)): constant subtrees have zero gradient, so the launch runs
+    // the constant-folded tape like dex_eval; the prepass evaluates the folded subtrees with the
+    // gradient path's validity rule (every value and every partial finite, dex_fold.cuh).
+    // Gradients w.r.t. constants and eval_diff run the unfolded tape.
+    const bool folded = mode == DEX_GRAD_FEATURES && F > 0;
+    const PackedPopulation& img = folded ? *h.folded : h;
+    const int64_t n_tiles = grad_num_tiles(h.dtype, F, img.max_stack, Gmax, N);
     const int64_t want = (int64_t)ctx->sm_count * 8 * 4;
     int64_t n_chunks = std::max<int64_t>(1, (want + n_tiles - 1) / n_tiles);
-    n_chunks = std::max<int64_t>(n_chunks, ((int64_t)h.tape.size() + 127) / 128);
+    n_chunks = std::max<int64_t>(n_chunks, ((int64_t)img.tape.size() + 127) / 128);
     n_chunks = std::min<int64_t>(n_chunks, std::min<int64_t>(h.n_trees, 65535));
     const int32_t* chunks = nullptr;
     int rc = chunk_table(ctx, pop, (int32_t)n_chunks, &chunks);
     if (rc) return rc;
-    if ((rc = ensure_xt(ctx, grad_xt_bytes(h.dtype, F, h.max_stack, Gmax, N)))) return rc;
+    if ((rc = ensure_xt(ctx, grad_xt_bytes(h.dtype, F, img.max_stack, Gmax, N)))) return rc;
     GradArgs a{};
     a.dtype = h.dtype;
-    a.tape = pop->d_tape; a.tape_off = pop->d_tape_off; a.const_ord = pop->d_const_ord;
+    if (folded) {
+        a.tape = pop->d_ftape; a.tape_off = pop->d_ftape_off;
+        if (!img.seg.empty()) { a.ctape = pop->d_ctape; a.seg = pop->d_seg; a.seg_off = pop->d_seg_off; }
+    } else {
+        a.tape = pop->d_tape; a.tape_off = pop->d_tape_off;
+    }
+    a.const_ord = pop->d_const_ord;   // indexed like the unfolded tape; not read for d/dX
     a.const_off = pop->d_const_off;
-    a.n_trees = h.n_trees; a.max_stack = h.max_stack;
+    a.n_trees = h.n_trees; a.max_stack = img.max_stack;
     a.X = X; a.xt = ctx->xt; a.F = F; a.N = N; a.ldx = ldx; a.mode = mode; a.direction = direction;
     a.out = out; a.ldo = ldo; a.grad = grad; a.ok = ok; a.grad_off = nullptr;
     if (mode >= 0) {

@@ -26,6 +26,7 @@
 // No tensor cores: the path is elementwise, not a contraction.
 #include "dex_kernels.h"
 #include "dex_ops.cuh"
+#include "dex_fold.cuh"
 
 #include <algorithm>
 #include <cstdlib>
@@ -561,57 +562,6 @@ __global__ void __launch_bounds__(DEX_MAX_THREADS, DEX_MIN_CTAS) eval_kernel(con
     }
 }
 
-// Constant-subtree folding of tree t: runs the scalar segments of the tree (dex_tape.h,
-// PackedPopulation::ctape) and stores each result into the inline-constant slot of the
-// instruction that consumes it.  Same operator code as the sample loop.  Returns false when
-// a value the reference's scalar walk checks is not finite (_eval_constant_tree returns
-// ResultOk(.., false), /root/reference/src/Evaluate.jl:1059-1114) — whatever early_exit says.
-template <typename T>
-__device__ bool fold_tree(Instr* tape, const Instr* ctape, const int64_t* seg, const int64_t* seg_off, int64_t t) {
-    bool ok = true;
-    T st[MAX_STACK_ROWS + 1];
-    for (int64_t sg = seg_off[t]; sg < seg_off[t + 1]; ++sg) {
-        const int64_t begin = seg[3 * sg], end = seg[3 * sg + 1], target = seg[3 * sg + 2];
-        T acc = T(0);
-        for (int64_t pc = begin; pc < end; ++pc) {
-            const uint4 ins = *reinterpret_cast<const uint4*>(ctape + pc);
-            const uint32_t w0 = ins.x;
-            const T c = const_of<T>(ins);
-            if (w0 & F_PUSH) st[push_row(w0)] = acc;
-            const uint32_t sa = (w0 >> 16) & 3u, sb = (w0 >> 18) & 3u;
-            const T x = sa == SRC_ROW ? st[row_a(ins.y)] : (sa == SRC_CONST ? c : acc);
-            const T y = sb == SRC_ROW ? st[row_b(ins.y)] : (sb == SRC_CONST ? c : acc);
-            const T z = acc;
-            if ((w0 & F_CHK_A) && !t_finite(x)) ok = false;
-            if ((w0 & F_CHK_B) && !t_finite(y)) ok = false;
-            T v;
-            switch ((w0 >> 8) & 0xffu) {
-#define U_CASE(SYM, VEXPR, GEXPR) case DEX_OP_##SYM: v = (VEXPR); break;
-                DEX_UNARY_OPS(U_CASE)
-#undef U_CASE
-#define B_CASE(SYM, VEXPR, G0, G1) case DEX_OP_##SYM: v = (VEXPR); break;
-                DEX_BINARY_OPS(B_CASE)
-#undef B_CASE
-#define T_CASE(SYM, VEXPR, G0, G1, G2) case DEX_OP_##SYM: v = (VEXPR); break;
-                DEX_TERNARY_OPS(T_CASE)
-#undef T_CASE
-                default: v = t_nan<T>(); break;
-            }
-            (void)y; (void)z;
-            if ((w0 & F_CHK_OUT) && !t_finite(v)) ok = false;
-            acc = v;
-        }
-        if (target >= 0) {
-            uint32_t lo, hi;
-            if (sizeof(T) == 4) { lo = __float_as_uint((float)acc); hi = 0; }
-            else { lo = (uint32_t)__double2loint((double)acc); hi = (uint32_t)__double2hiint((double)acc); }
-            tape[target].c_lo = lo;
-            tape[target].c_hi = hi;
-        }
-    }
-    return ok;
-}
-
 // Pre-pass: XT[f][s] = X[f, min(s, N-1)] for s < Npad — the feature-major, tile-padded image
 // of the caller's column-major X that the interpreter stages with bulk async copies.  The
 // first n_trees threads also fold the constant subtrees of one tree each and preset ok[] to
@@ -627,7 +577,7 @@ __global__ void transpose_pad_kernel(const T* __restrict__ X, int64_t ldx, int F
         const T* col = X + (s < N ? s : N - 1) * ldx;
         for (int f = 0; f < F; ++f) XT[(size_t)f * Npad + s] = __ldg(col + f);
     }
-    if (s < n_trees) ok[s] = (!seg_off || fold_tree<T>(tape, ctape, seg, seg_off, s)) ? 1 : 0;
+    if (s < n_trees) ok[s] = (!seg_off || fold_tree<T, false>(tape, ctape, seg, seg_off, s)) ? 1 : 0;
 }
 
 template <typename T>

@@ -57,6 +57,11 @@ struct GradArgs {
     int dtype;
     const Instr* tape;          // device: the evaluation tape
     const int64_t* tape_off;    // device, n_trees + 1
+    // constant-folded launch (d/dX only; null seg_off => `tape` is the unfolded image): the
+    // prepass runs the scalar tape with the gradient path's validity rule (dex_fold.cuh)
+    const Instr* ctape;
+    const int64_t* seg;
+    const int64_t* seg_off;
     const int32_t* const_ord;   // device, per tape instruction: tree-local constant ordinal or -1
     const int64_t* const_off;   // device, n_trees + 1 (constant ordinal base per tree)
     int64_t n_trees;
