@@ -578,7 +578,7 @@ __global__ void __launch_bounds__(DEX_GRAD_THREADS, DEX_GRAD_MIN_CTAS) grad_kern
             // registers): the Float32 128-thread launch runs the instruction loop as one inline-PTX
             // block with jump-table dispatch (gen_grad_ptx.py), which returns at the end of the tape
             // or at the first instruction it does not implement natively; `step` executes that one.
-            constexpr bool HAS_PTX = DEX_GRAD_PTX && sizeof(T) == 4 && U == 1 && !DIFF;
+            constexpr bool HAS_PTX = DEX_GRAD_PTX && sizeof(T) == 4 && (U == 1 || U == 2) && !DIFF;
             const bool use_ptx = HAS_PTX && nthr == 128;
             if (pass > 0) ins = __ldg(ip);
             int pc = 0;
@@ -588,7 +588,7 @@ __global__ void __launch_bounds__(DEX_GRAD_THREADS, DEX_GRAD_MIN_CTAS) grad_kern
                     if (use_ptx) {
                         const uint32_t my_s = (uint32_t)__cvta_generic_to_shared(my);
                         float nfa[2] = {nf, 0.f};
-                        GradLoopF32<GC>::run(pc, av, ad, nfa, ins, ip, n, my_s, S, S * GC, foff - S, coff, ordp,
+                        GradLoopF32<GC, U>::run(pc, av, ad, nfa, ins, ip, n, my_s, S, S * GC, foff - S, coff, ordp,
                                              mode != DEX_GRAD_FEATURES ? 1 : 0);
                         nf = nfa[0] + nfa[1];
                         if (pc < n) ins = __ldg(ip + pc);   // early exit: `ins` is two instructions ahead

@@ -399,6 +399,34 @@ def test_many_constants_gradient_passes(oracle):
     np.testing.assert_allclose(y, ry, rtol=1e-12)
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_gradient_constant_subtrees_follow_the_gradient_rule(dtype, oracle):
+    """d/dX runs the constant-folded tape; the folded subtrees must still obey the gradient
+    path's rule (value AND gradient of every node finite, EvaluateDerivative.jl:238-243):
+    sqrt(0.0) is a finite value with an infinite partial, so its zero-seeded gradient is NaN."""
+    ops = dexb200.OperatorEnum({1: ("sqrt", "exp", "cos"), 2: ("+", "*", "/")})
+    N_ = dexb200.Node
+    x1, x2 = N_(feature=1), N_(feature=2)
+    trees = [
+        N_(1, x1, N_(1, N_(val=0.0))),                                   # x1 + sqrt(0): d = Inf * 0
+        N_(1, x1, N_(1, N_(val=4.0))),                                   # x1 + sqrt(4): fine
+        N_(2, x2, N_(2, N_(val=1000.0))),                                # x2 * exp(1000): Inf value
+        N_(1, N_(2, x1, x2), N_(3, N_(2, N_(val=2.0), N_(val=3.0)))),    # x1*x2 + cos(2*3)
+        N_(1, x1, N_(3, N_(val=1.0), N_(1, N_(val=0.0)))),               # x1 + 1/sqrt(0): Inf value
+        N_(1, N_(val=0.0)),                                              # sqrt(0) alone
+        N_(1, x1, N_(1, N_(1, N_(val=0.0), N_(val=0.0)))),               # x1 + sqrt(0 + 0)
+    ]
+    X = np.random.default_rng(3).standard_normal((2, 257)).astype(dtype)
+    for i, tree in enumerate(trees):
+        y, g, ok = dexb200.eval_grad_tree_array(tree, X, ops, variable=True)
+        ry, rg, rok = oracle.eval_grad_tree_array(dexb200.to_wire(tree), ops.opcodes, X,
+                                                  oracle.GRAD_FEATURES | oracle.GRAD_ELEMENTWISE)
+        assert bool(ok) == bool(rok), (i, ok, rok)
+        if rok:
+            np.testing.assert_allclose(y, ry, rtol=1e-5)
+            np.testing.assert_allclose(g, rg, rtol=1e-5, atol=1e-6)
+
+
 def test_set_constants_equals_repack(oracle):
     ops = dexb200.OperatorEnum(treegen.OPSET_A)
     nodes, offsets = treegen.gen_population(80, 6, 2, 4, 3, seed=41)
