@@ -759,4 +759,47 @@ int dex_host_free(void* p) {
     return DEX_OK;
 }
 
+// ---- peer memory (CUDA IPC): see include/dexb200.h ------------------------------------------
+int dex_device_alloc(dex_ctx* ctx, void** out, int64_t bytes) {
+    int rc = ensure_device(ctx);
+    if (rc) return rc;
+    if (!out || bytes < 0) return set_err(ctx, DEX_ERR_INVALID, "null out / negative size");
+    *out = nullptr;
+    cudaError_t e = cudaMalloc(out, (size_t)std::max<int64_t>(bytes, 1));
+    if (e != cudaSuccess) { cudaGetLastError(); return set_err(ctx, DEX_ERR_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e)); }
+    return DEX_OK;
+}
+int dex_device_free(dex_ctx* ctx, void* p) {
+    int rc = ensure_device(ctx);
+    if (rc) return rc;
+    if (p) CU(ctx, cudaFree(p));
+    return DEX_OK;
+}
+int dex_ipc_export(dex_ctx* ctx, const void* dev_ptr, uint8_t* handle64) {
+    int rc = ensure_device(ctx);
+    if (rc) return rc;
+    if (!dev_ptr || !handle64) return set_err(ctx, DEX_ERR_INVALID, "null pointer");
+    static_assert(sizeof(cudaIpcMemHandle_t) == DEX_IPC_HANDLE_BYTES, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    CU(ctx, cudaIpcGetMemHandle(&h, const_cast<void*>(dev_ptr)));
+    memcpy(handle64, &h, sizeof(h));
+    return DEX_OK;
+}
+int dex_ipc_open(dex_ctx* ctx, const uint8_t* handle64, void** out) {
+    int rc = ensure_device(ctx);
+    if (rc) return rc;
+    if (!handle64 || !out) return set_err(ctx, DEX_ERR_INVALID, "null pointer");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof(h));
+    *out = nullptr;
+    CU(ctx, cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
+    return DEX_OK;
+}
+int dex_ipc_close(dex_ctx* ctx, void* p) {
+    int rc = ensure_device(ctx);
+    if (rc) return rc;
+    if (p) CU(ctx, cudaIpcCloseMemHandle(p));
+    return DEX_OK;
+}
+
 }  // extern "C"

@@ -59,6 +59,11 @@ ABI = {
     "dex_eval_host": (C.c_int, [_P, _P, _P, _I32, _I64, _I64, _P, _I64, _U8P, C.c_int]),
     "dex_host_alloc": (C.c_int, [C.POINTER(_P), _I64]),
     "dex_host_free": (C.c_int, [_P]),
+    "dex_device_alloc": (C.c_int, [_P, C.POINTER(_P), _I64]),
+    "dex_device_free": (C.c_int, [_P, _P]),
+    "dex_ipc_export": (C.c_int, [_P, _P, _P]),
+    "dex_ipc_open": (C.c_int, [_P, _P, C.POINTER(_P)]),
+    "dex_ipc_close": (C.c_int, [_P, _P]),
     "dex_ctx_launch_count": (_I64, [_P]),
     "dex_population_copy_tape": (_I64, [_P, _P, _I64, _P]),
     "dex_population_copy_folded": (C.c_int, [_P, _P, _P, _P, _P, _P]),
@@ -195,6 +200,62 @@ class Context:
             pass
 
 
+class PeerBuffer:
+    """A cudaMalloc'ed device buffer that other processes can map (CUDA IPC) — the landing zone of
+    the fused evaluate + gather (include/dexb200.h "peer memory").  ``PeerBuffer(ctx, nbytes)``
+    allocates and owns; ``PeerBuffer.open(ctx, handle)`` maps a peer's buffer."""
+
+    def __init__(self, ctx: "Context", nbytes: int):
+        self.ctx, self.nbytes, self.owner = ctx, int(nbytes), True
+        p = _P()
+        ctx.check(lib().dex_device_alloc(ctx.h, C.byref(p), self.nbytes))
+        self.ptr = int(p.value)
+
+    def handle(self) -> bytes:
+        h = (C.c_uint8 * 64)()
+        self.ctx.check(lib().dex_ipc_export(self.ctx.h, _P(self.ptr), C.cast(h, _P)))
+        return bytes(h)
+
+    @classmethod
+    def open(cls, ctx: "Context", handle: bytes):
+        self = cls.__new__(cls)
+        self.ctx, self.nbytes, self.owner = ctx, None, False
+        h = (C.c_uint8 * 64).from_buffer_copy(handle)
+        p = _P()
+        ctx.check(lib().dex_ipc_open(ctx.h, C.cast(h, _P), C.byref(p)))
+        self.ptr = int(p.value)
+        return self
+
+    def as_tensor(self, shape, dtype):
+        """torch view of an OWNED buffer (for reading the gathered result on the root)."""
+        import torch
+
+        class _Iface:
+            pass
+
+        holder = _Iface()
+        typestr = {torch.float32: "<f4", torch.float64: "<f8", torch.uint8: "|u1"}[dtype]
+        holder.__cuda_array_interface__ = {"shape": tuple(int(x) for x in shape), "typestr": typestr,
+                                           "data": (self.ptr, False), "version": 2, "strides": None}
+        t = torch.as_tensor(holder, device=f"cuda:{self.ctx.device}")
+        t._dex_keepalive = self
+        return t
+
+    def close(self):
+        if self.ptr:
+            if self.owner:
+                lib().dex_device_free(self.ctx.h, _P(self.ptr))
+            else:
+                lib().dex_ipc_close(self.ctx.h, _P(self.ptr))
+            self.ptr = 0
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def host_context():
     """A context that can pack/validate but not evaluate (no CUDA calls)."""
     c = Context.__new__(Context)
@@ -326,6 +387,19 @@ class Population:
                                       out.stride(0) if self.n_trees else N, _ptr(ok),
                                       EVAL_EARLY_EXIT if early_exit else 0))
         return out, ok
+
+    def eval_into(self, X, out_ptr, ldo, *, ok=None, early_exit=True):
+        """Batched ``eval_tree_array`` whose result rows are stored at a RAW device address with
+        row stride ``ldo`` (elements) — e.g. a column block inside a peer GPU's gathered
+        ``(P, N_total)`` matrix mapped with :class:`PeerBuffer` (fused evaluate + gather)."""
+        import torch
+        Xd, F, N, ldx = as_device_matrix(X, self.ctx.device, self.dtype_code)
+        if ok is None:
+            ok = torch.empty(self.n_trees, dtype=torch.uint8, device=f"cuda:{self.ctx.device}")
+        self.ctx.use_current_stream()
+        self.ctx.check(lib().dex_eval(self.ctx.h, self.h, _ptr(Xd), F, N, ldx, _P(int(out_ptr)), int(ldo),
+                                      _ptr(ok), EVAL_EARLY_EXIT if early_exit else 0))
+        return ok
 
     def eval_parametric(self, X, parameters, classes0, *, early_exit=True, out=None, ok=None):
         """``parameters``: (P, n_params, n_classes); ``classes0``: 0-based class per sample."""

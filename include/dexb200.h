@@ -194,6 +194,28 @@ int dex_eval_host(dex_ctx* ctx, const dex_population* pop, const void* X_host, i
 int dex_host_alloc(void** out, int64_t bytes);
 int dex_host_free(void* p);
 
+/* ---- peer memory: fused evaluate + gather over NVLink ---------------------
+ * The sample axis shards across GPUs, one process per GPU
+ * (/root/reference has no multi-device path; callers write
+ * `[eval_tree_array(t, X, ops) for t in trees]`, benchmark/benchmarks.jl:76-91).  When the caller
+ * wants the reference's single (n_trees x nsamples) result on ONE device, no collective is
+ * needed after the kernel: rank r passes `out_dev = root_buffer + first_column_r` with
+ * `ldo = nsamples_total` to dex_eval, and the interpreter's result stores land directly in the
+ * root GPU's memory through NVLink peer mapping, overlapped with the arithmetic tile by tile.
+ * These three calls provide the mapping across processes (CUDA IPC):
+ *   dex_device_alloc   plain cudaMalloc'ed buffer on the context's device (IPC-exportable:
+ *                      not a sub-allocation of a caching allocator)
+ *   dex_ipc_export     64-byte handle of such a buffer, to be sent to the peer processes
+ *   dex_ipc_open       maps a peer's buffer into this process (enables peer access);
+ *                      the returned pointer is valid as `out_dev` / `ok_dev` of dex_eval*
+ *   dex_ipc_close      unmaps it                                                        */
+#define DEX_IPC_HANDLE_BYTES 64
+int dex_device_alloc(dex_ctx* ctx, void** out, int64_t bytes);
+int dex_device_free(dex_ctx* ctx, void* p);
+int dex_ipc_export(dex_ctx* ctx, const void* dev_ptr, uint8_t* handle64);
+int dex_ipc_open(dex_ctx* ctx, const uint8_t* handle64, void** out);
+int dex_ipc_close(dex_ctx* ctx, void* p);
+
 /* ---- introspection (tests, benchmarks) -------------------------------------------------- */
 /* kernels launched through this context so far */
 int64_t dex_ctx_launch_count(const dex_ctx* ctx);

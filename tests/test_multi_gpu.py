@@ -1,0 +1,82 @@
+"""Multi-GPU path on real devices (needs >= 2 GPUs; skipped otherwise): sample-sharded
+evaluation, the NCCL all-gather of result rows and the fused evaluate + gather-to-root over
+NVLink peer memory (dexb200/sharded.py) must all reproduce the single-GPU evaluation bit for bit
+(the same kernel evaluates the same columns; only the tiling differs)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, N, q):
+    import torch.distributed as dist
+    import dexb200
+    from dexb200 import device as D, sharded, treegen
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{rank}"))
+    try:
+        ops = dexb200.OperatorEnum(treegen.OPSET_A)
+        nodes, offsets = treegen.gen_population(64, 6, 2, 4, 5, seed=11)
+        X = np.random.default_rng(5).standard_normal((5, N)).astype(np.float32)
+        ctx = D.Context.get(rank)
+        pop = D.Population(None, ops, np.float32, wire=(nodes, offsets), ctx=ctx)
+        s, e = sharded.column_block(N, rank, world)
+        Xl = np.ascontiguousarray(X[:, s:e])
+        # (1) local block + NCCL all-gather of the rows
+        out_l, ok_l = pop.eval(Xl)
+        full_nccl, ok_nccl = sharded.gather_results(out_l, ok_l, N)
+        # (2) fused evaluate + gather-to-root through peer memory
+        fg = sharded.FusedGather(ctx, pop.n_trees, N, torch.float32, root=0)
+        full_fused, ok_fused = fg.eval(pop, Xl)
+        full_fused2, _ = fg.eval(pop, Xl)          # reusable
+        # (3) the unsharded evaluation on this GPU
+        ref, ok_ref = pop.eval(X)
+        torch.cuda.synchronize()
+
+        def same(a, b):
+            a, b = a.cpu().numpy(), b.cpu().numpy()
+            return bool(((a == b) | (np.isnan(a) & np.isnan(b))).all())
+
+        res = {"rank": rank, "nccl": same(full_nccl, ref), "ok_nccl": same(ok_nccl, ok_ref),
+               "ok_fused": same(ok_fused, ok_ref)}
+        if rank == 0:
+            res["fused"] = same(full_fused, ref) and same(full_fused2, ref)
+        fg.close()
+        q.put(res)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("N", [4096 + 37, 100_000])
+def test_sharded_gather_and_fused_peer_gather_match_single_gpu(N):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    import torch.multiprocessing as mp
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, N, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    for r in res:
+        assert r["nccl"], f"rank {r['rank']}: NCCL-gathered rows differ from the unsharded evaluation"
+        assert r["ok_nccl"] and r["ok_fused"], f"rank {r['rank']}: reduced flags differ"
+        if r["rank"] == 0:
+            assert r["fused"], "fused peer-memory gather differs from the unsharded evaluation"
