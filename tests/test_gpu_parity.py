@@ -427,6 +427,64 @@ def test_gradient_constant_subtrees_follow_the_gradient_rule(dtype, oracle):
             np.testing.assert_allclose(g, rg, rtol=1e-5, atol=1e-6)
 
 
+FAST_UNARY = ("neg", "abs", "square", "cube", "inv", "sqrt", "exp", "log", "sin", "cos", "tanh", "relu",
+              "safe_log", "safe_sqrt")
+FAST_BINARY = ("+", "-", "*", "/", "max", "min")
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("mode", ["features", "constants", "both"])
+def test_gradient_of_every_fast_handler_and_operand_form(dtype, mode, oracle):
+    """Every operator with a specialised gradient code path (the generated PTX loop for Float32,
+    csrc/gen_grad_ptx.py) in every operand form — accumulator, stack slot, feature leaf, inline
+    constant on either side — against the oracle, for all three gradient modes."""
+    ops = dexb200.OperatorEnum({1: FAST_UNARY, 2: FAST_BINARY})
+    N_ = dexb200.Node
+    x1, x2, x3 = (N_(feature=k, T=dtype) for k in (1, 2, 3))
+    c = lambda v: N_(val=v, T=dtype)
+    mul = FAST_BINARY.index("*") + 1
+    add = FAST_BINARY.index("+") + 1
+    inner = lambda: N_(mul, x1, x2)            # an operator child: arrives in the accumulator
+    other = lambda: N_(add, x2, x3)            # a second operator child: one of the two is pushed
+    trees, labels = [x2, c(3.0)], ["load/feature", "load/constant"]
+    for i, name in enumerate(FAST_UNARY, start=1):
+        for form, t in (("leaf", N_(i, x1)), ("acc", N_(i, inner())), ("const", N_(add, x1, N_(i, c(0.7)))),
+                        ("acc2", N_(i, N_(add, inner(), c(1.25))))):
+            trees.append(t)
+            labels.append(f"{name}/{form}")
+    for i, name in enumerate(FAST_BINARY, start=1):
+        forms = {"AR": N_(i, inner(), x3), "RA": N_(i, x3, inner()), "AC": N_(i, inner(), c(1.5)),
+                 "CA": N_(i, c(-0.75), inner()), "RR": N_(i, x1, x2), "RR_same": N_(i, x1, x1),
+                 "RC": N_(i, x1, c(2.5)), "CR": N_(i, c(2.5), x3), "slot_acc": N_(i, inner(), other()),
+                 "deep": N_(i, N_(i, inner(), other()), N_(i, other(), inner()))}
+        for form, t in forms.items():
+            trees.append(t)
+            labels.append(f"{name}/{form}")
+    nodes, offsets = dexb200.to_wire_population(trees)
+    rng = np.random.default_rng(17)
+    omode = {"features": oracle.GRAD_FEATURES, "constants": oracle.GRAD_CONSTANTS, "both": oracle.GRAD_BOTH}[mode]
+    dmode = {"features": D.GRAD_FEATURES, "constants": D.GRAD_CONSTANTS, "both": D.GRAD_BOTH}[mode]
+    pop = D.Population(None, ops, dtype, wire=(nodes, offsets))
+    n_ok = 0
+    # positive inputs keep sqrt/log/inv finite; signed inputs exercise the failure paths
+    for X in (rng.uniform(0.5, 2.0, (3, 600)).astype(dtype), rng.standard_normal((3, 600)).astype(dtype)):
+        out, grad, off, ok = pop.eval_grad(X, dmode)
+        out, grad, ok = out.cpu().numpy(), grad.cpu().numpy(), ok.cpu().numpy().astype(bool)
+        ref, rgrads, rok = oracle.eval_grad_population(nodes, offsets, ops.opcodes, X, omode)
+        _, _, rok_elem = oracle.eval_grad_population(nodes, offsets, ops.opcodes, X, omode | oracle.GRAD_ELEMENTWISE)
+        _flags_agree(ok, rok, rok_elem, f"grad handlers/{mode}")
+        N = X.shape[1]
+        tol = 2e-5 if dtype == np.float32 else 1e-11
+        for t in np.nonzero(rok)[0]:
+            G = rgrads[t].shape[0]
+            g = grad[off[t]:off[t + 1]].reshape(N, G).T
+            assert _relerr(out[t], ref[t]) <= tol, labels[t]
+            if G:
+                assert _relerr(g, rgrads[t]) <= tol, (labels[t], mode)
+            n_ok += 1
+    assert n_ok > len(trees)
+
+
 def test_set_constants_equals_repack(oracle):
     ops = dexb200.OperatorEnum(treegen.OPSET_A)
     nodes, offsets = treegen.gen_population(80, 6, 2, 4, 3, seed=41)
