@@ -299,6 +299,31 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = node_ops_per_step * world / float(te.item())
 
+    # ---- the fused-loss entry point end to end (what optimiser-style callers consume): pinned X
+    # and y in, P float64 losses + flags out — no (P x N) result matrix crosses PCIe
+    y_host = torch.from_numpy(np.random.default_rng([1, rank]).standard_normal(NSAMPLES).astype(np.float32)).pin_memory()
+    loss_host = torch.empty(N_TREES, dtype=torch.float64).pin_memory()
+
+    def loss_step():
+        xd = X_host.to(dev, non_blocking=True)
+        yd = y_host.to(dev, non_blocking=True)
+        loss, okl = pop.eval_loss(xd.T, yd)
+        loss_host.copy_(loss, non_blocking=True)
+        ok_host.copy_(okl, non_blocking=True)
+        torch.cuda.synchronize()
+
+    for _ in range(2):
+        loss_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        loss_step()
+    loss_s = (time.perf_counter() - t0) / e2e_steps
+    tl = torch.tensor([loss_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tl, op=dist.ReduceOp.MAX)
+    e2e_loss_value = node_ops_per_step * world / float(tl.item())
+
     if rank == 0:
         peak, peak_src = peaks()
         alg_bytes = float(N_TREES) * NSAMPLES * BYTES_PER_UNIT      # per launch (per GPU)
@@ -329,6 +354,11 @@ def main():
                     "h2d_bytes_per_step": int(X_host.numel() * 4),
                     "d2h_bytes_per_step": int(out_host.numel() * 4 + ok_host.numel()),
                     "ms_per_step": float(te.item()) * 1e3, "entry": "dex_eval_host (pinned host buffers)"},
+            "e2e_fused_loss": {"value": e2e_loss_value, "unit": UNIT,
+                               "h2d_bytes_per_step": int(X_host.numel() * 4 + y_host.numel() * 4),
+                               "d2h_bytes_per_step": int(loss_host.numel() * 8 + ok_host.numel()),
+                               "ms_per_step": float(tl.item()) * 1e3,
+                               "entry": "dex_eval_loss (per-tree MSE; the P x N results never leave the SM)"},
             "gpu_launches": int(launches),
             "clocks": clk.summary(),
             "wall_s_timed_region": t_wall,

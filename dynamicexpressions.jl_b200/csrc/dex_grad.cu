@@ -54,11 +54,15 @@
 #ifndef DEX_GRAD_PTX
 #define DEX_GRAD_PTX 1
 #endif
+// shared memory per CTA above which the launcher halves the CTA (keeps >= 2 CTAs per SM)
+#ifndef DEX_GRAD_SMEM_SOFT
+#define DEX_GRAD_SMEM_SOFT (100 * 1024)
+#endif
 #ifndef DEX_GRAD_MIN_CTAS
-#define DEX_GRAD_MIN_CTAS 4
+#define DEX_GRAD_MIN_CTAS 2
 #endif
 #ifndef DEX_GRAD_THREADS
-#define DEX_GRAD_THREADS 128
+#define DEX_GRAD_THREADS 256
 #endif
 
 namespace dex {
@@ -352,7 +356,16 @@ __device__ __forceinline__ void combine_un(T (&ad)[GC][VK<T, U>::K], const T (&p
 }
 
 #if DEX_GRAD_PTX
-#include "dex_grad_f32.inc"
+#ifndef DEX_GRAD_INC
+#define DEX_GRAD_INC "dex_grad_f32.inc"     // generated for DEX_GRAD_THREADS threads per CTA
+#endif
+#include DEX_GRAD_INC
+// runs the generated loop for (GC, U, NT) when it exists; otherwise leaves pc untouched and the
+// C++ `step` executes the whole tape
+template <int GC, int U, int NT, typename... A>
+__device__ __forceinline__ void ptx_loop(A&&... a) {
+    if constexpr (GradLoopF32<GC, U, NT>::exists) GradLoopF32<GC, U, NT>::run(static_cast<A&&>(a)...);
+}
 #endif
 
 // DIFF: eval_diff_tree_array (one direction, no validity checks, GEN class everywhere)
@@ -575,21 +588,25 @@ __global__ void __launch_bounds__(DEX_GRAD_THREADS, DEX_GRAD_MIN_CTAS) grad_kern
                 if (!DIFF) A::check(nf, vo);
             };
             // single call site of `step` (so that it is inlined and the dual accumulator stays in
-            // registers): the Float32 128-thread launch runs the instruction loop as one inline-PTX
+            // registers): the Float32 256- and 128-thread launches run the instruction loop as one inline-PTX
             // block with jump-table dispatch (gen_grad_ptx.py), which returns at the end of the tape
             // or at the first instruction it does not implement natively; `step` executes that one.
-            constexpr bool HAS_PTX = DEX_GRAD_PTX && sizeof(T) == 4 && (U == 1 || U == 2) && !DIFF;
-            const bool use_ptx = HAS_PTX && nthr == 128;
+            constexpr bool HAS_PTX = DEX_GRAD_PTX && sizeof(T) == 4 && !DIFF;
             if (pass > 0) ins = __ldg(ip);
             int pc = 0;
             while (pc < n) {
 #if DEX_GRAD_PTX
                 if constexpr (HAS_PTX) {
-                    if (use_ptx) {
+                    // the loops are generated per CTA size (row strides are immediates)
+                    if (nthr == 256 || nthr == 128) {
                         const uint32_t my_s = (uint32_t)__cvta_generic_to_shared(my);
                         float nfa[2] = {nf, 0.f};
-                        GradLoopF32<GC, U>::run(pc, av, ad, nfa, ins, ip, n, my_s, S, S * GC, foff - S, coff, ordp,
-                                             mode != DEX_GRAD_FEATURES ? 1 : 0);
+                        if (nthr == 256)
+                            ptx_loop<GC, U, 256>(pc, av, ad, nfa, ins, ip, n, my_s, S, S * GC, foff - S, coff, ordp,
+                                                 mode != DEX_GRAD_FEATURES ? 1 : 0);
+                        else
+                            ptx_loop<GC, U, 128>(pc, av, ad, nfa, ins, ip, n, my_s, S, S * GC, foff - S, coff, ordp,
+                                                 mode != DEX_GRAD_FEATURES ? 1 : 0);
                         nf = nfa[0] + nfa[1];
                         if (pc < n) ins = __ldg(ip + pc);   // early exit: `ins` is two instructions ahead
                     }
@@ -695,7 +712,7 @@ GradShape pick_shape(int dtype, int F, int max_stack, int Gmax) {
     auto bytes = [&](int th, int gc) {
         return ((size_t)max_stack * (1 + gc) + (size_t)F) * (size_t)th * K * es;
     };
-    while (bytes(s.threads, s.GC) > 100 * 1024 && s.threads > 32) s.threads >>= 1;
+    while (bytes(s.threads, s.GC) > DEX_GRAD_SMEM_SOFT && s.threads > 32) s.threads >>= 1;
     while (bytes(s.threads, s.GC) > G_SMEM_LIMIT && s.GC > 1) s.GC = s.GC > 4 ? 4 : s.GC > 2 ? 2 : 1;
     s.smem = std::max<size_t>(bytes(s.threads, s.GC), 16);
     s.tile = (int64_t)s.threads * K;
