@@ -299,13 +299,18 @@ __global__ void __launch_bounds__(DEX_MAX_THREADS, DEX_MIN_CTAS) eval_kernel(con
     const bool full_tile = (s0 + TILE <= a.N) && ((a.ldo % C) == 0) &&
                            ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0);
 
+    // The tape offsets are loaded one tree ahead, and the first instruction of a tree arrives as
+    // the prefetch of its predecessor's last one (tapes are contiguous, the buffer carries slack):
+    // no tree starts with a chain of dependent global loads.
+    int64_t off = a.tape_off[t0], off_next = a.tape_off[t0 + 1];
+    uint4 ins0 = __ldg(a.tape + off);   // instruction at the current pc of the PTX loop
     for (int t = t0; t < t1; ++t) {
 #if DEX_SYNC_TREE
         __syncthreads();  // experiment: re-align the warps of the CTA at every tree
 #endif
-        const int64_t off = a.tape_off[t];
-        const int n = (int)(a.tape_off[t + 1] - off);
+        const int n = (int)(off_next - off);
         const uint4* ip = a.tape + off;
+        const int64_t off_next2 = a.tape_off[t + 2];   // slack behind the table: dex_api.cu upload()
         const T* ptree = PARAM ? a.params + (size_t)t * a.n_params * a.n_classes : nullptr;
         if (PARAM) {
             // ParametricExpression: gather this tree's per-sample parameters
@@ -500,12 +505,14 @@ __global__ void __launch_bounds__(DEX_MAX_THREADS, DEX_MIN_CTAS) eval_kernel(con
                 asm volatile(
 #include "dex_interp_f32.inc"
                     : "+r"(pc), "+f"(av[0]), "+f"(av[1]), "+f"(av[2]), "+f"(av[3]), "+f"(av[4]), "+f"(av[5]),
-                      "+f"(av[6]), "+f"(av[7]), "+f"(nfv[0]), "+f"(nfv[1])
+                      "+f"(av[6]), "+f"(av[7]), "+f"(nfv[0]), "+f"(nfv[1]), "+r"(ins0.x), "+r"(ins0.y),
+                      "+r"(ins0.z), "+r"(ins0.w)
                     : "l"(ip), "r"(n), "r"(my_s), "r"(tile_b), "r"(cs_b)
                     : "memory");
-                if (pc < n) {
+                if (pc < n) {   // early exit: ins0 is already two instructions ahead
                     step(__ldg(ip + pc));
                     ++pc;
+                    ins0 = __ldg(ip + pc);
                 }
             }
         } else {
@@ -559,6 +566,8 @@ __global__ void __launch_bounds__(DEX_MAX_THREADS, DEX_MIN_CTAS) eval_kernel(con
         }
         const bool bad = (nf[0] != nf[0]) || (nf[1] != nf[1]);
         if (__any_sync(0xffffffffu, bad) && (tid & 31) == 0) a.ok[t] = 0;
+        off = off_next;
+        off_next = off_next2;
     }
 }
 
