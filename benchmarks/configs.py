@@ -93,6 +93,19 @@ def main():
 
     if want("C2"):
         eval_cfg("C2", "1k depth-8 trees, 5 features, Float32, 2^16 samples", 1000, 8, 5, 1 << 16)
+    if want("C2-f64"):
+        P, F, N = 1000, 5, 1 << 16
+        nodes, offsets = treegen.gen_population(P, 8, 2, 4, F, seed=0, dtype=np.float64)
+        pop64 = D.Population(None, ops, np.float64, wire=(nodes, offsets))
+        X = torch.randn((N, F), device="cuda", dtype=torch.float64)
+        out = torch.empty((P, N), device="cuda", dtype=torch.float64)
+        ok = torch.empty(P, device="cuda", dtype=torch.uint8)
+        ms, med = timeit(lambda: pop64.eval(X.T, out=out, ok=ok), args.reps)
+        emit("C2-f64", "the C2 population in Float64 (C++ handlers, no PTX loop)", ms, med, pop64.info["n_nodes"] * N,
+             P * N * (F * 8 + 8))
+        ms, med = timeit(lambda: pop64.eval_grad(X.T, D.GRAD_FEATURES), args.reps)
+        emit("C3-f64", "d/dX of the C2 population in Float64", ms, med, pop64.info["n_nodes"] * N,
+             P * N * (F * 8 + (1 + F) * 8))
     if want("C3"):
         P, F, N = 1000, 5, 1 << 16
         pop = population(P, 8, F)
