@@ -602,18 +602,26 @@ int dex_eval_loss(dex_ctx* ctx, const dex_population* pop, const void* X_dev, in
     if (rc) return rc;
     if ((rc = check_eval_args(ctx, pop, X_dev, nfeatures, nsamples, ldx, nullptr, 0, ok_dev))) return rc;
     if (!y_dev || !loss_dev) return set_err(ctx, DEX_ERR_INVALID, "null y / loss");
-    if (weights_dev) return set_err(ctx, DEX_ERR_UNSUPPORTED, "weighted loss: normalise weights on the caller side (not implemented)");
     if (pop->h.max_parameter >= 0) return set_err(ctx, DEX_ERR_INVALID, "population has parameter leaves");
     if (pop->h.n_trees == 0) return DEX_OK;
     int threads; size_t smem;
     const int64_t n_tiles = eval_num_tiles(pop->h.dtype, nfeatures, pop->h.folded->max_stack + pop->h.n_param_rows, std::max<int64_t>(nsamples, 1), &threads, &smem);
-    if ((rc = ensure_scratch(ctx, (size_t)n_tiles * (size_t)pop->h.n_trees * sizeof(double)))) return rc;
-    double* partial = static_cast<double*>(ctx->scratch);
+    // scratch: [sum of weights (256 B slot)] [per-tile partial sums]
+    if ((rc = ensure_scratch(ctx, 256 + (size_t)n_tiles * (size_t)pop->h.n_trees * sizeof(double)))) return rc;
+    double* wsum = static_cast<double*>(ctx->scratch);
+    double* partial = reinterpret_cast<double*>(static_cast<char*>(ctx->scratch) + 256);
+    if (weights_dev && nsamples > 0) {
+        cudaError_t e = launch_weight_sum(pop->h.dtype, weights_dev, nsamples, wsum, ctx->stream);
+        if (e != cudaSuccess) return cuda_err(ctx, e, "weight sum");
+        ctx->launches += 1;
+    }
     if ((rc = run_eval(ctx, pop, X_dev, nfeatures, nsamples, ldx, nullptr, 0, ok_dev, eval_flags, nullptr, 0,
-                       0, nullptr, y_dev, nullptr, partial, nullptr)))
+                       0, nullptr, y_dev, weights_dev, partial, nullptr)))
         return rc;
-    cudaError_t e = launch_loss_reduce(partial, nsamples > 0 ? n_tiles : 0, pop->h.n_trees,
-                                       nsamples > 0 ? 1.0 / (double)nsamples : 0.0, loss_dev, ctx->stream);
+    cudaError_t e = launch_loss_grad_reduce(partial, nsamples > 0 ? n_tiles : 0, pop->h.n_trees, pop->h.n_trees,
+                                            nsamples > 0 ? 1.0 / (double)nsamples : 0.0,
+                                            (weights_dev && nsamples > 0) ? wsum : nullptr, loss_dev, nullptr,
+                                            ctx->stream);
     if (e != cudaSuccess) return cuda_err(ctx, e, "loss reduce");
     ctx->launches += 1;
     return DEX_OK;
@@ -633,9 +641,16 @@ int dex_grad_offsets(const dex_population* pop, int32_t nfeatures, int64_t nsamp
     return DEX_OK;
 }
 
+struct LossSpec {            // fused loss + gradient of the loss (dex_eval_loss_grad)
+    const void* y;
+    const void* w;
+    double* loss;
+    double* grad;
+};
+
 static int run_grad(dex_ctx* ctx, const dex_population* cpop, const void* X, int32_t F, int64_t N,
                     int64_t ldx, int mode, int32_t direction, void* out, int64_t ldo, void* grad,
-                    const int64_t* grad_offsets_host, uint8_t* ok) {
+                    const int64_t* grad_offsets_host, uint8_t* ok, const LossSpec* ls = nullptr) {
     dex_population* pop = const_cast<dex_population*>(cpop);
     const PackedPopulation& h = pop->h;
     if (h.max_parameter >= 0) return set_err(ctx, DEX_ERR_UNSUPPORTED, "derivatives of parametric populations are not implemented");
@@ -652,7 +667,7 @@ static int run_grad(dex_ctx* ctx, const dex_population* cpop, const void* X, int
     // Gradients w.r.t. constants and eval_diff run the unfolded tape.
     const bool folded = mode == DEX_GRAD_FEATURES && F > 0;
     const PackedPopulation& img = folded ? *h.folded : h;
-    const int64_t n_tiles = grad_num_tiles(h.dtype, F, img.max_stack, Gmax, N);
+    const int64_t n_tiles = grad_num_tiles(h.dtype, F, img.max_stack, Gmax, N, ls != nullptr);
     const int64_t want = (int64_t)ctx->sm_count * 8 * 4;
     int64_t n_chunks = std::max<int64_t>(1, (want + n_tiles - 1) / n_tiles);
     n_chunks = std::max<int64_t>(n_chunks, ((int64_t)img.tape.size() + 127) / 128);
@@ -660,7 +675,7 @@ static int run_grad(dex_ctx* ctx, const dex_population* cpop, const void* X, int
     const int32_t* chunks = nullptr;
     int rc = chunk_table(ctx, pop, (int32_t)n_chunks, &chunks);
     if (rc) return rc;
-    if ((rc = ensure_xt(ctx, grad_xt_bytes(h.dtype, F, img.max_stack, Gmax, N)))) return rc;
+    if ((rc = ensure_xt(ctx, grad_xt_bytes(h.dtype, F, img.max_stack, Gmax, N, ls != nullptr)))) return rc;
     GradArgs a{};
     a.dtype = h.dtype;
     if (folded) {
@@ -674,19 +689,65 @@ static int run_grad(dex_ctx* ctx, const dex_population* cpop, const void* X, int
     a.n_trees = h.n_trees; a.max_stack = img.max_stack;
     a.X = X; a.xt = ctx->xt; a.F = F; a.N = N; a.ldx = ldx; a.mode = mode; a.direction = direction;
     a.out = out; a.ldo = ldo; a.grad = grad; a.ok = ok; a.grad_off = nullptr;
+    double* wsum = nullptr;
+    int64_t stride = 0;
     if (mode >= 0) {
-        const size_t bytes = (size_t)(h.n_trees + 1) * sizeof(int64_t);
+        // scratch: [grad offsets (n_trees + 1) int64] [sum of weights] [per-tile partial sums]
+        const size_t off_bytes = (((size_t)(h.n_trees + 1) * sizeof(int64_t)) + 255) & ~(size_t)255;
+        size_t bytes = off_bytes;
+        if (ls) {
+            stride = h.n_trees + grad_offsets_host[h.n_trees];
+            bytes += 256 + (size_t)n_tiles * (size_t)stride * sizeof(double);
+        }
         if ((rc = ensure_scratch(ctx, bytes))) return rc;
         // pageable -> device: the runtime stages the source before returning, so the
         // caller's array may be reused immediately
-        CU(ctx, cudaMemcpyAsync(ctx->scratch, grad_offsets_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        CU(ctx, cudaMemcpyAsync(ctx->scratch, grad_offsets_host, (size_t)(h.n_trees + 1) * sizeof(int64_t),
+                                cudaMemcpyHostToDevice, ctx->stream));
         a.grad_off = static_cast<const int64_t*>(ctx->scratch);
+        if (ls) {
+            char* base = static_cast<char*>(ctx->scratch) + off_bytes;
+            wsum = reinterpret_cast<double*>(base);
+            a.partial = reinterpret_cast<double*>(base + 256);
+            a.partial_stride = stride;
+            a.y = ls->y; a.w = ls->w;
+            // trees whose gradient has fewer entries than a pass leave nothing unwritten, but a
+            // tree with G = 0 writes no gradient entry at all and entries of padded passes are
+            // skipped: clear the buffer so that the reduction reads defined values
+            CU(ctx, cudaMemsetAsync(a.partial, 0, (size_t)n_tiles * (size_t)stride * sizeof(double), ctx->stream));
+            if (ls->w) {
+                cudaError_t e2 = launch_weight_sum(h.dtype, ls->w, N, wsum, ctx->stream);
+                if (e2 != cudaSuccess) return cuda_err(ctx, e2, "weight sum");
+                ctx->launches += 1;
+            }
+        }
     }
     int launches = 0;
     cudaError_t e = launch_grad_ex(a, chunks, (int)n_chunks, Gmax, ctx->stream, &launches);
     ctx->launches += launches;
     if (e != cudaSuccess) return cuda_err(ctx, e, "grad kernel launch");
+    if (ls) {
+        e = launch_loss_grad_reduce(a.partial, n_tiles, stride, h.n_trees, 1.0 / (double)N, ls->w ? wsum : nullptr,
+                                    ls->loss, ls->grad, ctx->stream);
+        if (e != cudaSuccess) return cuda_err(ctx, e, "loss/gradient reduce");
+        ctx->launches += 1;
+    }
     return DEX_OK;
+}
+
+int dex_eval_loss_grad(dex_ctx* ctx, const dex_population* pop, const void* X_dev, int32_t nfeatures,
+                       int64_t nsamples, int64_t ldx, const void* y_dev, const void* weights_dev, int mode,
+                       double* loss_dev, double* grad_dev, const int64_t* grad_offsets_host, uint8_t* ok_dev) {
+    int rc = ensure_device(ctx);
+    if (rc) return rc;
+    if ((rc = check_eval_args(ctx, pop, X_dev, nfeatures, nsamples, ldx, nullptr, 0, ok_dev))) return rc;
+    if (mode < 0 || mode > 2) return set_err(ctx, DEX_ERR_INVALID, "mode must be DEX_GRAD_CONSTANTS/FEATURES/BOTH");
+    if (!y_dev || !loss_dev || !grad_offsets_host) return set_err(ctx, DEX_ERR_INVALID, "null y / loss / grad_offsets");
+    if (!grad_dev && grad_offsets_host[pop->h.n_trees] > 0) return set_err(ctx, DEX_ERR_INVALID, "null grad");
+    if (nsamples <= 0) return set_err(ctx, DEX_ERR_INVALID, "the loss needs at least one sample");
+    LossSpec ls{y_dev, weights_dev, loss_dev, grad_dev};
+    return run_grad(ctx, pop, X_dev, nfeatures, nsamples, ldx, mode, 0, nullptr, 0, nullptr, grad_offsets_host,
+                    ok_dev, &ls);
 }
 
 int dex_eval_grad(dex_ctx* ctx, const dex_population* pop, const void* X_dev, int32_t nfeatures,

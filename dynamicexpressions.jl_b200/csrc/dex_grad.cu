@@ -81,6 +81,11 @@ template <typename T> struct GK {
     uint8_t* ok;
     int64_t N, ldx, ldo, n_trees;
     int32_t F, max_stack, mode, direction;
+    // fused loss mode (KM_LOSS): targets, optional weights, per-tile partial sums
+    const T* y;
+    const T* w;
+    double* partial;          // [n_tiles][partial_stride]: n_trees losses, then the gradient entries
+    int64_t partial_stride;
 };
 
 template <typename T> __device__ __forceinline__ T gconst_of(const uint4& ins);
@@ -368,9 +373,18 @@ __device__ __forceinline__ void ptx_loop(A&&... a) {
 }
 #endif
 
-// DIFF: eval_diff_tree_array (one direction, no validity checks, GEN class everywhere)
-template <typename T, int GC, int U, bool DIFF>
+// Kernel modes.  KM_GRAD: eval_grad_tree_array, value rows and (G x N) gradient blocks are stored.
+// KM_DIFF: eval_diff_tree_array (one direction, no validity checks, GEN class everywhere).
+// KM_LOSS: fused weighted squared-error loss and its gradient (what constant optimisation
+// consumes: sum_j w_j (tree(x_j) - y_j)^2 and d/d theta of it, the contraction of the
+// reference's pullback, /root/reference/src/ChainRules.jl:56-77) — neither the value rows nor
+// the (G x N) gradient ever leave the SM; per tile one double per tree and gradient entry.
+enum : int { KM_GRAD = 0, KM_DIFF = 1, KM_LOSS = 2 };
+
+template <typename T, int GC, int U, int KMODE>
 __global__ void __launch_bounds__(DEX_GRAD_THREADS, DEX_GRAD_MIN_CTAS) grad_kernel(const GK<T> a) {
+    constexpr bool DIFF = KMODE == KM_DIFF;
+    constexpr bool LOSS = KMODE == KM_LOSS;
     using V = VK<T, U>;
     using A = VA<T, V::K>;
     constexpr int C = V::C;
@@ -394,6 +408,20 @@ __global__ void __launch_bounds__(DEX_GRAD_THREADS, DEX_GRAD_MIN_CTAS) grad_kern
 
     T* my = rows + tid * C;
     const T* myx = xs + tid * C;
+    // fused loss: this thread's targets and weights (0 for the padded tail of the last tile)
+    T yv[LOSS ? K : 1], wv[LOSS ? K : 1];
+    __shared__ double red[LOSS ? 2 : 1][LOSS ? DEX_GRAD_THREADS / 32 : 1][LOSS ? GC + 1 : 1];
+    int red_buf = 0;
+    if (LOSS) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            int64_t gs = s0 + (int64_t)(k / C) * CS + (int64_t)tid * C + (k % C);
+            const bool in = gs < a.N;
+            if (!in) gs = a.N - 1;
+            yv[k] = __ldg(a.y + gs);
+            wv[k] = in ? (a.w ? __ldg(a.w + gs) : T(1)) : T(0);
+        }
+    }
     const int t0 = a.chunk_start[blockIdx.y], t1 = a.chunk_start[blockIdx.y + 1];
     const int mode = a.mode;
     const bool full_tile = (s0 + TILE <= a.N);
@@ -625,6 +653,41 @@ __global__ void __launch_bounds__(DEX_GRAD_THREADS, DEX_GRAD_MIN_CTAS) grad_kern
                 for (int g = 0; g < GC; ++g)
                     if (g0 + g < G) A::check(nf, ad[g]);
             }
+            if constexpr (LOSS) {
+                // ---- fused loss: r_j = 2 w_j (v_j - y_j);  loss += w_j (v_j - y_j)^2;
+                //      dloss/dtheta_g += r_j * d_j[g]   — reduced over the tile, in double -----------
+                double acc[GC + 1];
+#pragma unroll
+                for (int g = 0; g <= GC; ++g) acc[g] = 0.0;
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const double d = (double)av[k] - (double)yv[k];
+                    const double wd = (double)wv[k] * d;
+                    acc[GC] += wd * d;
+#pragma unroll
+                    for (int g = 0; g < GC; ++g) acc[g] += (2.0 * wd) * (double)ad[g][k];
+                }
+#pragma unroll
+                for (int g = 0; g <= GC; ++g)
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) acc[g] += __shfl_xor_sync(0xffffffffu, acc[g], o);
+                if ((tid & 31) == 0) {
+#pragma unroll
+                    for (int g = 0; g <= GC; ++g) red[red_buf][tid >> 5][g] = acc[g];
+                }
+                __syncthreads();   // one barrier per (tree, pass): red[] is double buffered
+                if (tid <= GC) {
+                    double sum = 0.0;
+                    for (int wi = 0; wi < (nthr >> 5); ++wi) sum += red[red_buf][wi][tid];
+                    double* prow = a.partial + (size_t)blockIdx.x * a.partial_stride;
+                    if (tid == GC) {
+                        if (pass == 0) prow[t] = sum;
+                    } else if (g0 + tid < G) {
+                        prow[a.n_trees + goff + g0 + tid] = sum;
+                    }
+                }
+                red_buf ^= 1;
+            } else {
             // ---- outputs of this pass -----------------------------------------------------
 #pragma unroll
             for (int u = 0; u < U; ++u) {
@@ -668,6 +731,7 @@ __global__ void __launch_bounds__(DEX_GRAD_THREADS, DEX_GRAD_MIN_CTAS) grad_kern
                 }
             }
         }
+            }
         if (!DIFF) {
             const bool bad = nf != nf;
             if (__any_sync(0xffffffffu, bad) && (tid & 31) == 0) a.ok[t] = 0;
@@ -698,13 +762,13 @@ constexpr int GRAD_U = DEX_GRAD_U;
 
 struct GradShape { int threads; int GC; size_t smem; int64_t tile; };
 
-GradShape pick_shape(int dtype, int F, int max_stack, int Gmax) {
+GradShape pick_shape(int dtype, int F, int max_stack, int Gmax, bool loss = false) {
     const size_t es = dtype == DEX_F32 ? 4 : 8;
     const int K = (dtype == DEX_F32 ? 4 : 2) * GRAD_U;
     GradShape s;
     s.threads = DEX_GRAD_THREADS;
     s.GC = std::max(1, std::min(Gmax, 8));
-    if (dtype == DEX_F64) {   // instantiated: 1, 2, 4, 8
+    if (dtype == DEX_F64 || loss) {   // instantiated: 1, 2, 4, 8
         s.GC = s.GC <= 1 ? 1 : s.GC <= 2 ? 2 : s.GC <= 4 ? 4 : 8;
     } else if (s.GC == 7) {
         s.GC = 8;             // instantiated: 1..6, 8
@@ -719,9 +783,9 @@ GradShape pick_shape(int dtype, int F, int max_stack, int Gmax) {
     return s;
 }
 
-template <typename T, int GC, bool DIFF>
+template <typename T, int GC, int KMODE>
 cudaError_t launch_one(const GK<T>& a, const GradShape& sh, int64_t n_tiles, int n_chunks, cudaStream_t stream) {
-    auto kern = grad_kernel<T, GC, GRAD_U, DIFF>;
+    auto kern = grad_kernel<T, GC, GRAD_U, KMODE>;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh.smem);
     if (err != cudaSuccess) return err;
     dim3 grid((unsigned)n_tiles, (unsigned)n_chunks);
@@ -744,26 +808,72 @@ GK<T> make_args(const GradArgs& g, const int32_t* chunk_start, int64_t Npad) {
     a.ok = g.ok;
     a.N = g.N; a.ldx = Npad; a.ldo = g.ldo; a.n_trees = g.n_trees;
     a.F = g.F; a.max_stack = g.max_stack; a.mode = g.mode; a.direction = g.direction;
+    a.y = static_cast<const T*>(g.y); a.w = static_cast<const T*>(g.w);
+    a.partial = g.partial; a.partial_stride = g.partial_stride;
     return a;
+}
+
+// second stage of the fused loss: out[i] = scale * sum over tiles of partial[tile][i], in tile order
+// (deterministic); scale = 1 / sum of weights (read from *wsum when given) or 1 / N
+__global__ void loss_grad_reduce_kernel(const double* partial, int64_t n_tiles, int64_t stride, int64_t n_trees,
+                                        double inv_n, const double* wsum, double* loss, double* grad) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= stride) return;
+    double s = 0.0;
+    for (int64_t tl = 0; tl < n_tiles; ++tl) s += partial[tl * stride + i];
+    const double scale = wsum ? 1.0 / *wsum : inv_n;
+    if (i < n_trees) loss[i] = s * scale;
+    else grad[i - n_trees] = s * scale;
+}
+
+// sum of the weights, one block, fixed order (deterministic)
+template <typename T>
+__global__ void weight_sum_kernel(const T* w, int64_t n, double* out) {
+    __shared__ double sh[256];
+    double s = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += 256) s += (double)w[i];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = sh[0];
 }
 
 }  // namespace
 
-size_t grad_xt_bytes(int dtype, int F, int max_stack, int Gmax, int64_t N) {
-    const GradShape sh = pick_shape(dtype, F, max_stack, std::max(Gmax, 1));
+cudaError_t launch_loss_grad_reduce(const double* partial, int64_t n_tiles, int64_t stride, int64_t n_trees,
+                                    double inv_n, const double* wsum, double* loss, double* grad,
+                                    cudaStream_t stream) {
+    if (stride == 0) return cudaSuccess;
+    loss_grad_reduce_kernel<<<(unsigned)((stride + 255) / 256), 256, 0, stream>>>(partial, n_tiles, stride, n_trees,
+                                                                               inv_n, wsum, loss, grad);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_weight_sum(int dtype, const void* w, int64_t n, double* out, cudaStream_t stream) {
+    if (dtype == DEX_F32) weight_sum_kernel<float><<<1, 256, 0, stream>>>(static_cast<const float*>(w), n, out);
+    else weight_sum_kernel<double><<<1, 256, 0, stream>>>(static_cast<const double*>(w), n, out);
+    return cudaGetLastError();
+}
+
+size_t grad_xt_bytes(int dtype, int F, int max_stack, int Gmax, int64_t N, bool loss) {
+    const GradShape sh = pick_shape(dtype, F, max_stack, std::max(Gmax, 1), loss);
     const int64_t n_tiles = (N + sh.tile - 1) / sh.tile;
     return (size_t)std::max<int64_t>(n_tiles * sh.tile, 1) * (size_t)std::max(F, 1) * (dtype == DEX_F32 ? 4 : 8);
 }
 
-int64_t grad_num_tiles(int dtype, int F, int max_stack, int Gmax, int64_t N) {
-    const GradShape sh = pick_shape(dtype, F, max_stack, std::max(Gmax, 1));
+int64_t grad_num_tiles(int dtype, int F, int max_stack, int Gmax, int64_t N, bool loss) {
+    const GradShape sh = pick_shape(dtype, F, max_stack, std::max(Gmax, 1), loss);
     return (N + sh.tile - 1) / sh.tile;
 }
 
 cudaError_t launch_grad_ex(const GradArgs& g, const int32_t* chunk_start, int n_chunks, int Gmax,
                            cudaStream_t stream, int* launches) {
     if (g.n_trees == 0 || g.N == 0) return cudaSuccess;
-    const GradShape sh = pick_shape(g.dtype, g.F, g.max_stack, std::max(Gmax, 1));
+    const bool loss = g.partial != nullptr;
+    const GradShape sh = pick_shape(g.dtype, g.F, g.max_stack, std::max(Gmax, 1), loss);
     if (sh.smem > G_SMEM_LIMIT) return cudaErrorInvalidConfiguration;
     const int64_t n_tiles = (g.N + sh.tile - 1) / sh.tile;
     const int64_t Npad = n_tiles * sh.tile;
@@ -780,26 +890,44 @@ cudaError_t launch_grad_ex(const GradArgs& g, const int32_t* chunk_start, int n_
     if (err != cudaSuccess) return err;
     if (launches) *launches += 1;
     const bool diff = g.mode < 0;
-    if (g.dtype == DEX_F32) {
+    if (loss) {
+        if (g.dtype == DEX_F32) {
+            const GK<float> a = make_args<float>(g, chunk_start, Npad);
+            switch (sh.GC) {
+                case 1: err = launch_one<float, 1, KM_LOSS>(a, sh, n_tiles, n_chunks, stream); break;
+                case 2: err = launch_one<float, 2, KM_LOSS>(a, sh, n_tiles, n_chunks, stream); break;
+                case 4: err = launch_one<float, 4, KM_LOSS>(a, sh, n_tiles, n_chunks, stream); break;
+                default: err = launch_one<float, 8, KM_LOSS>(a, sh, n_tiles, n_chunks, stream); break;
+            }
+        } else {
+            const GK<double> a = make_args<double>(g, chunk_start, Npad);
+            switch (sh.GC) {
+                case 1: err = launch_one<double, 1, KM_LOSS>(a, sh, n_tiles, n_chunks, stream); break;
+                case 2: err = launch_one<double, 2, KM_LOSS>(a, sh, n_tiles, n_chunks, stream); break;
+                case 4: err = launch_one<double, 4, KM_LOSS>(a, sh, n_tiles, n_chunks, stream); break;
+                default: err = launch_one<double, 8, KM_LOSS>(a, sh, n_tiles, n_chunks, stream); break;
+            }
+        }
+    } else if (g.dtype == DEX_F32) {
         const GK<float> a = make_args<float>(g, chunk_start, Npad);
-        if (diff) err = launch_one<float, 1, true>(a, sh, n_tiles, n_chunks, stream);
+        if (diff) err = launch_one<float, 1, KM_DIFF>(a, sh, n_tiles, n_chunks, stream);
         else switch (sh.GC) {
-            case 1: err = launch_one<float, 1, false>(a, sh, n_tiles, n_chunks, stream); break;
-            case 2: err = launch_one<float, 2, false>(a, sh, n_tiles, n_chunks, stream); break;
-            case 3: err = launch_one<float, 3, false>(a, sh, n_tiles, n_chunks, stream); break;
-            case 4: err = launch_one<float, 4, false>(a, sh, n_tiles, n_chunks, stream); break;
-            case 5: err = launch_one<float, 5, false>(a, sh, n_tiles, n_chunks, stream); break;
-            case 6: err = launch_one<float, 6, false>(a, sh, n_tiles, n_chunks, stream); break;
-            default: err = launch_one<float, 8, false>(a, sh, n_tiles, n_chunks, stream); break;
+            case 1: err = launch_one<float, 1, KM_GRAD>(a, sh, n_tiles, n_chunks, stream); break;
+            case 2: err = launch_one<float, 2, KM_GRAD>(a, sh, n_tiles, n_chunks, stream); break;
+            case 3: err = launch_one<float, 3, KM_GRAD>(a, sh, n_tiles, n_chunks, stream); break;
+            case 4: err = launch_one<float, 4, KM_GRAD>(a, sh, n_tiles, n_chunks, stream); break;
+            case 5: err = launch_one<float, 5, KM_GRAD>(a, sh, n_tiles, n_chunks, stream); break;
+            case 6: err = launch_one<float, 6, KM_GRAD>(a, sh, n_tiles, n_chunks, stream); break;
+            default: err = launch_one<float, 8, KM_GRAD>(a, sh, n_tiles, n_chunks, stream); break;
         }
     } else {
         const GK<double> a = make_args<double>(g, chunk_start, Npad);
-        if (diff) err = launch_one<double, 1, true>(a, sh, n_tiles, n_chunks, stream);
+        if (diff) err = launch_one<double, 1, KM_DIFF>(a, sh, n_tiles, n_chunks, stream);
         else switch (sh.GC) {
-            case 1: err = launch_one<double, 1, false>(a, sh, n_tiles, n_chunks, stream); break;
-            case 2: err = launch_one<double, 2, false>(a, sh, n_tiles, n_chunks, stream); break;
-            case 4: err = launch_one<double, 4, false>(a, sh, n_tiles, n_chunks, stream); break;
-            default: err = launch_one<double, 8, false>(a, sh, n_tiles, n_chunks, stream); break;
+            case 1: err = launch_one<double, 1, KM_GRAD>(a, sh, n_tiles, n_chunks, stream); break;
+            case 2: err = launch_one<double, 2, KM_GRAD>(a, sh, n_tiles, n_chunks, stream); break;
+            case 4: err = launch_one<double, 4, KM_GRAD>(a, sh, n_tiles, n_chunks, stream); break;
+            default: err = launch_one<double, 8, KM_GRAD>(a, sh, n_tiles, n_chunks, stream); break;
         }
     }
     if (err == cudaSuccess && launches) *launches += 1;

@@ -78,12 +78,22 @@ struct GradArgs {
     void* grad;                 // per tree (G_t x N) column-major at grad_off[t]; diff: n_trees x N rows
     const int64_t* grad_off;    // device, n_trees + 1 (unused for diff)
     uint8_t* ok;
+    // fused loss + gradient of the loss (null partial => store value rows and gradient blocks):
+    // grad_off then indexes the per-tree gradient VECTORS (dex_grad_offsets with nsamples = 1)
+    const void* y;              // device, N targets
+    const void* w;              // device, N weights or null
+    double* partial;            // device, n_tiles x partial_stride
+    int64_t partial_stride;     // n_trees + total gradient entries
 };
 // chunk_start: device table of n_chunks + 1 tree indices; Gmax: largest gradient count of any tree
 cudaError_t launch_grad_ex(const GradArgs& a, const int32_t* chunk_start, int n_chunks, int Gmax,
                            cudaStream_t stream, int* launches);
-int64_t grad_num_tiles(int dtype, int F, int max_stack, int Gmax, int64_t N);
-size_t grad_xt_bytes(int dtype, int F, int max_stack, int Gmax, int64_t N);
+int64_t grad_num_tiles(int dtype, int F, int max_stack, int Gmax, int64_t N, bool loss = false);
+size_t grad_xt_bytes(int dtype, int F, int max_stack, int Gmax, int64_t N, bool loss = false);
+cudaError_t launch_loss_grad_reduce(const double* partial, int64_t n_tiles, int64_t stride, int64_t n_trees,
+                                    double inv_n, const double* wsum, double* loss, double* grad,
+                                    cudaStream_t stream);
+cudaError_t launch_weight_sum(int dtype, const void* w, int64_t n, double* out, cudaStream_t stream);
 
 // tiny helpers
 // pos[i] >= 0: tape[pos[i]]; pos[i] < 0: scalar_tape[-(1 + pos[i])] (folded image)

@@ -56,6 +56,7 @@ ABI = {
     "dex_grad_offsets": (C.c_int, [_P, _I32, _I64, C.c_int, _P]),
     "dex_eval_diff": (C.c_int, [_P, _P, _P, _I32, _I64, _I64, _I32, _P, _P, _I64, _U8P]),
     "dex_eval_loss": (C.c_int, [_P, _P, _P, _I32, _I64, _I64, _P, _P, _P, _U8P, C.c_int]),
+    "dex_eval_loss_grad": (C.c_int, [_P, _P, _P, _I32, _I64, _I64, _P, _P, C.c_int, _P, _P, _P, _U8P]),
     "dex_eval_host": (C.c_int, [_P, _P, _P, _I32, _I64, _I64, _P, _I64, _U8P, C.c_int]),
     "dex_host_alloc": (C.c_int, [C.POINTER(_P), _I64]),
     "dex_host_free": (C.c_int, [_P]),
@@ -457,20 +458,41 @@ class Population:
                                            _ptr(ok)))
         return out, dout, ok
 
-    def eval_loss(self, X, y, *, early_exit=True):
-        """Fused mean-squared-error per tree without materialising the results:
+    def eval_loss(self, X, y, *, weights=None, early_exit=True):
+        """Fused (weighted) mean-squared-error per tree without materialising the results:
         (loss[P] float64, ok[P])."""
         import torch
         Xd, F, N, ldx = as_device_matrix(X, self.ctx.device, self.dtype_code)
         dev = f"cuda:{self.ctx.device}"
         yd = torch.as_tensor(y).to(device=dev, dtype=_torch_dtype(self.dtype_code)).contiguous()
-        assert yd.numel() == N
+        wd = None if weights is None else torch.as_tensor(weights).to(device=dev, dtype=_torch_dtype(self.dtype_code)).contiguous()
+        assert yd.numel() == N and (wd is None or wd.numel() == N)
         loss = torch.empty(self.n_trees, dtype=torch.float64, device=dev)
         ok = torch.empty(self.n_trees, dtype=torch.uint8, device=dev)
         self.ctx.use_current_stream()
-        self.ctx.check(lib().dex_eval_loss(self.ctx.h, self.h, _ptr(Xd), F, N, ldx, _ptr(yd), None,
+        self.ctx.check(lib().dex_eval_loss(self.ctx.h, self.h, _ptr(Xd), F, N, ldx, _ptr(yd), _ptr(wd),
                                            _ptr(loss), _ptr(ok), EVAL_EARLY_EXIT if early_exit else 0))
         return loss, ok
+
+    def eval_loss_grad(self, X, y, mode=GRAD_CONSTANTS, *, weights=None):
+        """Fused (weighted) mean-squared error per tree AND its gradient w.r.t. the constants
+        and/or features, without materialising values or (G x N) gradients:
+        (loss[P] float64, grad[sum G] float64, offsets[P + 1], ok[P])."""
+        import torch
+        Xd, F, N, ldx = as_device_matrix(X, self.ctx.device, self.dtype_code)
+        dev = f"cuda:{self.ctx.device}"
+        tdt = _torch_dtype(self.dtype_code)
+        yd = torch.as_tensor(y).to(device=dev, dtype=tdt).contiguous()
+        wd = None if weights is None else torch.as_tensor(weights).to(device=dev, dtype=tdt).contiguous()
+        assert yd.numel() == N and (wd is None or wd.numel() == N)
+        off = self.grad_offsets(F, 1, mode)
+        loss = torch.empty(self.n_trees, dtype=torch.float64, device=dev)
+        grad = torch.empty(max(int(off[-1]), 1), dtype=torch.float64, device=dev)
+        ok = torch.empty(self.n_trees, dtype=torch.uint8, device=dev)
+        self.ctx.use_current_stream()
+        self.ctx.check(lib().dex_eval_loss_grad(self.ctx.h, self.h, _ptr(Xd), F, N, ldx, _ptr(yd), _ptr(wd), mode,
+                                                _ptr(loss), _ptr(grad), _ptr(off), _ptr(ok)))
+        return loss, grad[: int(off[-1])], off, ok
 
     def eval_host(self, X_host, out_host, ok_host, *, early_exit=True):
         """The host-buffer entry point (dex_eval_host): numpy / pinned torch CPU tensors in the

@@ -182,6 +182,21 @@ int dex_eval_loss(dex_ctx* ctx, const dex_population* pop, const void* X_dev, in
                   int64_t nsamples, int64_t ldx, const void* y_dev, const void* weights_dev,
                   double* loss_dev, uint8_t* ok_dev, int eval_flags);
 
+/* Fused loss AND its gradient (what constant optimisation consumes — the
+ * contraction the reference's pullback performs, /root/reference/src/ChainRules.jl:56-77, with
+ * dY = d loss / d y, used by /root/reference/ext/DynamicExpressionsOptimExt.jl and
+ * test/test_optim.jl:44-52):
+ *   loss_dev[t]                 = sum_j w_j (tree_t(X[:,j]) - y[j])^2 / sum_j w_j
+ *   grad_dev[offsets[t] + g]    = d loss_dev[t] / d theta_g      (g as in dex_eval_grad, `mode`)
+ * Neither the (n_trees x nsamples) values nor the (G x nsamples) gradients are written: the
+ * reduction happens in the interpreter, deterministically (per-tile partial sums in float64,
+ * summed in tile order).  grad_offsets_host = dex_grad_offsets(pop, nfeatures, 1, mode).
+ * weights_dev may be NULL (w_j = 1).  `ok` as in dex_eval_grad.                              */
+int dex_eval_loss_grad(dex_ctx* ctx, const dex_population* pop, const void* X_dev, int32_t nfeatures,
+                       int64_t nsamples, int64_t ldx, const void* y_dev, const void* weights_dev, int mode,
+                       double* loss_dev, double* grad_dev, const int64_t* grad_offsets_host,
+                       uint8_t* ok_dev);
+
 /* ---- host-buffer convenience (the reference-facing call: host arrays in, host arrays
  * out; copies are issued on the context stream through pinned staging buffers and the
  * call returns after the results have landed)                                          */

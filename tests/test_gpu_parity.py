@@ -527,6 +527,76 @@ def test_fused_loss_matches_materialised_results():
     np.testing.assert_allclose(got[good], want[good], rtol=1e-10)
 
 
+def test_weighted_fused_loss_matches_materialised_results():
+    ops = dexb200.OperatorEnum(treegen.OPSET_A)
+    nodes, offsets = treegen.gen_population(60, 6, 2, 4, 4, seed=52)
+    rng = np.random.default_rng(12)
+    X = rng.standard_normal((4, 3001)).astype(np.float32)
+    y = rng.standard_normal(3001).astype(np.float32)
+    w = rng.uniform(0.1, 3.0, 3001).astype(np.float32)
+    pop = D.Population(None, ops, np.float32, wire=(nodes, offsets))
+    out, ok = pop.eval(X)
+    loss, ok2 = pop.eval_loss(X, y, weights=w)
+    assert (ok == ok2).all()
+    o = out.cpu().numpy().astype(np.float64)
+    w64 = w.astype(np.float64)
+    want = (w64[None, :] * (o - y[None, :].astype(np.float64)) ** 2).sum(axis=1) / w64.sum()
+    good = ok.cpu().numpy().astype(bool)
+    np.testing.assert_allclose(loss.cpu().numpy()[good], want[good], rtol=1e-10)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("mode", ["constants", "features", "both"])
+@pytest.mark.parametrize("weighted", [False, True])
+def test_fused_loss_gradient_matches_oracle(dtype, mode, weighted, oracle):
+    """dex_eval_loss_grad: loss and d loss / d theta per tree, reduced inside the interpreter,
+    against the same contraction of the oracle's (value, gradient) arrays
+    (the reference's pullback, src/ChainRules.jl:56-77, with dY = 2 w (y_pred - y) / sum w)."""
+    spec = {1: ("cos", "exp", "sin"), 2: ("+", "-", "*", "/")}
+    ops = dexb200.OperatorEnum(spec)
+    nodes, offsets = treegen.gen_population(90, 6, 3, 4, 3, seed=77, dtype=dtype)
+    rng = np.random.default_rng(21)
+    N = 1500
+    X = rng.standard_normal((3, N)).astype(dtype)
+    y = rng.standard_normal(N).astype(dtype)
+    w = rng.uniform(0.2, 2.0, N).astype(dtype) if weighted else None
+    omode = {"features": oracle.GRAD_FEATURES, "constants": oracle.GRAD_CONSTANTS, "both": oracle.GRAD_BOTH}[mode]
+    dmode = {"features": D.GRAD_FEATURES, "constants": D.GRAD_CONSTANTS, "both": D.GRAD_BOTH}[mode]
+    pop = D.Population(None, ops, dtype, wire=(nodes, offsets))
+    loss, grad, off, ok = pop.eval_loss_grad(X, y, dmode, weights=w)
+    loss, grad, ok = loss.cpu().numpy(), grad.cpu().numpy(), ok.cpu().numpy().astype(bool)
+    ref, rgrads, rok = oracle.eval_grad_population(nodes, offsets, ops.opcodes, X, omode)
+    _, _, rok_elem = oracle.eval_grad_population(nodes, offsets, ops.opcodes, X, omode | oracle.GRAD_ELEMENTWISE)
+    _flags_agree(ok, rok, rok_elem, f"loss grad/{mode}")
+    # conditioning yardsticks (as in _check_population): how far the oracle's own value / gradient
+    # move when X is perturbed by one ulp and, for Float32, when evaluated in Float64; chaotic
+    # compositions such as cos(exp(exp(x))) are compared at 30x that movement
+    ref_p, rgrads_p, _ = oracle.eval_grad_population(nodes, offsets, ops.opcodes, np.nextafter(X, dtype(np.inf)), omode)
+    ref64, rgrads64, _ = oracle.eval_grad_population(nodes, offsets, ops.opcodes, X.astype(np.float64), omode)
+    w64 = np.ones(N) if w is None else w.astype(np.float64)
+    n_checked = 0
+    for t in np.nonzero(rok)[0]:
+        G = rgrads[t].shape[0]
+        cond = max(_relerr(ref_p[t], ref[t]), _relerr(rgrads_p[t], rgrads[t]) if G else 0.0)
+        if dtype == np.float32:
+            cond = max(cond, _relerr(ref[t], ref64[t]), _relerr(rgrads[t], rgrads64[t]) if G else 0.0)
+        if not np.isfinite(cond):
+            continue
+        tol = max(2e-4 if dtype == np.float32 else 1e-6, 30 * cond)
+        r = ref[t].astype(np.float64) - y.astype(np.float64)
+        want_loss = (w64 * r * r).sum() / w64.sum()
+        assert abs(loss[t] - want_loss) <= tol * max(want_loss, 1e-30), (t, loss[t], want_loss)
+        assert off[t + 1] - off[t] == G
+        if G:
+            terms = 2.0 * w64[None, :] * r[None, :] * rgrads[t].astype(np.float64)     # (G, N)
+            want = terms.sum(axis=1) / w64.sum()
+            scale = np.abs(terms).sum(axis=1) / w64.sum()                                # conditioning of the sum
+            got = grad[off[t]:off[t + 1]]
+            assert np.all(np.abs(got - want) <= tol * np.maximum(scale, 1e-30)), (t, mode, got, want)
+            n_checked += 1
+    assert n_checked > 10
+
+
 @pytest.mark.parametrize("P_,N", [(64, 4096), (400, 8192)])   # the second takes the sliced D2H pipeline
 def test_host_entry_point_matches_device_entry_point(P_, N):
     import torch
