@@ -485,6 +485,53 @@ def test_gradient_of_every_fast_handler_and_operand_form(dtype, mode, oracle):
     assert n_ok > len(trees)
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_random_trees_with_ternary_operators_value_and_gradient(dtype, oracle):
+    """The reference's property test (test/test_supposition_consistency.jl:16-104: random trees
+    over ((abs, cos, exp), (+, -, *, /), (fma, clamp, +, max)), X 5 x (1..16)) as a population:
+    values, flags and gradients (ternary operators take the generic gradient path)."""
+    from tests.test_abi_and_flatten import _random_wire
+    spec = {1: ("abs", "cos", "exp"), 2: ("+", "-", "*", "/"), 3: ("fma", "clamp", "+", "max")}
+    ops = dexb200.OperatorEnum(spec)
+    rng = np.random.default_rng(2024)
+    wires = []
+    while len(wires) < 250:
+        w = _random_wire(rng, ops, 5, max_nodes=int(rng.integers(1, 60)))
+        if np.isfinite(w["val"][(w["degree"] == 0) & (w["kind"] == 0)]).all():
+            wires.append(w)
+    nodes = np.concatenate(wires)
+    offsets = np.concatenate([[0], np.cumsum([len(w) for w in wires])]).astype(np.int64)
+    for N in (1, 16, 333):
+        X = rng.standard_normal((5, N)).astype(dtype)
+        errs, ok = _check_population(oracle, nodes, offsets, ops, X, dtype, label=f"ternary N={N}")
+        assert len(errs) > 20
+        pop = D.Population(None, ops, dtype, wire=(nodes, offsets))
+        for dmode, omode in ((D.GRAD_FEATURES, oracle.GRAD_FEATURES), (D.GRAD_BOTH, oracle.GRAD_BOTH)):
+            out, grad, off, gok = pop.eval_grad(X, dmode)
+            out, grad, gok = out.cpu().numpy(), grad.cpu().numpy(), gok.cpu().numpy().astype(bool)
+            ref, rgrads, rok = oracle.eval_grad_population(nodes, offsets, ops.opcodes, X, omode)
+            _, _, rok_elem = oracle.eval_grad_population(nodes, offsets, ops.opcodes, X, omode | oracle.GRAD_ELEMENTWISE)
+            ref_p, rgrads_p, _ = oracle.eval_grad_population(nodes, offsets, ops.opcodes,
+                                                             np.nextafter(X, dtype(np.inf)), omode)
+            ref64, rgrads64, _ = oracle.eval_grad_population(nodes, offsets, ops.opcodes, X.astype(np.float64), omode)
+            _flags_agree(gok, rok, rok_elem, f"ternary grad N={N}")
+            n_checked = 0
+            for t in np.nonzero(rok)[0]:
+                G = rgrads[t].shape[0]
+                g = grad[off[t]:off[t + 1]].reshape(N, G).T
+                cond = max(_relerr(ref_p[t], ref[t]), _relerr(rgrads_p[t], rgrads[t]) if G else 0.0)
+                if dtype == np.float32:
+                    cond = max(cond, _relerr(ref[t], ref64[t]), _relerr(rgrads[t], rgrads64[t]) if G else 0.0)
+                if not np.isfinite(cond) or cond > 1e-2:      # chaotic: nothing to compare
+                    continue
+                tol = max(RTOL[dtype], 30 * cond)
+                assert _relerr(out[t], ref[t]) <= tol, (t, N)
+                if G:
+                    assert _relerr(g, rgrads[t]) <= tol, (t, N, dmode)
+                n_checked += 1
+            assert n_checked > 20
+
+
 def test_set_constants_equals_repack(oracle):
     ops = dexb200.OperatorEnum(treegen.OPSET_A)
     nodes, offsets = treegen.gen_population(80, 6, 2, 4, 3, seed=41)
