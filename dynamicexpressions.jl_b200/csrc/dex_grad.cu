@@ -763,12 +763,13 @@ constexpr int GRAD_U = DEX_GRAD_U;
 struct GradShape { int threads; int GC; size_t smem; int64_t tile; };
 
 GradShape pick_shape(int dtype, int F, int max_stack, int Gmax, bool loss = false) {
+    (void)loss;
     const size_t es = dtype == DEX_F32 ? 4 : 8;
     const int K = (dtype == DEX_F32 ? 4 : 2) * GRAD_U;
     GradShape s;
     s.threads = DEX_GRAD_THREADS;
     s.GC = std::max(1, std::min(Gmax, 8));
-    if (dtype == DEX_F64 || loss) {   // instantiated: 1, 2, 4, 8
+    if (dtype == DEX_F64) {   // instantiated: 1, 2, 4, 8
         s.GC = s.GC <= 1 ? 1 : s.GC <= 2 ? 2 : s.GC <= 4 ? 4 : 8;
     } else if (s.GC == 7) {
         s.GC = 8;             // instantiated: 1..6, 8
@@ -896,7 +897,10 @@ cudaError_t launch_grad_ex(const GradArgs& g, const int32_t* chunk_start, int n_
             switch (sh.GC) {
                 case 1: err = launch_one<float, 1, KM_LOSS>(a, sh, n_tiles, n_chunks, stream); break;
                 case 2: err = launch_one<float, 2, KM_LOSS>(a, sh, n_tiles, n_chunks, stream); break;
+                case 3: err = launch_one<float, 3, KM_LOSS>(a, sh, n_tiles, n_chunks, stream); break;
                 case 4: err = launch_one<float, 4, KM_LOSS>(a, sh, n_tiles, n_chunks, stream); break;
+                case 5: err = launch_one<float, 5, KM_LOSS>(a, sh, n_tiles, n_chunks, stream); break;
+                case 6: err = launch_one<float, 6, KM_LOSS>(a, sh, n_tiles, n_chunks, stream); break;
                 default: err = launch_one<float, 8, KM_LOSS>(a, sh, n_tiles, n_chunks, stream); break;
             }
         } else {
