@@ -48,6 +48,10 @@
 
 #include <algorithm>
 
+// 16-byte chunks per thread for Float64 (K = 2 * U samples)
+#ifndef DEX_GRAD_U64
+#define DEX_GRAD_U64 1
+#endif
 #ifndef DEX_GRAD_U
 #define DEX_GRAD_U 1
 #endif
@@ -759,26 +763,23 @@ __global__ void gtranspose_pad_kernel(const T* __restrict__ X, int64_t ldx, int 
 
 constexpr size_t G_SMEM_LIMIT = 227 * 1024;
 constexpr int GRAD_U = DEX_GRAD_U;
+constexpr int GRAD_U64 = DEX_GRAD_U64;
 
 struct GradShape { int threads; int GC; size_t smem; int64_t tile; };
 
 GradShape pick_shape(int dtype, int F, int max_stack, int Gmax, bool loss = false) {
     (void)loss;
     const size_t es = dtype == DEX_F32 ? 4 : 8;
-    const int K = (dtype == DEX_F32 ? 4 : 2) * GRAD_U;
+    const int K = dtype == DEX_F32 ? 4 * GRAD_U : 2 * GRAD_U64;
     GradShape s;
     s.threads = DEX_GRAD_THREADS;
     s.GC = std::max(1, std::min(Gmax, 8));
-    if (dtype == DEX_F64) {   // instantiated: 1, 2, 4, 8
-        s.GC = s.GC <= 1 ? 1 : s.GC <= 2 ? 2 : s.GC <= 4 ? 4 : 8;
-    } else if (s.GC == 7) {
-        s.GC = 8;             // instantiated: 1..6, 8
-    }
+    if (s.GC == 7) s.GC = 8;   // instantiated: 1..6, 8
     auto bytes = [&](int th, int gc) {
         return ((size_t)max_stack * (1 + gc) + (size_t)F) * (size_t)th * K * es;
     };
     while (bytes(s.threads, s.GC) > DEX_GRAD_SMEM_SOFT && s.threads > 32) s.threads >>= 1;
-    while (bytes(s.threads, s.GC) > G_SMEM_LIMIT && s.GC > 1) s.GC = s.GC > 4 ? 4 : s.GC > 2 ? 2 : 1;
+    while (bytes(s.threads, s.GC) > G_SMEM_LIMIT && s.GC > 1) s.GC = s.GC > 4 ? 4 : s.GC > 2 ? 2 : 1;   // all instantiated
     s.smem = std::max<size_t>(bytes(s.threads, s.GC), 16);
     s.tile = (int64_t)s.threads * K;
     return s;
@@ -786,7 +787,7 @@ GradShape pick_shape(int dtype, int F, int max_stack, int Gmax, bool loss = fals
 
 template <typename T, int GC, int KMODE>
 cudaError_t launch_one(const GK<T>& a, const GradShape& sh, int64_t n_tiles, int n_chunks, cudaStream_t stream) {
-    auto kern = grad_kernel<T, GC, GRAD_U, KMODE>;
+    auto kern = grad_kernel<T, GC, (sizeof(T) == 8 ? GRAD_U64 : GRAD_U), KMODE>;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh.smem);
     if (err != cudaSuccess) return err;
     dim3 grid((unsigned)n_tiles, (unsigned)n_chunks);
@@ -908,7 +909,10 @@ cudaError_t launch_grad_ex(const GradArgs& g, const int32_t* chunk_start, int n_
             switch (sh.GC) {
                 case 1: err = launch_one<double, 1, KM_LOSS>(a, sh, n_tiles, n_chunks, stream); break;
                 case 2: err = launch_one<double, 2, KM_LOSS>(a, sh, n_tiles, n_chunks, stream); break;
+                case 3: err = launch_one<double, 3, KM_LOSS>(a, sh, n_tiles, n_chunks, stream); break;
                 case 4: err = launch_one<double, 4, KM_LOSS>(a, sh, n_tiles, n_chunks, stream); break;
+                case 5: err = launch_one<double, 5, KM_LOSS>(a, sh, n_tiles, n_chunks, stream); break;
+                case 6: err = launch_one<double, 6, KM_LOSS>(a, sh, n_tiles, n_chunks, stream); break;
                 default: err = launch_one<double, 8, KM_LOSS>(a, sh, n_tiles, n_chunks, stream); break;
             }
         }
@@ -930,7 +934,10 @@ cudaError_t launch_grad_ex(const GradArgs& g, const int32_t* chunk_start, int n_
         else switch (sh.GC) {
             case 1: err = launch_one<double, 1, KM_GRAD>(a, sh, n_tiles, n_chunks, stream); break;
             case 2: err = launch_one<double, 2, KM_GRAD>(a, sh, n_tiles, n_chunks, stream); break;
+            case 3: err = launch_one<double, 3, KM_GRAD>(a, sh, n_tiles, n_chunks, stream); break;
             case 4: err = launch_one<double, 4, KM_GRAD>(a, sh, n_tiles, n_chunks, stream); break;
+            case 5: err = launch_one<double, 5, KM_GRAD>(a, sh, n_tiles, n_chunks, stream); break;
+            case 6: err = launch_one<double, 6, KM_GRAD>(a, sh, n_tiles, n_chunks, stream); break;
             default: err = launch_one<double, 8, KM_GRAD>(a, sh, n_tiles, n_chunks, stream); break;
         }
     }
