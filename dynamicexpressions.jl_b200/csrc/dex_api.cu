@@ -57,6 +57,10 @@ struct dex_population {
     Instr* d_ctape = nullptr;
     int64_t* d_seg = nullptr;
     int64_t* d_seg_off = nullptr;
+    // outcome of the constant folding for the CURRENT constants, per rule (0 = evaluation,
+    // 1 = gradient): computed by launch_fold on first use, invalidated when constants change
+    uint8_t* d_fold_ok[2] = {nullptr, nullptr};
+    bool fold_valid[2] = {false, false};
     std::map<int32_t, int32_t*> chunk_tables;  // n_chunks -> device table
     std::map<int32_t, std::vector<int32_t>> chunk_tables_host;
     std::map<std::string, int64_t*> grad_off_tables;
@@ -193,6 +197,25 @@ int check_eval_args(dex_ctx* ctx, const dex_population* pop, const void* X, int3
     return DEX_OK;
 }
 
+// Constant folding is a function of the constants only: run the scalar tape once per change of
+// the constants (launch_fold) instead of in every call's prepass.  Returns the per-tree outcome.
+int ensure_folded(dex_ctx* ctx, dex_population* pop, int rule, const uint8_t** fold_ok) {
+    *fold_ok = nullptr;
+    const PackedPopulation& f = *pop->h.folded;
+    if (f.seg.empty()) return DEX_OK;          // nothing to fold: the prepass presets ok[] = 1
+    if (!pop->d_fold_ok[rule])
+        CU(ctx, cudaMalloc(reinterpret_cast<void**>(&pop->d_fold_ok[rule]), (size_t)std::max<int64_t>(f.n_trees, 1)));
+    if (!pop->fold_valid[rule]) {
+        cudaError_t e = launch_fold(f.dtype, rule == 1, pop->d_ftape, pop->d_ctape, pop->d_seg, pop->d_seg_off,
+                                    f.n_trees, pop->d_fold_ok[rule], ctx->stream);
+        if (e != cudaSuccess) return cuda_err(ctx, e, "constant folding");
+        ctx->launches += 1;
+        pop->fold_valid[rule] = true;
+    }
+    *fold_ok = pop->d_fold_ok[rule];
+    return DEX_OK;
+}
+
 int run_eval(dex_ctx* ctx, const dex_population* cpop, const void* X, int32_t F, int64_t N,
              int64_t ldx, void* out, int64_t ldo, uint8_t* ok, int eval_flags, const void* params,
              int32_t n_params, int32_t n_classes, const int32_t* classes, const void* y,
@@ -225,10 +248,10 @@ int run_eval(dex_ctx* ctx, const dex_population* cpop, const void* X, int32_t F,
     a.dtype = h.dtype;
     a.tape = pop->d_ftape;
     a.tape_off = pop->d_ftape_off;
-    if (!h.seg.empty()) { a.ctape = pop->d_ctape; a.seg = pop->d_seg; a.seg_off = pop->d_seg_off; }
-    a.n_trees = h.n_trees;
-    int rc = chunk_table(ctx, pop, (int32_t)n_chunks, &a.chunk_start);
+    int rc = ensure_folded(ctx, pop, 0, &a.fold_ok);
     if (rc) return rc;
+    a.n_trees = h.n_trees;
+    if ((rc = chunk_table(ctx, pop, (int32_t)n_chunks, &a.chunk_start))) return rc;
     a.n_chunks = (int32_t)n_chunks;
     a.max_stack = h.max_stack;
     a.n_param_rows = h.n_param_rows;
@@ -445,6 +468,7 @@ int dex_population_destroy(dex_population* pop) {
         cudaFree(pop->d_const_off); cudaFree(pop->d_const_pos);
         cudaFree(pop->d_ftape); cudaFree(pop->d_ftape_off); cudaFree(pop->d_fconst_pos);
         cudaFree(pop->d_ctape); cudaFree(pop->d_seg); cudaFree(pop->d_seg_off);
+        cudaFree(pop->d_fold_ok[0]); cudaFree(pop->d_fold_ok[1]);
         for (auto& kv : pop->chunk_tables) cudaFree(kv.second);
         for (auto& kv : pop->grad_off_tables) cudaFree(kv.second);
     }
@@ -559,6 +583,7 @@ int dex_population_set_constants(dex_ctx* ctx, dex_population* pop, const void* 
                                      n_values, ctx->stream);
     if (e != cudaSuccess) return cuda_err(ctx, e, "scatter constants");
     ctx->launches += 2;
+    pop->fold_valid[0] = pop->fold_valid[1] = false;   // the folded constants are stale now
     CU(ctx, cudaStreamSynchronize(ctx->stream));  // pinned staging is reused by later calls
     return DEX_OK;
 }
@@ -680,7 +705,7 @@ static int run_grad(dex_ctx* ctx, const dex_population* cpop, const void* X, int
     a.dtype = h.dtype;
     if (folded) {
         a.tape = pop->d_ftape; a.tape_off = pop->d_ftape_off;
-        if (!img.seg.empty()) { a.ctape = pop->d_ctape; a.seg = pop->d_seg; a.seg_off = pop->d_seg_off; }
+        if ((rc = ensure_folded(ctx, pop, 1, &a.fold_ok))) return rc;
     } else {
         a.tape = pop->d_tape; a.tape_off = pop->d_tape_off;
     }

@@ -580,13 +580,14 @@ template <typename T>
 __global__ void transpose_pad_kernel(const T* __restrict__ X, int64_t ldx, int F, int64_t N,
                                      T* __restrict__ XT, int64_t Npad, uint8_t* ok, int64_t n_trees,
                                      Instr* tape, const Instr* ctape, const int64_t* seg,
-                                     const int64_t* seg_off) {
+                                     const int64_t* seg_off, const uint8_t* fold_ok) {
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s < Npad) {
         const T* col = X + (s < N ? s : N - 1) * ldx;
         for (int f = 0; f < F; ++f) XT[(size_t)f * Npad + s] = __ldg(col + f);
     }
-    if (s < n_trees) ok[s] = (!seg_off || fold_tree<T, false>(tape, ctape, seg, seg_off, s)) ? 1 : 0;
+    if (s < n_trees)
+        ok[s] = fold_ok ? fold_ok[s] : ((!seg_off || fold_tree<T, false>(tape, ctape, seg, seg_off, s)) ? 1 : 0);
 }
 
 template <typename T>
@@ -705,11 +706,11 @@ cudaError_t launch_eval(const EvalArgs& e, cudaStream_t stream, int sm_count, in
         if (e.dtype == DEX_F32)
             transpose_pad_kernel<float><<<(unsigned)((cover + 255) / 256), 256, 0, stream>>>(
                 static_cast<const float*>(e.X), e.ldx, e.F, e.N, static_cast<float*>(e.xt), Npad, e.ok, e.n_trees,
-                const_cast<Instr*>(e.tape), e.ctape, e.seg, e.seg_off);
+                const_cast<Instr*>(e.tape), e.ctape, e.seg, e.seg_off, e.fold_ok);
         else
             transpose_pad_kernel<double><<<(unsigned)((cover + 255) / 256), 256, 0, stream>>>(
                 static_cast<const double*>(e.X), e.ldx, e.F, e.N, static_cast<double*>(e.xt), Npad, e.ok, e.n_trees,
-                const_cast<Instr*>(e.tape), e.ctape, e.seg, e.seg_off);
+                const_cast<Instr*>(e.tape), e.ctape, e.seg, e.seg_off, e.fold_ok);
         err = cudaGetLastError();
         if (err != cudaSuccess) return err;
         if (launches) *launches += 1;
@@ -721,6 +722,27 @@ cudaError_t launch_eval(const EvalArgs& e, cudaStream_t stream, int sm_count, in
                              : launch_typed<double, EVAL_U>(k, stream, threads, smem, n_tiles);
     if (err == cudaSuccess && launches) *launches += 1;
     return err;
+}
+
+template <typename T, bool GRAD>
+__global__ void fold_kernel(Instr* tape, const Instr* ctape, const int64_t* seg, const int64_t* seg_off,
+                            int64_t n_trees, uint8_t* fold_ok) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n_trees) fold_ok[t] = fold_tree<T, GRAD>(tape, ctape, seg, seg_off, t) ? 1 : 0;
+}
+
+cudaError_t launch_fold(int dtype, bool grad_rule, Instr* tape, const Instr* ctape, const int64_t* seg,
+                        const int64_t* seg_off, int64_t n_trees, uint8_t* fold_ok, cudaStream_t stream) {
+    if (n_trees == 0) return cudaSuccess;
+    const unsigned blocks = (unsigned)((n_trees + 63) / 64);
+    if (dtype == DEX_F32) {
+        if (grad_rule) fold_kernel<float, true><<<blocks, 64, 0, stream>>>(tape, ctape, seg, seg_off, n_trees, fold_ok);
+        else fold_kernel<float, false><<<blocks, 64, 0, stream>>>(tape, ctape, seg, seg_off, n_trees, fold_ok);
+    } else {
+        if (grad_rule) fold_kernel<double, true><<<blocks, 64, 0, stream>>>(tape, ctape, seg, seg_off, n_trees, fold_ok);
+        else fold_kernel<double, false><<<blocks, 64, 0, stream>>>(tape, ctape, seg, seg_off, n_trees, fold_ok);
+    }
+    return cudaGetLastError();
 }
 
 cudaError_t launch_scatter_constants(int dtype, Instr* tape, Instr* scalar_tape, const int64_t* pos,

@@ -752,13 +752,14 @@ template <typename T>
 __global__ void gtranspose_pad_kernel(const T* __restrict__ X, int64_t ldx, int F, int64_t N,
                                       T* __restrict__ XT, int64_t Npad, uint8_t* ok, int64_t n_trees,
                                       Instr* tape, const Instr* ctape, const int64_t* seg,
-                                      const int64_t* seg_off) {
+                                      const int64_t* seg_off, const uint8_t* fold_ok) {
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s < Npad) {
         const T* col = X + (s < N ? s : N - 1) * ldx;
         for (int f = 0; f < F; ++f) XT[(size_t)f * Npad + s] = __ldg(col + f);
     }
-    if (s < n_trees) ok[s] = (!seg_off || fold_tree<T, true>(tape, ctape, seg, seg_off, s)) ? 1 : 0;
+    if (s < n_trees)
+        ok[s] = fold_ok ? fold_ok[s] : ((!seg_off || fold_tree<T, true>(tape, ctape, seg, seg_off, s)) ? 1 : 0);
 }
 
 constexpr size_t G_SMEM_LIMIT = 227 * 1024;
@@ -883,11 +884,11 @@ cudaError_t launch_grad_ex(const GradArgs& g, const int32_t* chunk_start, int n_
     if (g.dtype == DEX_F32)
         gtranspose_pad_kernel<float><<<(unsigned)((cover + 255) / 256), 256, 0, stream>>>(
             static_cast<const float*>(g.X), g.ldx, g.F, g.N, static_cast<float*>(g.xt), Npad, g.ok, g.n_trees,
-            const_cast<Instr*>(g.tape), g.ctape, g.seg, g.seg_off);
+            const_cast<Instr*>(g.tape), g.ctape, g.seg, g.seg_off, g.fold_ok);
     else
         gtranspose_pad_kernel<double><<<(unsigned)((cover + 255) / 256), 256, 0, stream>>>(
             static_cast<const double*>(g.X), g.ldx, g.F, g.N, static_cast<double*>(g.xt), Npad, g.ok, g.n_trees,
-            const_cast<Instr*>(g.tape), g.ctape, g.seg, g.seg_off);
+            const_cast<Instr*>(g.tape), g.ctape, g.seg, g.seg_off, g.fold_ok);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return err;
     if (launches) *launches += 1;

@@ -17,6 +17,9 @@ struct EvalArgs {
     const Instr* ctape;         // device
     const int64_t* seg;         // device, 3 per folded subtree: ctape begin, end, target in `tape`
     const int64_t* seg_off;     // device, n_trees + 1
+    // folding already done for the current constants (launch_fold): per-tree outcome; when set,
+    // the prepass copies it into ok[] instead of running the scalar tape
+    const uint8_t* fold_ok;
     int64_t n_trees;
     const int32_t* chunk_start; // device, n_chunks + 1 (tree index ranges, balanced by tape length)
     int32_t n_chunks;
@@ -62,6 +65,7 @@ struct GradArgs {
     const Instr* ctape;
     const int64_t* seg;
     const int64_t* seg_off;
+    const uint8_t* fold_ok;     // as in EvalArgs (gradient rule)
     const int32_t* const_ord;   // device, per tape instruction: tree-local constant ordinal or -1
     const int64_t* const_off;   // device, n_trees + 1 (constant ordinal base per tree)
     int64_t n_trees;
@@ -94,6 +98,12 @@ cudaError_t launch_loss_grad_reduce(const double* partial, int64_t n_tiles, int6
                                     double inv_n, const double* wsum, double* loss, double* grad,
                                     cudaStream_t stream);
 cudaError_t launch_weight_sum(int dtype, const void* w, int64_t n, double* out, cudaStream_t stream);
+
+// Runs the scalar tape of every tree once (one thread per tree): stores the folded constants into
+// `tape` and the per-tree outcome into fold_ok.  grad_rule: dex_fold.cuh.  The result stays valid
+// until the constants change.
+cudaError_t launch_fold(int dtype, bool grad_rule, Instr* tape, const Instr* ctape, const int64_t* seg,
+                        const int64_t* seg_off, int64_t n_trees, uint8_t* fold_ok, cudaStream_t stream);
 
 // tiny helpers
 // pos[i] >= 0: tape[pos[i]]; pos[i] < 0: scalar_tape[-(1 + pos[i])] (folded image)
