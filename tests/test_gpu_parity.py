@@ -532,6 +532,47 @@ def test_random_trees_with_ternary_operators_value_and_gradient(dtype, oracle):
             assert n_checked > 20
 
 
+def test_native_float32_handlers_are_accurate_to_a_few_ulp():
+    """The specialised Float32 handlers of the generated PTX loops (default early_exit=True path)
+    against float64 numpy on inputs where every result is finite: a few ulp, not just the 1e-4 of
+    the population tests.  (test_every_builtin_operator runs early_exit=False = the C++ handlers.)"""
+    rng = np.random.default_rng(99)
+    n = 4096
+    pos = np.exp(rng.uniform(-80.0, 80.0, n)).astype(np.float32)            # wide-range positive
+    sgn = (rng.standard_normal(n) * 10.0).astype(np.float32)
+    small = rng.uniform(-80.0, 80.0, n).astype(np.float32)
+    unary = {
+        "log": (pos, np.log), "safe_log": (pos, np.log), "sqrt": (pos, np.sqrt), "safe_sqrt": (pos, np.sqrt),
+        "inv": (pos, lambda x: 1.0 / x), "exp": (small, np.exp), "sin": (sgn * 50, np.sin), "cos": (sgn * 50, np.cos),
+        "abs": (sgn, np.abs), "neg": (sgn, np.negative), "square": (sgn, np.square), "cube": (sgn, lambda x: x ** 3),
+        "relu": (sgn, lambda x: np.maximum(x, 0.0)),
+    }
+    N_ = dexb200.Node
+    for name, (x, f) in unary.items():
+        ops = dexb200.OperatorEnum({1: (name,), 2: ("*",)})
+        X = np.stack([x, np.ones_like(x)])
+        for form, tree in (("R", N_(1, N_(feature=1))), ("A", N_(1, N_(1, N_(feature=1), N_(feature=2))))):
+            y, ok = dexb200.eval_tree_array(tree, X, ops)
+            want = f(x.astype(np.float64))
+            assert ok, (name, form)
+            np.testing.assert_allclose(y, want, rtol=4e-7, atol=1e-37, err_msg=f"{name}/{form}")
+    a = (rng.standard_normal(n) * 100).astype(np.float32)
+    b = np.where(rng.random(n) < 0.5, -1, 1).astype(np.float32) * np.exp(rng.uniform(-20, 20, n)).astype(np.float32)
+    binary = {"+": np.add, "-": np.subtract, "*": np.multiply, "/": np.divide, "max": np.maximum, "min": np.minimum}
+    for name, f in binary.items():
+        ops = dexb200.OperatorEnum({2: (name, "*")})
+        X = np.stack([a, b, np.ones_like(a)])
+        x1, x2, x3 = (N_(feature=k) for k in (1, 2, 3))
+        forms = {"RR": N_(1, x1, x2), "AR": N_(1, N_(2, x1, x3), x2), "RA": N_(1, x1, N_(2, x2, x3)),
+                 "RC": N_(1, x1, N_(val=2.5)), "CR": N_(1, N_(val=2.5), x2)}
+        for form, tree in forms.items():
+            y, ok = dexb200.eval_tree_array(tree, X, ops)
+            lhs = np.full(n, 2.5) if form == "CR" else a.astype(np.float64)
+            rhs = np.full(n, 2.5) if form == "RC" else b.astype(np.float64)
+            assert ok, (name, form)
+            np.testing.assert_allclose(y, f(lhs, rhs), rtol=2e-7, atol=1e-37, err_msg=f"{name}/{form}")
+
+
 def test_set_constants_equals_repack(oracle):
     ops = dexb200.OperatorEnum(treegen.OPSET_A)
     nodes, offsets = treegen.gen_population(80, 6, 2, 4, 3, seed=41)
