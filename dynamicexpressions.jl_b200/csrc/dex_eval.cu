@@ -603,15 +603,6 @@ __global__ void scatter_constants_kernel(Instr* tape, Instr* scalar_tape, const 
     if (dst) { dst->c_lo = lo; dst->c_hi = hi; }
 }
 
-__global__ void loss_reduce_kernel(const double* partial, int64_t n_tiles, int64_t n_trees,
-                                   double denom_inv, double* loss) {
-    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_trees) return;
-    double s = 0.0;
-    for (int64_t i = 0; i < n_tiles; ++i) s += partial[i * n_trees + t];
-    loss[t] = s * denom_inv;
-}
-
 constexpr size_t SMEM_LIMIT = 227 * 1024;
 
 template <typename T, int U>
@@ -753,13 +744,6 @@ cudaError_t launch_scatter_constants(int dtype, Instr* tape, Instr* scalar_tape,
         scatter_constants_kernel<float><<<blocks, 256, 0, stream>>>(tape, scalar_tape, pos, static_cast<const float*>(values), n);
     else
         scatter_constants_kernel<double><<<blocks, 256, 0, stream>>>(tape, scalar_tape, pos, static_cast<const double*>(values), n);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_loss_reduce(const double* partial, int64_t n_tiles, int64_t n_trees,
-                               double denom_inv, double* loss, cudaStream_t stream) {
-    if (n_trees == 0) return cudaSuccess;
-    loss_reduce_kernel<<<(unsigned)((n_trees + 255) / 256), 256, 0, stream>>>(partial, n_tiles, n_trees, denom_inv, loss);
     return cudaGetLastError();
 }
 

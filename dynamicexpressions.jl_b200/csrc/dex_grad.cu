@@ -41,6 +41,13 @@
 // non-finite), so derivatives are checked once, at the root; values are checked at every
 // node.  eval_diff never checks (:68-85) and takes the GEN class everywhere, so that its
 // non-finite patterns are those of the reference's arithmetic.
+//
+// The C++ `step` below is the complete form of one tape instruction (all operators, both element
+// types).  For Float32 the instruction loop of the 256- and 128-thread launches is the generated
+// inline-PTX block of gen_grad_ptx.py (jump tables, in-place register updates, stage 2 inlined
+// per operand-kind variant); it hands instructions without a native code path to `step`.
+// Kernel modes (KM_*): gradient blocks stored, eval_diff, or the fused loss + gradient of the
+// loss whose reduction replaces the stores.
 #include "dex_kernels.h"
 #include "dex_ops.cuh"
 #include "dex_fold.cuh"

@@ -109,7 +109,4 @@ cudaError_t launch_fold(int dtype, bool grad_rule, Instr* tape, const Instr* cta
 // pos[i] >= 0: tape[pos[i]]; pos[i] < 0: scalar_tape[-(1 + pos[i])] (folded image)
 cudaError_t launch_scatter_constants(int dtype, Instr* tape, Instr* scalar_tape, const int64_t* pos,
                                      const void* values, int64_t n, cudaStream_t stream);
-cudaError_t launch_loss_reduce(const double* partial, int64_t n_tiles, int64_t n_trees,
-                               double denom_inv, double* loss, cudaStream_t stream);
-
 }  // namespace dex
