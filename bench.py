@@ -78,29 +78,44 @@ class ClockSampler:
         self.stop = threading.Event()
         self.th = threading.Thread(target=self.run, daemon=True)
 
-    def run(self):
-        # NVML in-process (sub-millisecond per sample) so that even a 20-step timed region of a
-        # few milliseconds is sampled many times; nvidia-smi (the recipe's clocks line) as fallback
+    def _nvml_open(self):
+        """NVML is opened BEFORE the timed region starts (it takes tens of milliseconds), so that
+        even a 10 ms region is sampled every 2 ms."""
         try:
             import pynvml
             pynvml.nvmlInit()
-            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
-            mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
-            R = {"hw_slowdown": pynvml.nvmlClocksThrottleReasonHwSlowdown,
-                 "hw_thermal_slowdown": pynvml.nvmlClocksThrottleReasonHwThermalSlowdown,
-                 "sw_thermal_slowdown": pynvml.nvmlClocksThrottleReasonSwThermalSlowdown,
-                 "sw_power_cap": pynvml.nvmlClocksThrottleReasonSwPowerCap}
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self._mx = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+            self._R = {"hw_slowdown": pynvml.nvmlClocksThrottleReasonHwSlowdown,
+                       "hw_thermal_slowdown": pynvml.nvmlClocksThrottleReasonHwThermalSlowdown,
+                       "sw_thermal_slowdown": pynvml.nvmlClocksThrottleReasonSwThermalSlowdown,
+                       "sw_power_cap": pynvml.nvmlClocksThrottleReasonSwPowerCap}
+            self._nvml_sample()
+            return True
+        except Exception:
+            self._nv = None
+            return False
+
+    def _nvml_sample(self):
+        nv, h = self._nv, self._h
+        sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+        mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        row = [str(self.index), str(sm), str(self._mx), "", ""]
+        row += ["Active" if (mask & self._R[nm]) else "Not Active"
+                for nm in ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")]
+        self.rows.append(row)
+
+    def run(self):
+        # NVML in-process (sub-millisecond per sample); nvidia-smi (the recipe's clocks line) as fallback
+        if getattr(self, "_nv", None) is not None:
             while not self.stop.is_set():
-                sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
-                mask = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                row = [str(self.index), str(sm), str(mx), "", ""]
-                row += ["Active" if (mask & R[nm]) else "Not Active"
-                        for nm in ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")]
-                self.rows.append(row)
+                try:
+                    self._nvml_sample()
+                except Exception:
+                    break
                 self.stop.wait(0.002)
             return
-        except Exception:
-            pass
         while not self.stop.is_set():
             try:
                 o = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
@@ -113,6 +128,7 @@ class ClockSampler:
             self.stop.wait(0.1)
 
     def __enter__(self):
+        self._nvml_open()
         self.th.start()
         return self
 
