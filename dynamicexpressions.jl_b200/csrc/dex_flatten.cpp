@@ -10,7 +10,9 @@
 
 #include <algorithm>
 #include <cstring>
+#include <cstdlib>
 #include <limits>
+#include <thread>
 
 #include "../../include/dexb200.h"
 
@@ -562,6 +564,27 @@ struct Flattener {
     bool elide = true;
 
     int run(const dex_node* nodes, const int64_t* offsets, int64_t n_trees) {
+        if (int rc = run_trees(nodes, offsets, n_trees)) return rc;
+        return finish(out, rebase, err);
+    }
+
+    // the per-tree part: everything except the final row rebasing, which needs the stack depth
+    // of the WHOLE population (so that partial results of several threads can be merged first)
+    int run_trees(const dex_node* nodes, const int64_t* offsets, int64_t n_trees) {
+        {   // one allocation per array instead of a growth series (a tape has at most one
+            // instruction per node; about half of the nodes are leaves)
+            const size_t nn = n_trees > 0 ? (size_t)(offsets[n_trees] - offsets[0]) : 0;
+            out.tape.reserve(nn);
+            out.tape_const_ord.reserve(nn);
+            rebase.reserve(nn);
+            out.const_pos.reserve(nn / 2 + 16);
+            out.tape_off.reserve((size_t)n_trees + 1);
+            out.const_off.reserve((size_t)n_trees + 1);
+            out.seg_off.reserve((size_t)n_trees + 1);
+            out.n_nodes_tree.reserve((size_t)n_trees);
+            out.n_const_tree.reserve((size_t)n_trees);
+            cur.reserve(256);
+        }
         out.tape_off.assign(1, 0);
         out.const_off.assign(1, 0);
         out.seg_off.assign(1, 0);
@@ -605,13 +628,20 @@ struct Flattener {
             out.const_off.push_back(out.n_constants);
             out.tape_off.push_back((int64_t)out.tape.size());
         }
+        out.n_trees = n_trees;
+        return DEX_OK;
+    }
+
+    static int finish(PackedPopulation& out, const std::vector<uint8_t>& rebase, std::string& err) {
         // row layout: [0, max_stack) operand stack, then one row per parameter, then the features
         out.n_param_rows = out.max_parameter + 1;
         const uint32_t pbase = (uint32_t)out.max_stack;
         const uint32_t base = pbase + (uint32_t)out.n_param_rows;
-        if (out.max_feature >= 0 && (int64_t)out.max_feature + base > MAX_ROWS)
-            return fail(DEX_ERR_UNSUPPORTED, "feature index " + std::to_string(out.max_feature) +
-                                                 " + stack rows exceed the device row limit " + std::to_string(MAX_ROWS));
+        if (out.max_feature >= 0 && (int64_t)out.max_feature + base > MAX_ROWS) {
+            err = "feature index " + std::to_string(out.max_feature) + " + stack rows exceed the device row limit " +
+                  std::to_string(MAX_ROWS);
+            return DEX_ERR_UNSUPPORTED;
+        }
         for (size_t k = 0; k < out.tape.size(); ++k) {
             Instr& ins = out.tape[k];
             uint32_t ra = row_a(ins.w1), rb = row_b(ins.w1);
@@ -621,29 +651,125 @@ struct Flattener {
             if (rebase[k] & 8) rb += pbase;
             ins.w1 = ra | (rb << 16);
         }
-        out.n_trees = n_trees;
         return DEX_OK;
     }
 };
+
+// appends the partial result `p` (trees [t0, t1) flattened on their own) to `out`
+void append_part(PackedPopulation& out, std::vector<uint8_t>& rebase, const PackedPopulation& p,
+                 const std::vector<uint8_t>& p_rebase) {
+    const int64_t tape_base = (int64_t)out.tape.size(), ctape_base = (int64_t)out.ctape.size();
+    const int64_t seg_base = (int64_t)out.seg.size() / 3, const_base = out.n_constants;
+    out.tape.insert(out.tape.end(), p.tape.begin(), p.tape.end());
+    rebase.insert(rebase.end(), p_rebase.begin(), p_rebase.end());
+    out.tape_const_ord.insert(out.tape_const_ord.end(), p.tape_const_ord.begin(), p.tape_const_ord.end());
+    out.n_nodes_tree.insert(out.n_nodes_tree.end(), p.n_nodes_tree.begin(), p.n_nodes_tree.end());
+    out.n_const_tree.insert(out.n_const_tree.end(), p.n_const_tree.begin(), p.n_const_tree.end());
+    for (size_t k = 1; k < p.tape_off.size(); ++k) out.tape_off.push_back(p.tape_off[k] + tape_base);
+    for (size_t k = 1; k < p.const_off.size(); ++k) out.const_off.push_back(p.const_off[k] + const_base);
+    for (size_t k = 1; k < p.seg_off.size(); ++k) out.seg_off.push_back(p.seg_off[k] + seg_base);
+    for (int64_t v : p.const_pos) out.const_pos.push_back(v >= 0 ? v + tape_base : v - ctape_base);
+    out.ctape.insert(out.ctape.end(), p.ctape.begin(), p.ctape.end());
+    for (size_t k = 0; k + 2 < p.seg.size(); k += 3) {
+        out.seg.push_back(p.seg[k] + ctape_base);
+        out.seg.push_back(p.seg[k + 1] + ctape_base);
+        out.seg.push_back(p.seg[k + 2] >= 0 ? p.seg[k + 2] + tape_base : p.seg[k + 2]);
+    }
+    out.n_trees += p.n_trees;
+    out.n_nodes += p.n_nodes;
+    out.n_constants += p.n_constants;
+    out.n_generic += p.n_generic;
+    out.n_checks += p.n_checks;
+    out.max_stack = std::max(out.max_stack, p.max_stack);
+    out.max_feature = std::max(out.max_feature, p.max_feature);
+    out.max_parameter = std::max(out.max_parameter, p.max_parameter);
+}
+
+// One image (unfolded or folded) of the population.  Trees are independent, so large
+// populations are flattened by several threads over contiguous tree ranges (balanced by node
+// count) and the partial tapes concatenated; a failing range is redone serially so that the
+// error message names the tree exactly as the one-thread walk would.
+int flatten_image(const OpTable& ops, const dex_node* nodes, const int64_t* offsets, int64_t n_trees, int dtype,
+                  int pack_flags, bool fold, int nthreads, PackedPopulation& out, std::string& err) {
+    out = PackedPopulation();
+    out.dtype = dtype;
+    out.pack_flags = pack_flags;
+    const int64_t total_nodes = n_trees > 0 ? offsets[n_trees] - offsets[0] : 0;
+    nthreads = (int)std::min<int64_t>(nthreads, std::max<int64_t>(1, total_nodes / 2048));
+    if (nthreads <= 1) {
+        Flattener f(ops, dtype, pack_flags, fold, out, err);
+        return f.run(nodes, offsets, n_trees);
+    }
+    struct Part {
+        PackedPopulation pop;
+        std::vector<uint8_t> rebase;
+        std::string err;
+        int rc = DEX_OK;
+        int64_t t0 = 0, t1 = 0;
+    };
+    std::vector<Part> parts((size_t)nthreads);
+    {   // contiguous ranges with about total_nodes / nthreads records each
+        int64_t t = 0;
+        for (int k = 0; k < nthreads; ++k) {
+            parts[(size_t)k].t0 = t;
+            const int64_t goal = offsets[0] + total_nodes * (k + 1) / nthreads;
+            while (t < n_trees && (offsets[t + 1] <= goal || k == nthreads - 1)) ++t;
+            parts[(size_t)k].t1 = t;
+        }
+        parts.back().t1 = n_trees;
+    }
+    std::vector<std::thread> workers;
+    for (Part& p : parts) {
+        workers.emplace_back([&ops, nodes, offsets, dtype, pack_flags, fold, &p]() {
+            p.pop.dtype = dtype;
+            p.pop.pack_flags = pack_flags;
+            Flattener f(ops, dtype, pack_flags, fold, p.pop, p.err);
+            p.rc = f.run_trees(nodes, offsets + p.t0, p.t1 - p.t0);
+            p.rebase.swap(f.rebase);
+        });
+    }
+    for (std::thread& w : workers) w.join();
+    for (const Part& p : parts)
+        if (p.rc != DEX_OK) {   // exact message (global tree index): the one-thread walk
+            out = PackedPopulation();
+            out.dtype = dtype;
+            out.pack_flags = pack_flags;
+            Flattener f(ops, dtype, pack_flags, fold, out, err);
+            return f.run(nodes, offsets, n_trees);
+        }
+    std::vector<uint8_t> rebase;
+    out.tape_off.assign(1, 0);
+    out.const_off.assign(1, 0);
+    out.seg_off.assign(1, 0);
+    for (const Part& p : parts) append_part(out, rebase, p.pop, p.rebase);
+    return Flattener::finish(out, rebase, err);
+}
 
 }  // namespace
 
 int flatten_population(const OpTable& ops, const void* nodes, const int64_t* offsets,
                        int64_t n_trees, int dtype, int pack_flags, PackedPopulation& out,
                        std::string& err) {
-    out = PackedPopulation();
-    out.dtype = dtype;
-    out.pack_flags = pack_flags;
-    Flattener f(ops, dtype, pack_flags, false, out, err);
-    int rc = f.run(reinterpret_cast<const dex_node*>(nodes), offsets, n_trees);
-    if (rc) return rc;
-    // second image for evaluation: constant subtrees folded into the scalar tape
+    int nthreads = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u);
+    if (const char* env = getenv("DEXB200_PACK_THREADS")) nthreads = std::max(1, atoi(env));
+    const dex_node* nd = reinterpret_cast<const dex_node*>(nodes);
+    // second image for evaluation: constant subtrees folded into the scalar tape.  The two images
+    // are independent: the folded one is built by its own thread (group) at the same time.
     auto folded = std::make_shared<PackedPopulation>();
-    folded->dtype = dtype;
-    folded->pack_flags = pack_flags;
-    Flattener g(ops, dtype, pack_flags, true, *folded, err);
-    rc = g.run(reinterpret_cast<const dex_node*>(nodes), offsets, n_trees);
-    if (rc) return rc;
+    std::string err2;
+    int rc2 = DEX_OK;
+    const int half = std::max(1, nthreads / 2);
+    if (nthreads > 1) {
+        std::thread second([&]() { rc2 = flatten_image(ops, nd, offsets, n_trees, dtype, pack_flags, true, half, *folded, err2); });
+        const int rc = flatten_image(ops, nd, offsets, n_trees, dtype, pack_flags, false, half, out, err);
+        second.join();
+        if (rc) return rc;
+    } else {
+        const int rc = flatten_image(ops, nd, offsets, n_trees, dtype, pack_flags, false, 1, out, err);
+        if (rc) return rc;
+        rc2 = flatten_image(ops, nd, offsets, n_trees, dtype, pack_flags, true, 1, *folded, err2);
+    }
+    if (rc2) { err = err2; return rc2; }
     out.folded = folded;
     return DEX_OK;
 }

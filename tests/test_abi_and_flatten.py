@@ -213,6 +213,47 @@ def _random_wire(rng, ops, F, max_nodes):
     return dexb200.to_wire(t)
 
 
+def test_parallel_flattening_equals_the_one_thread_walk(monkeypatch):
+    """Large populations are flattened by several threads over tree ranges and the partial tapes
+    merged (csrc/dex_flatten.cpp flatten_image): every array of both images must be identical to
+    the one-thread result, including constant positions (checked through a constants round trip)
+    and the error message of a malformed tree."""
+    spec = {1: ("cos", "exp", "abs"), 2: ("+", "-", "*", "/"), 3: ("fma", "clamp")}
+    ops = dexb200.OperatorEnum(spec)
+    rng = np.random.default_rng(5)
+    wires = [_random_wire(rng, ops, 6, max_nodes=int(rng.integers(1, 50))) for _ in range(1500)]
+    nodes = np.concatenate(wires)
+    offsets = np.concatenate([[0], np.cumsum([len(w) for w in wires])]).astype(np.int64)
+    hctx = D.host_context()
+    images = {}
+    for thr in ("1", "3", "8"):
+        monkeypatch.setenv("DEXB200_PACK_THREADS", thr)
+        pop = D.Population(None, ops, np.float64, ctx=hctx, wire=(nodes, offsets))
+        ins, off = pop.tape()
+        c = pop.get_constants()
+        pop.set_constants(c * 2.0 + 1.0)                      # exercises const_pos of both images
+        ins2, _ = pop.tape()
+        images[thr] = (ins, off, pop.folded(), c, dict(pop.info), ins2, pop.constant_counts())
+    a = images["1"]
+    for thr, b in images.items():
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[3].tobytes() == b[3].tobytes(), thr
+        assert a[4] == b[4] and np.array_equal(a[5], b[5]) and np.array_equal(a[6], b[6]), thr
+        for k in a[2]:
+            assert np.array_equal(a[2][k], b[2][k]), (thr, k)
+    # a malformed tree in the middle: same error (with the global tree index) for any thread count
+    bad = nodes.copy()
+    t_bad = 777
+    bad["op"][offsets[t_bad]] = 200 if bad["degree"][offsets[t_bad]] > 0 else bad["op"][offsets[t_bad]]
+    bad["degree"][offsets[t_bad]] = max(bad["degree"][offsets[t_bad]], 1)
+    msgs = []
+    for thr in ("1", "8"):
+        monkeypatch.setenv("DEXB200_PACK_THREADS", thr)
+        with pytest.raises(D.DexError) as ei:
+            D.Population(None, ops, np.float64, ctx=hctx, wire=(bad, offsets))
+        msgs.append(str(ei.value))
+    assert msgs[0] == msgs[1] and str(t_bad) in msgs[0], msgs
+
+
 def test_stack_need_uses_sethi_ullman_order():
     """A right-deep tree needs no more stack rows than its left-deep mirror."""
     hctx = D.host_context()
