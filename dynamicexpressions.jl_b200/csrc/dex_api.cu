@@ -9,6 +9,7 @@
 #include <map>
 #include <new>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/dexb200.h"
@@ -59,6 +60,9 @@ struct dex_population {
     int64_t* d_seg_off = nullptr;
     // outcome of the constant folding for the CURRENT constants, per rule (0 = evaluation,
     // 1 = gradient): computed by launch_fold on first use, invalidated when constants change
+    // all device arrays above live in ONE allocation (eleven cudaMalloc/cudaFree pairs per packed
+    // population cost more than flattening it): d_blob owns, the typed pointers are views
+    void* d_blob = nullptr;
     uint8_t* d_fold_ok[2] = {nullptr, nullptr};
     bool fold_valid[2] = {false, false};
     std::map<int32_t, int32_t*> chunk_tables;  // n_chunks -> device table
@@ -150,6 +154,45 @@ int upload(dex_ctx* ctx, U** dptr, const std::vector<U>& v) {
     const size_t bytes = (std::max<size_t>(v.size(), 1) + 64) * sizeof(U);
     CU(ctx, cudaMalloc(reinterpret_cast<void**>(dptr), bytes));
     if (!v.empty()) CU(ctx, cudaMemcpyAsync(*dptr, v.data(), v.size() * sizeof(U), cudaMemcpyHostToDevice, ctx->stream));
+    return DEX_OK;
+}
+
+// Every device array of a packed population in one allocation.  Each array keeps the 64 elements
+// of slack behind its last entry that the interpreters rely on (tape line prefetch, offsets read
+// one tree ahead) and starts on a 256-byte boundary.
+int upload_population(dex_ctx* ctx, dex_population* pop) {
+    const PackedPopulation& h = pop->h;
+    const PackedPopulation& f = *h.folded;
+    struct Item { void** dst; const void* src; size_t bytes, padded, off; };
+    std::vector<Item> items;
+    size_t total = 0;
+    auto add = [&](auto** dptr, const auto& vec) {
+        using U = typename std::remove_reference<decltype(vec)>::type::value_type;
+        Item it;
+        it.dst = reinterpret_cast<void**>(dptr);
+        it.src = vec.data();
+        it.bytes = vec.size() * sizeof(U);
+        it.padded = (((std::max<size_t>(vec.size(), 1) + 64) * sizeof(U)) + 255) & ~(size_t)255;
+        it.off = total;
+        total += it.padded;
+        items.push_back(it);
+    };
+    add(&pop->d_tape, h.tape);
+    add(&pop->d_tape_off, h.tape_off);
+    add(&pop->d_const_ord, h.tape_const_ord);
+    add(&pop->d_const_off, h.const_off);
+    add(&pop->d_const_pos, h.const_pos);
+    add(&pop->d_ftape, f.tape);
+    add(&pop->d_ftape_off, f.tape_off);
+    add(&pop->d_fconst_pos, f.const_pos);
+    add(&pop->d_ctape, f.ctape);
+    add(&pop->d_seg, f.seg);
+    add(&pop->d_seg_off, f.seg_off);
+    CU(ctx, cudaMalloc(&pop->d_blob, total));
+    for (const Item& it : items) {
+        *it.dst = static_cast<char*>(pop->d_blob) + it.off;
+        if (it.bytes) CU(ctx, cudaMemcpyAsync(*it.dst, it.src, it.bytes, cudaMemcpyHostToDevice, ctx->stream));
+    }
     return DEX_OK;
 }
 
@@ -441,18 +484,7 @@ int dex_population_pack(dex_ctx* ctx, const dex_optable* ops, const dex_node* no
     pop->device = ctx->device;
     if (ctx->device >= 0) {
         rc = ensure_device(ctx);
-        if (!rc) rc = upload(ctx, &pop->d_tape, pop->h.tape);
-        if (!rc) rc = upload(ctx, &pop->d_tape_off, pop->h.tape_off);
-        if (!rc) rc = upload(ctx, &pop->d_const_ord, pop->h.tape_const_ord);
-        if (!rc) rc = upload(ctx, &pop->d_const_off, pop->h.const_off);
-        if (!rc) rc = upload(ctx, &pop->d_const_pos, pop->h.const_pos);
-        const PackedPopulation& f = *pop->h.folded;
-        if (!rc) rc = upload(ctx, &pop->d_ftape, f.tape);
-        if (!rc) rc = upload(ctx, &pop->d_ftape_off, f.tape_off);
-        if (!rc) rc = upload(ctx, &pop->d_fconst_pos, f.const_pos);
-        if (!rc) rc = upload(ctx, &pop->d_ctape, f.ctape);
-        if (!rc) rc = upload(ctx, &pop->d_seg, f.seg);
-        if (!rc) rc = upload(ctx, &pop->d_seg_off, f.seg_off);
+        if (!rc) rc = upload_population(ctx, pop);
         if (!rc && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = set_err(ctx, DEX_ERR_CUDA, "tape upload failed");
         if (rc) { dex_population_destroy(pop); return rc; }
     }
@@ -464,10 +496,7 @@ int dex_population_destroy(dex_population* pop) {
     if (!pop) return DEX_OK;
     if (pop->device >= 0) {
         cudaSetDevice(pop->device);
-        cudaFree(pop->d_tape); cudaFree(pop->d_tape_off); cudaFree(pop->d_const_ord);
-        cudaFree(pop->d_const_off); cudaFree(pop->d_const_pos);
-        cudaFree(pop->d_ftape); cudaFree(pop->d_ftape_off); cudaFree(pop->d_fconst_pos);
-        cudaFree(pop->d_ctape); cudaFree(pop->d_seg); cudaFree(pop->d_seg_off);
+        cudaFree(pop->d_blob);
         cudaFree(pop->d_fold_ok[0]); cudaFree(pop->d_fold_ok[1]);
         for (auto& kv : pop->chunk_tables) cudaFree(kv.second);
         for (auto& kv : pop->grad_off_tables) cudaFree(kv.second);
