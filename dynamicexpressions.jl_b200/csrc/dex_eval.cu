@@ -114,8 +114,8 @@ template <int K> struct VOp2<DEX_OP_MUL, float, K> {
         for (int k = 0; k < K; k += 2) { const float2 r = __fmul2_rn(f2(x + k), f2(y + k)); out[k] = r.x; out[k + 1] = r.y; }
     }
 };
-// packed sin/cos: the same algorithm as fast_sincosf (dex_ops.cuh) on pairs; rint() by the
-// 1.5*2^23 magic-number add (exact for |x * 2/pi| < 2^22), quadrant from the low mantissa bits.
+// packed sin/cos: the same algorithm as fast_sincosf (dex_ops.cuh) on pairs, operation for
+// operation (bit-identical results).
 template <int QADD, int K> __device__ __forceinline__ void sincos_packed(float* out, const float* x) {
     float big = 0.f;
 #pragma unroll
@@ -125,27 +125,32 @@ template <int QADD, int K> __device__ __forceinline__ void sincos_packed(float* 
         for (int k = 0; k < K; ++k) out[k] = QADD ? m_cos(x[k]) : m_sin(x[k]);
         return;
     }
-    const float2 MAGIC = make_float2(12582912.0f, 12582912.0f);
+    const float2 MAGIC = make_float2(12582912.0f, 12582912.0f), NMAGIC = make_float2(-12582912.0f, -12582912.0f);
+    const float2 INVPI = make_float2(0.318309886183790672f, 0.318309886183790672f);
 #pragma unroll
     for (int k = 0; k < K; k += 2) {
         const float2 xx = f2(x + k);
-        const float2 m = __ffma2_rn(xx, make_float2(0.636619772367581343f, 0.636619772367581343f), MAGIC);
-        const float2 j = __fadd2_rn(m, make_float2(-12582912.0f, -12582912.0f));
-        const float2 nj = make_float2(-j.x, -j.y);
-        float2 r = __ffma2_rn(nj, make_float2(1.5707962513e+00f, 1.5707962513e+00f), xx);
-        r = __ffma2_rn(nj, make_float2(7.5497894159e-08f, 7.5497894159e-08f), r);
-        r = __ffma2_rn(nj, make_float2(5.3903029534e-15f, 5.3903029534e-15f), r);
+        float2 m, q;
+        if (QADD) {
+            const float2 u = __ffma2_rn(xx, INVPI, make_float2(-0.5f, -0.5f));
+            m = __fadd2_rn(u, MAGIC);
+            q = __ffma2_rn(__fadd2_rn(m, NMAGIC), make_float2(2.0f, 2.0f), make_float2(1.0f, 1.0f));
+        } else {
+            m = __ffma2_rn(xx, INVPI, MAGIC);
+            const float2 j = __fadd2_rn(m, NMAGIC);
+            q = __fadd2_rn(j, j);
+        }
+        float2 r = __ffma2_rn(q, make_float2(-1.5707962513e+00f, -1.5707962513e+00f), xx);
+        r = __ffma2_rn(q, make_float2(-7.5497894159e-08f, -7.5497894159e-08f), r);
+        r = __ffma2_rn(q, make_float2(-5.3903029534e-15f, -5.3903029534e-15f), r);
         const float2 z = __fmul2_rn(r, r);
-        float2 sp = __ffma2_rn(z, make_float2(-1.9515295891e-4f, -1.9515295891e-4f), make_float2(8.3321608736e-3f, 8.3321608736e-3f));
-        sp = __ffma2_rn(sp, z, make_float2(-1.6666654611e-1f, -1.6666654611e-1f));
+        float2 sp = __ffma2_rn(z, make_float2(0x1.5dbce6p-19f, 0x1.5dbce6p-19f), make_float2(-0x1.9f6feep-13f, -0x1.9f6feep-13f));
+        sp = __ffma2_rn(sp, z, make_float2(0x1.110ed4p-7f, 0x1.110ed4p-7f));
+        sp = __ffma2_rn(sp, z, make_float2(-0x1.55554cp-3f, -0x1.55554cp-3f));
         sp = __ffma2_rn(__fmul2_rn(sp, z), r, r);
-        float2 cp = __ffma2_rn(z, make_float2(2.443315711809948e-5f, 2.443315711809948e-5f), make_float2(-1.388731625493765e-3f, -1.388731625493765e-3f));
-        cp = __ffma2_rn(cp, z, make_float2(4.166664568298827e-2f, 4.166664568298827e-2f));
-        cp = __ffma2_rn(__fmul2_rn(cp, z), z, __ffma2_rn(z, make_float2(-0.5f, -0.5f), make_float2(1.0f, 1.0f)));
-        const int q0 = __float_as_int(m.x) + QADD, q1 = __float_as_int(m.y) + QADD;
-        const float v0 = (q0 & 1) ? cp.x : sp.x, v1 = (q1 & 1) ? cp.y : sp.y;
-        out[k] = __int_as_float(__float_as_int(v0) ^ ((q0 & 2) << 30));
-        out[k + 1] = __int_as_float(__float_as_int(v1) ^ ((q1 & 2) << 30));
+        const unsigned p0 = (__float_as_uint(m.x) & 1u) ^ (QADD ? 1u : 0u), p1 = (__float_as_uint(m.y) & 1u) ^ (QADD ? 1u : 0u);
+        out[k] = __uint_as_float(__float_as_uint(sp.x) ^ (p0 << 31));
+        out[k + 1] = __uint_as_float(__float_as_uint(sp.y) ^ (p1 << 31));
     }
 }
 template <int K> struct VOp1<DEX_OP_SIN, float, K> {

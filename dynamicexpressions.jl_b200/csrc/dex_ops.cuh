@@ -40,8 +40,8 @@ __device__ __forceinline__ double m_fma(double a, double b, double c) { return f
 #undef DEX_M2
 
 // ---- sin / cos ------------------------------------------------------------------------
-// Float32: an inline fast path (three-constant Cody-Waite reduction by pi/2 carried in FMAs,
-// Cephes minimax polynomials on [-pi/4, pi/4]; <= ~1.5 ulp) for |x| <= 105615, and ONE shared
+// Float32: an inline fast path (three-constant Cody-Waite reduction by multiples of pi/2 carried in
+// FMAs, one sine polynomial on [-pi/2, pi/2]; <= 1.83 ulp) for |x| <= 105615, and ONE shared
 // out-of-line call to the CUDA library function (Payne-Hanek reduction) for huge or
 // infinite arguments.  The interpreter unrolls every operator K times per handler; keeping
 // the rare, large slow path out of line keeps the hot loop inside the instruction cache.
@@ -52,25 +52,33 @@ static __device__ __noinline__ double slow_sin(double x) { return sin(x); }
 static __device__ __noinline__ double slow_cos(double x) { return cos(x); }
 
 template <int QADD> __device__ __forceinline__ float fast_sincosf(float x) {
-    // j = rint(x * 2/pi) by the 1.5 * 2^23 magic-number add (exact for |x * 2/pi| < 2^22); the
-    // quadrant is in the low mantissa bits of m.  Must stay bit-identical to sincos_packed
-    // (dex_eval.cu), which evaluates the same formula on pairs with FFMA2.
-    const float m = fmaf(x, 0.636619772367581343f, 12582912.0f);
-    const float j = m - 12582912.0f;
-    const int q = __float_as_int(m) + QADD;
-    float r = fmaf(-j, 1.5707962513e+00f, x);
-    r = fmaf(-j, 7.5497894159e-08f, r);
-    r = fmaf(-j, 5.3903029534e-15f, r);
+    // x = q pi/2 + r with q even (sin: q = 2 rint(x/pi)) or odd (cos: q = 2 rint(x/pi - 1/2) + 1):
+    // r lies in [-pi/2, pi/2] and the result is +-sin(r), the sign being the parity of the rounded
+    // integer (low mantissa bit of the 1.5 * 2^23 magic-number sum, exact for |x/pi| < 2^22).
+    // sin(r) = r + r^3 (s0 + z (s1 + z (s2 + z s3))): own least-squares fit, <= 1.83 ulp against
+    // float64 for |x| <= 105615.  Must stay operation-for-operation identical to the packed forms
+    // (sincos_packed in dex_eval.cu, sincos() in gen_interp_ptx.py): results are bit-identical
+    // whichever code path a sample takes.
+    float m, q;
+    if (QADD) {
+        const float u = fmaf(x, 0.318309886183790672f, -0.5f);
+        m = u + 12582912.0f;
+        q = fmaf(m - 12582912.0f, 2.0f, 1.0f);
+    } else {
+        m = fmaf(x, 0.318309886183790672f, 12582912.0f);
+        const float j = m - 12582912.0f;
+        q = j + j;
+    }
+    float r = fmaf(q, -1.5707962513e+00f, x);
+    r = fmaf(q, -7.5497894159e-08f, r);
+    r = fmaf(q, -5.3903029534e-15f, r);
     const float z = r * r;
-    // sin(r) = r + r z (s2 + z (s1 + z s0)),  cos(r) = 1 - z/2 + z^2 (c2 + z (c1 + z c0))
-    float sp = fmaf(z, -1.9515295891e-4f, 8.3321608736e-3f);
-    sp = fmaf(sp, z, -1.6666654611e-1f);
+    float sp = fmaf(z, 0x1.5dbce6p-19f, -0x1.9f6feep-13f);
+    sp = fmaf(sp, z, 0x1.110ed4p-7f);
+    sp = fmaf(sp, z, -0x1.55554cp-3f);
     sp = fmaf(sp * z, r, r);
-    float cp = fmaf(z, 2.443315711809948e-5f, -1.388731625493765e-3f);
-    cp = fmaf(cp, z, 4.166664568298827e-2f);
-    cp = fmaf(cp * z, z, fmaf(z, -0.5f, 1.0f));
-    float v = (q & 1) ? cp : sp;
-    return (q & 2) ? -v : v;
+    const unsigned par = (__float_as_uint(m) & 1u) ^ (QADD ? 1u : 0u);
+    return __uint_as_float(__float_as_uint(sp) ^ (par << 31));
 }
 __device__ __forceinline__ float m_sin(float x) {
     if (fabsf(x) > 105615.0f) return slow_sinf(x);   // false for NaN: the fast path propagates it

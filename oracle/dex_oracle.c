@@ -94,6 +94,10 @@ int32_t dexo_count_constants(const dex_node* nodes, int64_t n_nodes) {
 static __thread int g_elementwise = 0;
 
 /* ---- instantiate for Float32 and Float64 ------------------------------------ */
+/* see dex_oracle_ops.inc (apply1): test-only conditioning yardstick */
+static int dexo_ulp_nudge = 0;
+void dexo_set_ulp_nudge(int n) { dexo_ulp_nudge = n; }
+
 #define T float
 #define S(name) name##_f32
 #define M(fn) fn##f

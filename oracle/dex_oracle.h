@@ -121,6 +121,9 @@ float dexo_apply_f32(int opcode, float a, float b, float c);
 void dexo_partials_f64(int opcode, double a, double b, double c, double* g);
 int dexo_max_threads(void);
 
+/* TEST-ONLY: move every transcendental unary result by n ulps (0 = off); see dex_oracle_ops.inc */
+void dexo_set_ulp_nudge(int n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -171,6 +171,12 @@ def eval_parametric(wire, opcodes, X, parameters, classes0, flags=DEFAULT_FLAGS)
     return out, bool(ok.value)
 
 
+def set_ulp_nudge(n):
+    """TEST-ONLY conditioning yardstick: move the result of every transcendental unary operator
+    by ``n`` ulps in later evaluations (0 switches it off)."""
+    lib().dexo_set_ulp_nudge(C.c_int(int(n)))
+
+
 def eval_population(nodes, offsets, opcodes, X, flags=DEFAULT_FLAGS, nthreads=0, out=None):
     """(out[P, N], ok[P]); OpenMP over trees when nthreads != 1."""
     F, N, Xc = _prep_X(X)

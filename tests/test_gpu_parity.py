@@ -158,10 +158,18 @@ def _check_population(oracle, nodes, offsets, ops, X, dtype, *, ctx=None, label=
         ref2, _ = oracle.eval_population(nodes, offsets, ops.opcodes, X.astype(np.float64), _oflags(oracle, c))
     else:  # float64: the same algorithm with 80-bit intermediates
         ref2, _ = oracle.eval_population_f80(nodes, offsets, ops.opcodes, X, _oflags(oracle, c))
+    # (c) the oracle with every transcendental result moved by one ulp (oracle.set_ulp_nudge): two
+    # faithful implementations of sin / exp / ... may differ by exactly that, and a pole such as
+    # x3 / (0.997 - sin(x3 + x2)) amplifies it without any sensitivity to X showing in (a)
+    try:
+        oracle.set_ulp_nudge(1)
+        ref_n, _ = oracle.eval_population(nodes, offsets, ops.opcodes, X, _oflags(oracle, c))
+    finally:
+        oracle.set_ulp_nudge(0)
     errs = []
     for t in np.nonzero(rok)[0]:
         err = _relerr(out[t], ref[t])
-        cond = _relerr(ref_p[t], ref[t])
+        cond = max(_relerr(ref_p[t], ref[t]), _relerr(ref_n[t], ref[t]))
         if ref2 is not None:
             cond = max(cond, _relerr(ref[t], ref2[t]))
         if not np.isfinite(cond):
