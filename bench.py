@@ -351,6 +351,22 @@ def main():
                 traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
+        # instruction-issue roofline of the interpreter (SURVEY.md §8d caveat ii): warp instructions
+        # of one launch (ncu, profiles/) at 148 SMs x 4 schedulers x the SM clock sampled above
+        issue = None
+        mpath = os.path.join(ROOT, "profiles", "r01_eval_kernel_ncu_metrics.json")
+        clocks = clk.summary()
+        if os.path.exists(mpath) and clocks.get("sm_mhz"):
+            try:
+                inst = float(json.load(open(mpath))["smsp__inst_executed.sum"]["value"])
+                sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
+                peak = sm_count * 4 * clocks["sm_mhz"] * 1e6
+                issue = {"bound": "issue", "warp_instructions_per_launch": inst,
+                         "peak_warp_instructions_per_s": peak, "ms_at_peak": inst / peak * 1e3,
+                         "frac": (inst / peak * 1e3) / ms_step,
+                         "source": "smsp__inst_executed.sum of profiles/r01_eval_kernel_ncu_metrics.json"}
+            except Exception:
+                issue = None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step_max, "higher_is_better": True,
@@ -375,8 +391,9 @@ def main():
                                "d2h_bytes_per_step": int(loss_host.numel() * 8 + ok_host.numel()),
                                "ms_per_step": float(tl.item()) * 1e3,
                                "entry": "dex_eval_loss (per-tree MSE; the P x N results never leave the SM)"},
+            "issue_roofline": issue,
             "gpu_launches": int(launches),
-            "clocks": clk.summary(),
+            "clocks": clocks,
             "wall_s_timed_region": t_wall,
             "ms_per_step_min": min(ms), "ms_per_step_median": statistics.median(ms),
         }

@@ -437,6 +437,11 @@ __global__ void __launch_bounds__(DEX_GRAD_THREADS, DEX_GRAD_MIN_CTAS) grad_kern
     const int mode = a.mode;
     const bool full_tile = (s0 + TILE <= a.N);
     const int NEVER = -(1 << 20);   // one-hot index that matches no direction
+    // tree-invariant conditions, hoisted out of the tree loop
+    const bool out_vec = !LOSS && full_tile && (a.ldo % C) == 0 && (reinterpret_cast<uintptr_t>(a.out) & 15) == 0;
+    const bool grad_al = !LOSS && !DIFF && full_tile && (reinterpret_cast<uintptr_t>(a.grad) & 15) == 0;
+    const bool mode_feat = mode == DEX_GRAD_FEATURES, mode_const = mode == DEX_GRAD_CONSTANTS;
+    const int F = a.F;
 
     // Per-tree metadata is loaded one tree ahead (the loads of tree t + 1 are issued while tree t
     // runs) and the first instruction of a tree arrives as the prefetch of its predecessor's last
@@ -455,15 +460,14 @@ __global__ void __launch_bounds__(DEX_GRAD_THREADS, DEX_GRAD_MIN_CTAS) grad_kern
         const int64_t off_next2 = a.tape_off[t + 2];
         const int64_t co_next2 = a.const_off[t + 2];
         if (!DIFF && a.grad_off) go = a.grad_off[t + 1 < (int)a.n_trees ? t + 1 : t];
-        const int G = DIFF ? 1 : mode == DEX_GRAD_FEATURES ? a.F
-                    : mode == DEX_GRAD_CONSTANTS ? nconst : a.F + nconst;
+        const int G = DIFF ? 1 : mode_feat ? F : mode_const ? nconst : F + nconst;
         T nf = T(0);
-        const int npass = G > 0 ? (G + GC - 1) / GC : 1;
+        const int npass = G <= GC ? 1 : (G + GC - 1) / GC;
         for (int pass = 0; pass < npass; ++pass) {
             const int g0 = pass * GC;
             // one-hot index of feature f: f + foff; of the constant with ordinal o: o + coff
-            const int foff = DIFF ? -a.direction : (mode == DEX_GRAD_CONSTANTS ? NEVER : -g0);
-            const int coff = DIFF ? NEVER : mode == DEX_GRAD_CONSTANTS ? -g0 : mode == DEX_GRAD_BOTH ? a.F - g0 : NEVER;
+            const int foff = DIFF ? -a.direction : (mode_const ? NEVER : -g0);
+            const int coff = DIFF ? NEVER : mode_const ? -g0 : mode_feat ? NEVER : F - g0;
             T av[K], ad[GC][K];   // accumulator dual
 #pragma unroll
             for (int k = 0; k < K; ++k) av[k] = T(0);
@@ -660,9 +664,21 @@ __global__ void __launch_bounds__(DEX_GRAD_THREADS, DEX_GRAD_MIN_CTAS) grad_kern
             }
             // root derivative check (see the header comment: non-finite components propagate)
             if (!DIFF) {   // padded directions (g0 + g >= G) are not part of the gradient
+                T racc[2] = {nf, T(0)};
+                if (G - g0 >= GC) {
 #pragma unroll
-                for (int g = 0; g < GC; ++g)
-                    if (g0 + g < G) A::check(nf, ad[g]);
+                    for (int g = 0; g < GC; ++g)
+#pragma unroll
+                        for (int k = 0; k < K; ++k) racc[k & 1] = m_fma(ad[g][k], T(0), racc[k & 1]);
+                } else {
+#pragma unroll
+                    for (int g = 0; g < GC; ++g)
+                        if (g0 + g < G) {
+#pragma unroll
+                            for (int k = 0; k < K; ++k) racc[k & 1] = m_fma(ad[g][k], T(0), racc[k & 1]);
+                        }
+                }
+                nf = racc[0] + racc[1];
             }
             if constexpr (LOSS) {
                 // ---- fused loss: r_j = 2 w_j (v_j - y_j);  loss += w_j (v_j - y_j)^2;
@@ -705,7 +721,7 @@ __global__ void __launch_bounds__(DEX_GRAD_THREADS, DEX_GRAD_MIN_CTAS) grad_kern
                 const int64_t sbase = s0 + (int64_t)u * CS + (int64_t)tid * C;
                 if (pass == 0) {
                     T* o = a.out + (size_t)t * a.ldo + sbase;
-                    if (full_tile && (a.ldo % C) == 0 && (reinterpret_cast<uintptr_t>(a.out) & 15) == 0)
+                    if (out_vec)
                         *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(&av[u * C]);
                     else {
 #pragma unroll
@@ -720,7 +736,9 @@ __global__ void __launch_bounds__(DEX_GRAD_THREADS, DEX_GRAD_MIN_CTAS) grad_kern
                     // (G x N) column-major block: element (g, s) at s * G + g
                     T* gout = a.grad + goff + sbase * G + g0;
                     const int gc = min(GC, G - g0);
-                    if (gc == GC && G == GC && full_tile && ((reinterpret_cast<uintptr_t>(gout) & 15) == 0)) {
+                    // 16-byte alignment of gout given an aligned base: (goff + sbase * G + g0) % C == 0,
+                    // and sbase is a multiple of C, g0 = 0 when G == GC
+                    if (G == GC && grad_al && (goff % C) == 0) {
                         // the thread's C samples x GC directions are C*GC contiguous elements
                         T flat[C * GC];
 #pragma unroll
