@@ -360,10 +360,10 @@ def main():
             try:
                 inst = float(json.load(open(mpath))["smsp__inst_executed.sum"]["value"])
                 sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
-                peak = sm_count * 4 * clocks["sm_mhz"] * 1e6
+                issue_peak = sm_count * 4 * clocks["sm_mhz"] * 1e6
                 issue = {"bound": "issue", "warp_instructions_per_launch": inst,
-                         "peak_warp_instructions_per_s": peak, "ms_at_peak": inst / peak * 1e3,
-                         "frac": (inst / peak * 1e3) / ms_step,
+                         "peak_warp_instructions_per_s": issue_peak, "ms_at_peak": inst / issue_peak * 1e3,
+                         "frac": (inst / issue_peak * 1e3) / ms_step,
                          "source": "smsp__inst_executed.sum of profiles/r01_eval_kernel_ncu_metrics.json"}
             except Exception:
                 issue = None
