@@ -30,6 +30,8 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <map>
+#include <utility>
 
 // samples per thread = DEX_EVAL_U chunks of 16 bytes (8 floats / 4 doubles for U = 2)
 #ifndef DEX_EVAL_U
@@ -643,7 +645,7 @@ cudaError_t launch_typed(const EvalArgs& e, cudaStream_t stream, int threads, si
         kern = loss ? (param ? eval_kernel<T, U, false, true, true> : eval_kernel<T, U, false, false, true>)
                     : (param ? eval_kernel<T, U, false, true, false> : eval_kernel<T, U, false, false, false>);
     }
-    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t err = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem);
     if (err != cudaSuccess) return err;
     kern<<<grid, threads, smem, stream>>>(a);
     return cudaGetLastError();
@@ -725,6 +727,18 @@ __global__ void fold_kernel(Instr* tape, const Instr* ctape, const int64_t* seg,
                             int64_t n_trees, uint8_t* fold_ok) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t < n_trees) fold_ok[t] = fold_tree<T, GRAD>(tape, ctape, seg, seg_off, t) ? 1 : 0;
+}
+
+cudaError_t ensure_dynamic_smem(const void* kernel, size_t bytes) {
+    static thread_local std::map<std::pair<int, const void*>, size_t> granted;
+    int dev = 0;
+    cudaError_t err = cudaGetDevice(&dev);
+    if (err != cudaSuccess) return err;
+    size_t& have = granted[std::make_pair(dev, kernel)];
+    if (bytes <= have) return cudaSuccess;
+    err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (err == cudaSuccess) have = bytes;
+    return err;
 }
 
 cudaError_t launch_fold(int dtype, bool grad_rule, Instr* tape, const Instr* ctape, const int64_t* seg,

@@ -814,7 +814,7 @@ GradShape pick_shape(int dtype, int F, int max_stack, int Gmax, bool loss = fals
 template <typename T, int GC, int KMODE>
 cudaError_t launch_one(const GK<T>& a, const GradShape& sh, int64_t n_tiles, int n_chunks, cudaStream_t stream) {
     auto kern = grad_kernel<T, GC, (sizeof(T) == 8 ? GRAD_U64 : GRAD_U), KMODE>;
-    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh.smem);
+    cudaError_t err = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), sh.smem);
     if (err != cudaSuccess) return err;
     dim3 grid((unsigned)n_tiles, (unsigned)n_chunks);
     kern<<<grid, sh.threads, sh.smem, stream>>>(a);

@@ -8,6 +8,11 @@
 
 namespace dex {
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) costs about a microsecond of driver time: issue it
+// only when a (device, kernel) pair needs more than it was last given.  Thread-local: a context is
+// single-threaded and different host threads may drive different devices.
+cudaError_t ensure_dynamic_smem(const void* kernel, size_t bytes);
+
 struct EvalArgs {
     int dtype;                  // DEX_F32 / DEX_F64
     const Instr* tape;          // device
