@@ -253,6 +253,9 @@ int ensure_folded(dex_ctx* ctx, dex_population* pop, int rule, const uint8_t** f
                                     f.n_trees, pop->d_fold_ok[rule], ctx->stream);
         if (e != cudaSuccess) return cuda_err(ctx, e, "constant folding");
         ctx->launches += 1;
+        // the result is reused by later calls, possibly issued on another stream
+        // (dex_ctx_set_stream): complete it now — this happens once per change of the constants
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
         pop->fold_valid[rule] = true;
     }
     *fold_ok = pop->d_fold_ok[rule];
