@@ -40,6 +40,11 @@ struct dex_ctx {
     void* dev_io = nullptr;  // device staging for the *_host entry points
     size_t dev_io_bytes = 0;
     cudaEvent_t ev[2] = {nullptr, nullptr};
+    // recorded behind the device work of every compute call: the context's scratch buffers (xt,
+    // scratch, dev_io) are shared by all calls, so a call issued on ANOTHER stream must first wait
+    // for the previous one (dex_ctx_set_stream)
+    cudaEvent_t ev_done = nullptr;
+    bool ev_done_valid = false;
     int64_t launches = 0;    // kernels launched through this context
 };
 
@@ -115,6 +120,22 @@ int ensure_device(dex_ctx* ctx) {
     if (!ctx) return DEX_ERR_INVALID;
     if (ctx->device < 0) return set_err(ctx, DEX_ERR_CUDA, "host-only context: no CUDA device bound (libdexb200 has no CPU fallback)");
     CU(ctx, cudaSetDevice(ctx->device));
+    return DEX_OK;
+}
+
+// marks the end of the device work of a compute call on the current stream (see dex_ctx::ev_done)
+int finish_call(dex_ctx* ctx, int rc) {
+    if (rc == DEX_OK && ctx->ev_done) {
+        CU(ctx, cudaEventRecord(ctx->ev_done, ctx->stream));
+        ctx->ev_done_valid = true;
+    }
+    return rc;
+}
+// work enqueued on `next` from now on runs after everything this context has enqueued so far
+int order_after_previous(dex_ctx* ctx, cudaStream_t next) {
+    if (ctx->device < 0 || next == ctx->stream || !ctx->ev_done_valid) return DEX_OK;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaStreamWaitEvent(next, ctx->ev_done, 0));
     return DEX_OK;
 }
 
@@ -262,6 +283,22 @@ int ensure_folded(dex_ctx* ctx, dex_population* pop, int rule, const uint8_t** f
     return DEX_OK;
 }
 
+// Zero samples: nothing to launch, but the `complete` flags are still an output.  The reference
+// validates an empty array as is_valid(sum(())) = true, so a tree is complete unless one of its
+// folded constant subtrees is not (/root/reference/src/Evaluate.jl:347-354).
+// rule: 0 evaluation, 1 gradient (folded launches only), -1 no folding on this path
+int preset_ok_empty(dex_ctx* ctx, dex_population* pop, int rule, uint8_t* ok) {
+    const uint8_t* fold_ok = nullptr;
+    if (rule >= 0) {
+        int rc = ensure_folded(ctx, pop, rule, &fold_ok);
+        if (rc) return rc;
+    }
+    const size_t P = (size_t)pop->h.n_trees;
+    if (fold_ok) CU(ctx, cudaMemcpyAsync(ok, fold_ok, P, cudaMemcpyDeviceToDevice, ctx->stream));
+    else CU(ctx, cudaMemsetAsync(ok, 1, P, ctx->stream));
+    return DEX_OK;
+}
+
 int run_eval(dex_ctx* ctx, const dex_population* cpop, const void* X, int32_t F, int64_t N,
              int64_t ldx, void* out, int64_t ldo, uint8_t* ok, int eval_flags, const void* params,
              int32_t n_params, int32_t n_classes, const int32_t* classes, const void* y,
@@ -269,7 +306,8 @@ int run_eval(dex_ctx* ctx, const dex_population* cpop, const void* X, int32_t F,
              void* out_host = nullptr, int64_t ldo_host = 0) {
     dex_population* pop = const_cast<dex_population*>(cpop);
     const PackedPopulation& h = *pop->h.folded;   // evaluation runs the folded image
-    if (h.n_trees == 0 || N == 0) return DEX_OK;
+    if (h.n_trees == 0) return DEX_OK;
+    if (N == 0) return preset_ok_empty(ctx, pop, 0, ok);
     int threads;
     size_t smem;
     const int32_t front_rows = h.max_stack + h.n_param_rows;
@@ -397,7 +435,8 @@ int dex_ctx_create(int device, dex_ctx** out) {
             cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
             cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
             cudaEventCreateWithFlags(&ctx->ev[0], cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventCreateWithFlags(&ctx->ev[1], cudaEventDisableTiming) != cudaSuccess) {
+            cudaEventCreateWithFlags(&ctx->ev[1], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ctx->ev_done, cudaEventDisableTiming) != cudaSuccess) {
             cudaGetLastError();
             delete ctx;
             return DEX_ERR_CUDA;
@@ -419,6 +458,7 @@ int dex_ctx_destroy(dex_ctx* ctx) {
         if (ctx->dev_io) cudaFree(ctx->dev_io);
         if (ctx->pinned) cudaFreeHost(ctx->pinned);
         for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
+        if (ctx->ev_done) cudaEventDestroy(ctx->ev_done);
         if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
         if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     }
@@ -428,12 +468,17 @@ int dex_ctx_destroy(dex_ctx* ctx) {
 
 int dex_ctx_set_stream(dex_ctx* ctx, void* stream) {
     if (!ctx) return DEX_ERR_INVALID;
-    ctx->stream = static_cast<cudaStream_t>(stream);
+    cudaStream_t next = static_cast<cudaStream_t>(stream);
+    int rc = order_after_previous(ctx, next);
+    if (rc) return rc;
+    ctx->stream = next;
     return DEX_OK;
 }
 
 int dex_ctx_use_own_stream(dex_ctx* ctx) {
     if (!ctx) return DEX_ERR_INVALID;
+    int rc = order_after_previous(ctx, ctx->own_stream);
+    if (rc) return rc;
     ctx->stream = ctx->own_stream;
     return DEX_OK;
 }
@@ -479,6 +524,10 @@ int dex_population_pack(dex_ctx* ctx, const dex_optable* ops, const dex_node* no
     *out = nullptr;
     if (!ops || !offsets || n_trees < 0 || (n_trees > 0 && !nodes)) return set_err(ctx, DEX_ERR_INVALID, "null argument");
     if (dtype != DEX_F32 && dtype != DEX_F64) return set_err(ctx, DEX_ERR_INVALID, "dtype must be DEX_F32 or DEX_F64");
+    if (offsets[0] < 0) return set_err(ctx, DEX_ERR_INVALID, "offsets[0] is negative");
+    for (int64_t t = 0; t < n_trees; ++t)
+        if (offsets[t + 1] <= offsets[t])
+            return set_err(ctx, DEX_ERR_INVALID, "tree " + std::to_string(t) + ": offsets must be strictly increasing (empty tree or overlapping records)");
     dex_population* pop = new (std::nothrow) dex_population();
     if (!pop) return set_err(ctx, DEX_ERR_NOMEM, "out of host memory");
     std::string err;
@@ -629,8 +678,8 @@ int dex_eval(dex_ctx* ctx, const dex_population* pop, const void* X_dev, int32_t
     if ((rc = check_eval_args(ctx, pop, X_dev, nfeatures, nsamples, ldx, out_dev, ldo, ok_dev))) return rc;
     if (!out_dev && nsamples > 0 && pop->h.n_trees > 0) return set_err(ctx, DEX_ERR_INVALID, "null out");
     if (pop->h.max_parameter >= 0) return set_err(ctx, DEX_ERR_INVALID, "population has parameter leaves: use dex_eval_parametric");
-    return run_eval(ctx, pop, X_dev, nfeatures, nsamples, ldx, out_dev, ldo, ok_dev, eval_flags,
-                    nullptr, 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr);
+    return finish_call(ctx, run_eval(ctx, pop, X_dev, nfeatures, nsamples, ldx, out_dev, ldo, ok_dev, eval_flags,
+                                     nullptr, 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr));
 }
 
 int dex_eval_parametric(dex_ctx* ctx, const dex_population* pop, const void* X_dev,
@@ -647,9 +696,9 @@ int dex_eval_parametric(dex_ctx* ctx, const dex_population* pop, const void* X_d
         return set_err(ctx, DEX_ERR_RANGE, "population uses parameter " + std::to_string(pop->h.max_parameter + 1) +
                                                " (1-based) but only " + std::to_string(n_params) + " were passed");
     // a dummy non-null params pointer keeps the parametric kernel selected when n_params == 0
-    return run_eval(ctx, pop, X_dev, nfeatures, nsamples, ldx, out_dev, ldo, ok_dev, eval_flags,
-                    params_dev ? params_dev : X_dev, n_params, n_classes, classes_dev, nullptr,
-                    nullptr, nullptr, nullptr);
+    return finish_call(ctx, run_eval(ctx, pop, X_dev, nfeatures, nsamples, ldx, out_dev, ldo, ok_dev, eval_flags,
+                                     params_dev ? params_dev : X_dev, n_params, n_classes, classes_dev, nullptr,
+                                     nullptr, nullptr, nullptr));
 }
 
 int dex_eval_loss(dex_ctx* ctx, const dex_population* pop, const void* X_dev, int32_t nfeatures,
@@ -681,7 +730,7 @@ int dex_eval_loss(dex_ctx* ctx, const dex_population* pop, const void* X_dev, in
                                             ctx->stream);
     if (e != cudaSuccess) return cuda_err(ctx, e, "loss reduce");
     ctx->launches += 1;
-    return DEX_OK;
+    return finish_call(ctx, DEX_OK);
 }
 
 int dex_grad_offsets(const dex_population* pop, int32_t nfeatures, int64_t nsamples, int mode,
@@ -711,7 +760,8 @@ static int run_grad(dex_ctx* ctx, const dex_population* cpop, const void* X, int
     dex_population* pop = const_cast<dex_population*>(cpop);
     const PackedPopulation& h = pop->h;
     if (h.max_parameter >= 0) return set_err(ctx, DEX_ERR_UNSUPPORTED, "derivatives of parametric populations are not implemented");
-    if (h.n_trees == 0 || N == 0) return DEX_OK;
+    if (h.n_trees == 0) return DEX_OK;
+    if (N == 0) return preset_ok_empty(ctx, pop, mode == DEX_GRAD_FEATURES && F > 0 ? 1 : -1, ok);
     int Gmax = 1;
     if (mode >= 0) {
         int32_t ncmax = 0;
@@ -803,8 +853,8 @@ int dex_eval_loss_grad(dex_ctx* ctx, const dex_population* pop, const void* X_de
     if (!grad_dev && grad_offsets_host[pop->h.n_trees] > 0) return set_err(ctx, DEX_ERR_INVALID, "null grad");
     if (nsamples <= 0) return set_err(ctx, DEX_ERR_INVALID, "the loss needs at least one sample");
     LossSpec ls{y_dev, weights_dev, loss_dev, grad_dev};
-    return run_grad(ctx, pop, X_dev, nfeatures, nsamples, ldx, mode, 0, nullptr, 0, nullptr, grad_offsets_host,
-                    ok_dev, &ls);
+    return finish_call(ctx, run_grad(ctx, pop, X_dev, nfeatures, nsamples, ldx, mode, 0, nullptr, 0, nullptr,
+                                     grad_offsets_host, ok_dev, &ls));
 }
 
 int dex_eval_grad(dex_ctx* ctx, const dex_population* pop, const void* X_dev, int32_t nfeatures,
@@ -816,7 +866,8 @@ int dex_eval_grad(dex_ctx* ctx, const dex_population* pop, const void* X_dev, in
     if (mode < 0 || mode > 2) return set_err(ctx, DEX_ERR_INVALID, "mode must be DEX_GRAD_CONSTANTS/FEATURES/BOTH");
     if ((!out_dev && nsamples > 0 && pop->h.n_trees > 0) || !grad_offsets_host) return set_err(ctx, DEX_ERR_INVALID, "null out / grad_offsets");
     if (!grad_dev && grad_offsets_host[pop->h.n_trees] > 0) return set_err(ctx, DEX_ERR_INVALID, "null grad");
-    return run_grad(ctx, pop, X_dev, nfeatures, nsamples, ldx, mode, 0, out_dev, ldo, grad_dev, grad_offsets_host, ok_dev);
+    return finish_call(ctx, run_grad(ctx, pop, X_dev, nfeatures, nsamples, ldx, mode, 0, out_dev, ldo, grad_dev,
+                                     grad_offsets_host, ok_dev));
 }
 
 int dex_eval_diff(dex_ctx* ctx, const dex_population* pop, const void* X_dev, int32_t nfeatures,
@@ -827,7 +878,8 @@ int dex_eval_diff(dex_ctx* ctx, const dex_population* pop, const void* X_dev, in
     if ((rc = check_eval_args(ctx, pop, X_dev, nfeatures, nsamples, ldx, out_dev, ldo, ok_dev))) return rc;
     if ((!out_dev || !dout_dev) && nsamples > 0 && pop->h.n_trees > 0) return set_err(ctx, DEX_ERR_INVALID, "null out / dout");
     if (direction < 0) return set_err(ctx, DEX_ERR_RANGE, "direction must be a feature index");
-    return run_grad(ctx, pop, X_dev, nfeatures, nsamples, ldx, -1, direction, out_dev, ldo, dout_dev, nullptr, ok_dev);
+    return finish_call(ctx, run_grad(ctx, pop, X_dev, nfeatures, nsamples, ldx, -1, direction, out_dev, ldo, dout_dev,
+                                     nullptr, ok_dev));
 }
 
 int dex_eval_host(dex_ctx* ctx, const dex_population* pop, const void* X_host, int32_t nfeatures,
@@ -836,9 +888,26 @@ int dex_eval_host(dex_ctx* ctx, const dex_population* pop, const void* X_host, i
     int rc = ensure_device(ctx);
     if (rc) return rc;
     if (!pop || !out_host || !ok_host || (!X_host && nfeatures > 0 && nsamples > 0)) return set_err(ctx, DEX_ERR_INVALID, "null argument");
+    if (pop->device != ctx->device) return set_err(ctx, DEX_ERR_INVALID, "population was packed on another device");
+    if (nfeatures < 0 || nsamples < 0) return set_err(ctx, DEX_ERR_INVALID, "negative size");
+    if (ldx < nfeatures) return set_err(ctx, DEX_ERR_INVALID, "ldx < nfeatures");
+    if (ldo < nsamples) return set_err(ctx, DEX_ERR_INVALID, "ldo < nsamples");
+    if (pop->h.max_parameter >= 0) return set_err(ctx, DEX_ERR_INVALID, "population has parameter leaves");
+    if (pop->h.max_feature >= nfeatures)
+        return set_err(ctx, DEX_ERR_RANGE,
+                       "population uses feature " + std::to_string(pop->h.max_feature + 1) +
+                           " (1-based) but X has only " + std::to_string(nfeatures) + " rows");
     const size_t es = pop->h.dtype == DEX_F32 ? 4 : 8;
     const int64_t P = pop->h.n_trees, N = nsamples;
-    if (P == 0 || N == 0) return DEX_OK;
+    if (P == 0) return DEX_OK;
+    if (N == 0) {   // no samples: only the flags are an output
+        if ((rc = ensure_dev_io(ctx, (size_t)P))) return rc;
+        uint8_t* dK0 = static_cast<uint8_t*>(ctx->dev_io);
+        if ((rc = preset_ok_empty(ctx, const_cast<dex_population*>(pop), 0, dK0))) return rc;
+        CU(ctx, cudaMemcpyAsync(ok_host, dK0, (size_t)P, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        return DEX_OK;
+    }
     // device staging: X | out | ok
     const size_t xb = (size_t)ldx * (size_t)N * es;
     const size_t xoff = 0, ooff = (xb + 255) & ~(size_t)255;
@@ -851,7 +920,6 @@ int dex_eval_host(dex_ctx* ctx, const dex_population* pop, const void* X_host, i
     uint8_t* dK = reinterpret_cast<uint8_t*>(base + koff);
     CU(ctx, cudaMemcpyAsync(dX, X_host, xb, cudaMemcpyHostToDevice, ctx->stream));
     if ((rc = check_eval_args(ctx, pop, dX, nfeatures, N, ldx, dO, N, dK))) return rc;
-    if (pop->h.max_parameter >= 0) return set_err(ctx, DEX_ERR_INVALID, "population has parameter leaves");
     // results travel back slice by slice on the copy stream while the next slice computes
     const int n_slices = (size_t)P * (size_t)N * es >= ((size_t)8 << 20) ? 8 : 1;
     if ((rc = run_eval(ctx, pop, dX, nfeatures, N, ldx, dO, N, dK, eval_flags, nullptr, 0, 0, nullptr,

@@ -526,15 +526,18 @@ struct Flattener {
         std::vector<Instr>& tape = scalar ? out.ctape : out.tape;
         for (EIns e : split) {
             // commutative operators: bring the operands into (ACC|ROW, ROW|CONST) order
+            bool swapped = false;
             if (commutative(e.op)) {
                 auto rank = [](const Opnd& o) { return o.src == SRC_ACC ? 0 : o.src == SRC_ROW ? 1 : o.src == SRC_PARAM ? 1 : 2; };
-                if (rank(e.a) > rank(e.b)) std::swap(e.a, e.b);
+                if (rank(e.a) > rank(e.b)) { std::swap(e.a, e.b); swapped = true; }
             }
             Instr ins{};
             const bool a_chk_row = e.a.chk && e.a.src != SRC_CONST && e.a.src != SRC_ACC;
             const bool b_chk_row = e.b.chk && e.b.src != SRC_CONST && e.b.src != SRC_ACC;
             const uint32_t h = scalar ? (uint32_t)H_GENERIC : pick_handler(e, a_chk_row, b_chk_row);
             ins.w0 = h | ((uint32_t)e.op << 8) | (e.a.src << 16) | (e.b.src << 18) | e.flags;
+            // max / min partials break ties by operand order (dex_tape.h, SWAPPED)
+            if (swapped && (e.op == DEX_OP_MAX || e.op == DEX_OP_MIN)) ins.w0 |= F_SWAPPED;
             if (e.a.chk) ins.w0 |= F_CHK_A;
             if (e.b.chk) ins.w0 |= F_CHK_B;
             if ((e.a.chk && e.a.src == SRC_CONST) || (e.b.chk && e.b.src == SRC_CONST)) ins.w0 |= F_CHK_CONST;

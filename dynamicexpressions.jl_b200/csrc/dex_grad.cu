@@ -607,6 +607,16 @@ __global__ void __launch_bounds__(DEX_GRAD_THREADS, DEX_GRAD_MIN_CTAS) grad_kern
                     } break;
                 }
 
+                // max / min whose operands the flattener exchanged: the reference's partials
+                // (x > y, !(x > y)) give a tie to the SECOND operand of the original order, which
+                // is operand A here (/root/reference/src/EvaluateDerivative.jl:340-365 via Zygote)
+                if (w0 & F_SWAPPED) {
+                    const bool is_max = op == (uint32_t)DEX_OP_MAX;
+#pragma unroll
+                    for (int k = 0; k < K; ++k)
+                        if (x[k] == y[k]) { p0[k] = is_max ? T(1) : T(0); p1[k] = is_max ? T(0) : T(1); }
+                }
+
                 // ---- stage 2: derivative combination ---------------------------------------------
                 switch (sel) {
 #define CB(CLS, KA, KB) \

@@ -30,7 +30,11 @@ namespace dex {
 // 16 bytes, fetched as one uint4 (x=w0, y=w1, z/w = constant).
 //   w0 [ 5: 0] handler  HANDLER id (H_*), 0 = generic
 //      [ 6]    copy of PUSH: the Float32 jump table has one entry per (handler, PUSH)
-//              so that the push costs nothing when it does not happen; bit 7 is zero
+//              so that the push costs nothing when it does not happen
+//      [ 7]    SWAPPED  the flattener exchanged the operands of max / min (to reach an
+//              (ACC|ROW, ROW|CONST) handler form): values are symmetric, but the reference's
+//              partials (x > y, !(x > y)) break ties by operand ORDER, so the gradient
+//              interpreters apply them to the original order
 //      [15: 8] opcode   builtin opcode of include/dex_ops.def (IDENTITY doubles as LOAD)
 //      [17:16] srcA     SRC_*
 //      [19:18] srcB     SRC_*   (ternary: third operand is always ACC)
@@ -59,6 +63,7 @@ static_assert(sizeof(Instr) == 16, "tape instruction must be 16 bytes");
 
 enum : uint32_t { SRC_ACC = 0, SRC_ROW = 1, SRC_CONST = 2, SRC_PARAM = 3 };
 enum : uint32_t {
+    F_SWAPPED = 1u << 7,
     F_PUSH = 1u << 20,
     F_CHK_OUT = 1u << 21,
     F_CHK_A = 1u << 22,

@@ -74,6 +74,32 @@ def test_pack_validation_errors():
         D.Population(None, ops, np.float32, ctx=ctx, wire=(w, np.array([0, 2])))
     with pytest.raises(ValueError, match="no device implementation"):
         dexb200.OperatorEnum({1: ("my_custom_function",)})
+    # offsets must start at >= 0 and increase: a negative or non-monotonic table would make the
+    # flattener read outside the node array
+    w2 = dexb200.to_wire(N(1, N(feature=1)))
+    nodes = np.concatenate([w2, w2])
+    for bad in ([-5, 2, 4], [0, 4, 2], [0, 0, 2], [2, 0, 4]):
+        with pytest.raises(D.DexError, match="offsets"):
+            D.Population(None, ops, np.float32, ctx=ctx, wire=(nodes, np.array(bad, dtype=np.int64)))
+
+
+def test_max_min_operand_exchange_is_recorded_for_the_gradient():
+    """The flattener brings commutative operators into (ACC|ROW, ROW|CONST) order.  For max / min
+    the reference's partials (x > y, !(x > y)) break ties by operand order, so an exchange must be
+    visible to the gradient interpreters: bit 7 of w0 (csrc/dex_tape.h)."""
+    ctx = D.host_context()
+    ops = dexb200.OperatorEnum({1: ("cos",), 2: ("max", "min", "+")})
+    N = dexb200.Node
+    inner = lambda: N(1, N(feature=1))
+    trees = [N(1, N(val=0.0), N(feature=1)),     # max(c, x1)    -> (ROW, CONST): exchanged
+             N(1, N(feature=1), N(val=0.0)),     # max(x1, c)    -> as written
+             N(2, N(feature=2), inner()),        # min(x2, cos)  -> (ACC, ROW): exchanged
+             N(2, inner(), N(feature=2)),        # min(cos, x2)  -> as written
+             N(3, N(val=1.0), N(feature=1))]     # c + x1: exchanged, but + has no tie rule -> no flag
+    pop = D.Population(trees, ops, np.float32, ctx=ctx)
+    ins, off = pop.tape()
+    last = ins[off[1:] - 1, 0]
+    assert [int(w >> 7) & 1 for w in last] == [1, 0, 1, 0, 0]
 
 
 def test_population_info_and_constants_roundtrip():

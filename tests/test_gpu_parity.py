@@ -13,6 +13,7 @@ from dexb200 import device as D
 from dexb200 import treegen
 from tests.golden_util import (CONTEXTS, expected_grad, expected_y, load_cases, make_matrix,
                                make_operators, make_tree)
+from tests.parity_util import check_trees, tree_verdict
 
 pytestmark = pytest.mark.gpu
 
@@ -138,49 +139,68 @@ def test_known_gradients_through_public_api(case):
 # ---------------------------------------------------------------------------------------
 # 2. random populations against the oracle
 # ---------------------------------------------------------------------------------------
-def _check_population(oracle, nodes, offsets, ops, X, dtype, *, ctx=None, label=""):
+def _grad_verdict(dtype, out, g, ref, rg, yard_pairs):
+    """Verdict of one tree of a gradient call: the value row and the (G x N) gradient block, each
+    against the oracle with the oracle's own yardstick evaluations [(value, gradient), ...]."""
+    parts = [(out, ref, [y for y, _ in yard_pairs])]
+    if rg.shape[0]:
+        parts.append((g, rg, [yg for _, yg in yard_pairs]))
+    return tree_verdict(dtype, parts)
+
+
+def _check_population(oracle, nodes, offsets, ops, X, dtype, *, ctx=None, label="", min_strict=0.85, pop=None):
+    """Device vs oracle for a population: flags exactly, values per tree in the classes of
+    tests/parity_util.py (strict / loose / elementwise; no tree is skipped).  Returns (errors of the compared trees, ok)."""
     c = ctx or {}
-    pop = D.Population(None, ops, dtype, wire=(nodes, offsets), bumper=c.get("bumper", False),
-                       use_fused=c.get("use_fused", True))
-    out, ok = pop.eval(X, early_exit=c.get("early_exit", True))
+    early = c.get("early_exit", True)
+    if pop is None:
+        pop = D.Population(None, ops, dtype, wire=(nodes, offsets), bumper=c.get("bumper", False),
+                           use_fused=c.get("use_fused", True))
+    out, ok = pop.eval(X, early_exit=early)
     out = out.cpu().numpy()
     ok = ok.cpu().numpy().astype(bool)
     ref, rok = oracle.eval_population(nodes, offsets, ops.opcodes, X, _oflags(oracle, c))
     _, rok_elem = oracle.eval_population(nodes, offsets, ops.opcodes, X, _oflags(oracle, c) | oracle.ELEMENTWISE)
     _flags_agree(ok, rok, rok_elem, label)
     # conditioning yardsticks: how far the oracle's own result moves (a) when X is perturbed
-    # by one ulp, (b) for float32, when it is evaluated in float64.  A tree whose value swings
-    # by more than the tolerance under a 1-ulp input change (cos(exp(exp(x))) ...) cannot be
-    # compared tighter than that swing by ANY two correct implementations.
+    # by one ulp, (b) for float32, when it is evaluated in float64 (float64: with 80-bit
+    # intermediates), (c) with every transcendental result moved by one ulp
+    # (oracle.set_ulp_nudge): two faithful implementations of sin / exp / ... may differ by exactly
+    # that, and a pole such as x3 / (0.997 - sin(x3 + x2)) amplifies it without any sensitivity
+    # to X showing in (a)
     ref_p, _ = oracle.eval_population(nodes, offsets, ops.opcodes, np.nextafter(X, dtype(np.inf)),
                                       _oflags(oracle, c))
     if dtype == np.float32:
         ref2, _ = oracle.eval_population(nodes, offsets, ops.opcodes, X.astype(np.float64), _oflags(oracle, c))
-    else:  # float64: the same algorithm with 80-bit intermediates
+    else:
         ref2, _ = oracle.eval_population_f80(nodes, offsets, ops.opcodes, X, _oflags(oracle, c))
-    # (c) the oracle with every transcendental result moved by one ulp (oracle.set_ulp_nudge): two
-    # faithful implementations of sin / exp / ... may differ by exactly that, and a pole such as
-    # x3 / (0.997 - sin(x3 + x2)) amplifies it without any sensitivity to X showing in (a)
     try:
         oracle.set_ulp_nudge(1)
         ref_n, _ = oracle.eval_population(nodes, offsets, ops.opcodes, X, _oflags(oracle, c))
     finally:
         oracle.set_ulp_nudge(0)
-    errs = []
+    verdicts, ids = [], []
+    n_pattern = 0
     for t in np.nonzero(rok)[0]:
-        err = _relerr(out[t], ref[t])
-        cond = max(_relerr(ref_p[t], ref[t]), _relerr(ref_n[t], ref[t]))
-        if ref2 is not None:
-            cond = max(cond, _relerr(ref[t], ref2[t]))
-        if not np.isfinite(cond):
-            continue
-        tol = max(RTOL[dtype], 30.0 * cond)
-        assert err <= tol, f"{label}: tree {t} rel err {err:.3e} > {tol:.3e}"
-        errs.append(err)
-    if not c.get("early_exit", True):
-        for t in range(len(offsets) - 1):
-            assert _same_nonfinite(out[t], ref[t]) or not rok[t] or True
-    return np.array(errs), ok
+        r = ref[t]
+        yards = (ref_p[t], ref_n[t], ref2[t])
+        fin = np.isfinite(r)
+        mask = None
+        if not fin.all():
+            # only possible with early_exit = false: the row holds the Inf / NaN the reference's
+            # arithmetic produces.  The PATTERN is part of the answer wherever the oracle's own
+            # pattern is stable under the yardstick perturbations.
+            assert not early, f"{label}: tree {t} is complete but the oracle row is not finite"
+            if all(_same_nonfinite(np.asarray(y, dtype=r.dtype), r) for y in yards):
+                assert _same_nonfinite(out[t], r), f"{label}: tree {t}: non-finite pattern differs from the oracle"
+                n_pattern += 1
+            mask = fin & np.isfinite(out[t])
+        verdicts.append(tree_verdict(dtype, [(out[t], r, yards, mask)]))
+        ids.append(int(t))
+    stats = check_trees(label, dtype, verdicts, min_strict=min_strict, ids=ids)
+    stats["n_pattern_checked"] = n_pattern
+    errs = np.array([v[1] for v in verdicts])
+    return errs, ok
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
@@ -210,7 +230,7 @@ def test_depth12_ten_features_population(oracle):
     ops = dexb200.OperatorEnum(treegen.OPSET_A)
     nodes, offsets = treegen.gen_population(120, 12, 2, 4, 10, seed=3)
     X = np.random.default_rng(2).standard_normal((10, 2048)).astype(np.float32)
-    _check_population(oracle, nodes, offsets, ops, X, np.float32, label="depth12")
+    _check_population(oracle, nodes, offsets, ops, X, np.float32, label="depth12", min_strict=0.65)
 
 
 @pytest.mark.parametrize("N", [1, 2, 3, 5, 127, 128, 129, 1023, 1024, 1025, 4097])
@@ -258,9 +278,84 @@ def test_empty_inputs():
     pop = D.Population(None, ops, np.float32, wire=(nodes, offsets))
     out, ok = pop.eval(np.zeros((2, 0), np.float32))
     assert out.shape == (3, 0)
+    assert ok.cpu().numpy().tolist() == [1, 1, 1]          # is_valid_array(empty) is true in the reference
+    y, g, off, gok = pop.eval_grad(np.zeros((2, 0), np.float32), D.GRAD_FEATURES)
+    assert y.shape == (3, 0) and g.numel() == 0 and gok.cpu().numpy().tolist() == [1, 1, 1]
+    # ... unless a folded constant subtree is invalid (Evaluate.jl:347-354, whatever N is)
+    N_ = dexb200.Node
+    bad = D.Population([N_(1, N_(val=1.0), N_(3, N_(val=1.0), N_(val=0.0))), N_(feature=1)], ops, np.float32)
+    out, ok = bad.eval(np.zeros((2, 0), np.float32))
+    assert ok.cpu().numpy().tolist() == [0, 1]
+    oh, kh = np.zeros((2, 0), np.float32), np.full(2, 7, np.uint8)
+    bad.eval_host(np.zeros((0, 2), np.float32), oh, kh)
+    assert kh.tolist() == [0, 1]
     empty = D.Population(None, ops, np.float32, wire=(nodes[:0], np.zeros(1, np.int64)))
     out, ok = empty.eval(np.zeros((2, 10), np.float32))
     assert out.shape == (0, 10)
+
+
+def test_calls_on_different_streams_do_not_race_on_the_context_scratch(oracle):
+    """One context, two torch streams: the transposed copy of X and the other scratch buffers
+    belong to the context, so a call issued on stream B must run after the previous call on
+    stream A (dex_ctx_set_stream orders them)."""
+    import torch
+    ops = dexb200.OperatorEnum(treegen.OPSET_A)
+    nodes, offsets = treegen.gen_population(400, 8, 2, 4, 5, seed=3)
+    pop = D.Population(None, ops, np.float32, wire=(nodes, offsets))
+    rng = np.random.default_rng(5)
+    N = 1 << 15
+    Xa = torch.from_numpy(rng.standard_normal((N, 5)).astype(np.float32)).cuda()
+    Xb = torch.from_numpy(rng.standard_normal((N, 5)).astype(np.float32)).cuda()
+    ref_a, _ = pop.eval(Xa.T)
+    ref_b, _ = pop.eval(Xb.T)
+    ya, ga, _, _ = pop.eval_grad(Xa.T, D.GRAD_FEATURES)
+    torch.cuda.synchronize()
+    sa, sb = torch.cuda.Stream(), torch.cuda.Stream()
+    for _ in range(20):
+        with torch.cuda.stream(sa):
+            oa, _ = pop.eval(Xa.T)
+        with torch.cuda.stream(sb):
+            ob, _ = pop.eval(Xb.T)
+        with torch.cuda.stream(sa):
+            y2, g2, _, _ = pop.eval_grad(Xa.T, D.GRAD_FEATURES)
+        with torch.cuda.stream(sb):
+            ob2, _ = pop.eval(Xb.T)
+        torch.cuda.synchronize()
+        same = lambda u, v: bool(((u == v) | (torch.isnan(u) & torch.isnan(v))).all())
+        assert same(oa, ref_a) and same(ob, ref_b) and same(ob2, ref_b) and same(g2, ga) and same(y2, ya)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_max_min_gradient_ties_follow_the_operand_order(dtype, oracle):
+    """max(0.0, x1) at x1 == 0: the reference gives the tie to the second operand
+    (partials (x > y, !(x > y))), whatever order the flattener evaluates in."""
+    ops = dexb200.OperatorEnum({1: ("cos", "relu"), 2: ("max", "min", "*", "+")})
+    N_ = dexb200.Node
+    x1, x2 = N_(feature=1, T=dtype), N_(feature=2, T=dtype)
+    c0 = lambda: N_(val=0.0, T=dtype)
+    prod = lambda: N_(3, x1, x2)
+    trees = []
+    for op in (1, 2):
+        trees += [N_(op, c0(), x1), N_(op, x1, c0()), N_(op, x1, x2), N_(op, x2, x1), N_(op, x2, prod()),
+                  N_(op, prod(), x2), N_(op, c0(), prod()), N_(op, prod(), c0()),
+                  N_(op, N_(4, prod(), x1), N_(4, x1, prod())), N_(op, N_(4, x1, prod()), N_(4, prod(), x1))]
+    X = np.random.default_rng(0).standard_normal((2, 512)).astype(dtype)
+    X[0, ::3] = 0.0                 # ties with the constant and (through x1 * x2 = 0) with products
+    X[1, ::5] = X[0, ::5]           # ties between features
+    X[1, 1::7] = 1.0                # x1 * x2 == x1
+    nodes, offsets = dexb200.to_wire_population(trees)
+    pop = D.Population(None, ops, dtype, wire=(nodes, offsets))
+    for dmode, omode in ((D.GRAD_FEATURES, oracle.GRAD_FEATURES), (D.GRAD_BOTH, oracle.GRAD_BOTH),
+                         (D.GRAD_CONSTANTS, oracle.GRAD_CONSTANTS)):
+        out, grad, off, ok = pop.eval_grad(X, dmode)
+        out, grad = out.cpu().numpy(), grad.cpu().numpy()
+        ref, rgrads, rok = oracle.eval_grad_population(nodes, offsets, ops.opcodes, X, omode)
+        assert rok.all() and ok.cpu().numpy().all()
+        for t in range(len(trees)):
+            G = rgrads[t].shape[0]
+            g = grad[off[t]:off[t + 1]].reshape(X.shape[1], G).T
+            np.testing.assert_array_equal(out[t], ref[t])
+            np.testing.assert_allclose(g, rgrads[t], rtol=1e-6, atol=0, err_msg=f"tree {t} mode {dmode}")
 
 
 def test_feature_out_of_range_is_an_error():
@@ -291,8 +386,7 @@ def test_strided_inputs_and_outputs(oracle):
     assert (big[:, N:] == -7.0).all()
     o = out.cpu().numpy()
     ref64, _ = oracle.eval_population(nodes, offsets, ops.opcodes, Xpad[:, :4].T.astype(np.float64))
-    for t in np.nonzero(rok)[0]:
-        assert _relerr(o[t], ref[t]) <= max(1e-4, 30 * _relerr(ref[t], ref64[t]))
+    check_trees("strided", np.float32, [tree_verdict(np.float32, [(o[t], ref[t], (ref64[t],))]) for t in np.nonzero(rok)[0]])
     # torch in => torch out, same values
     y, okk = dexb200.eval_trees_array([dexb200.from_wire(nodes[offsets[0]:offsets[1]])], Xview, ops)
     assert y.is_cuda and torch.equal(y[0], out[0])
@@ -353,8 +447,9 @@ def test_parametric_population_matches_oracle(oracle):
     _flags_agree(ok, rok, rok_elem, "parametric")
     ref64, _ = oracle.eval_parametric_population(nodes, offsets, ops.opcodes, X.astype(np.float64),
                                                  params.astype(np.float64), cls0)
-    for t in np.nonzero(rok)[0]:
-        assert _relerr(out[t], ref[t]) <= max(1e-4, 30 * _relerr(ref[t], ref64[t]))
+    st = check_trees("parametric", np.float32,
+                     [tree_verdict(np.float32, [(out[t], ref[t], (ref64[t],))]) for t in np.nonzero(rok)[0]])
+    assert st["n_complete"] > 30
     with pytest.raises(D.DexError):
         pop.eval(X)                                   # parameter leaves need the parametric entry point
     with pytest.raises(D.DexError):
@@ -377,19 +472,17 @@ def test_gradient_population_matches_oracle(dtype, mode, oracle):
     _, _, rok_elem = oracle.eval_grad_population(nodes, offsets, ops.opcodes, X, omode | oracle.GRAD_ELEMENTWISE)
     ref64, rgrads64, _ = oracle.eval_grad_population(nodes, offsets, ops.opcodes, X.astype(np.float64), omode)
     _flags_agree(ok, rok, rok_elem, f"grad/{mode}")
+    ref_p, rgrads_p, _ = oracle.eval_grad_population(nodes, offsets, ops.opcodes, np.nextafter(X, dtype(np.inf)), omode)
     N = X.shape[1]
-    n_checked = 0
+    verdicts, n_with_grad = [], 0
     for t in np.nonzero(rok)[0]:
         G = rgrads[t].shape[0]
         assert off[t + 1] - off[t] == G * N                      # layout: (G x N), gradient index fastest
         g = grad[off[t]:off[t + 1]].reshape(N, G).T
-        cond = max(_relerr(ref[t], ref64[t]), _relerr(rgrads[t], rgrads64[t]) if G else 0.0) if dtype == np.float32 else 0.0
-        tol = max(RTOL[dtype], 30 * cond)
-        assert _relerr(out[t], ref[t]) <= tol
-        if G:
-            assert _relerr(g, rgrads[t]) <= tol, (t, mode)
-            n_checked += 1
-    assert n_checked > 10
+        verdicts.append(_grad_verdict(dtype, out[t], g, ref[t], rgrads[t], [(ref_p[t], rgrads_p[t]), (ref64[t], rgrads64[t])]))
+        n_with_grad += bool(G)
+    check_trees(f"grad/{mode}/{np.dtype(dtype).name}", dtype, verdicts)
+    assert n_with_grad > 10
 
 
 def test_many_constants_gradient_passes(oracle):
@@ -523,21 +616,15 @@ def test_random_trees_with_ternary_operators_value_and_gradient(dtype, oracle):
                                                              np.nextafter(X, dtype(np.inf)), omode)
             ref64, rgrads64, _ = oracle.eval_grad_population(nodes, offsets, ops.opcodes, X.astype(np.float64), omode)
             _flags_agree(gok, rok, rok_elem, f"ternary grad N={N}")
-            n_checked = 0
+            verdicts = []
             for t in np.nonzero(rok)[0]:
                 G = rgrads[t].shape[0]
                 g = grad[off[t]:off[t + 1]].reshape(N, G).T
-                cond = max(_relerr(ref_p[t], ref[t]), _relerr(rgrads_p[t], rgrads[t]) if G else 0.0)
-                if dtype == np.float32:
-                    cond = max(cond, _relerr(ref[t], ref64[t]), _relerr(rgrads[t], rgrads64[t]) if G else 0.0)
-                if not np.isfinite(cond) or cond > 1e-2:      # chaotic: nothing to compare
-                    continue
-                tol = max(RTOL[dtype], 30 * cond)
-                assert _relerr(out[t], ref[t]) <= tol, (t, N)
-                if G:
-                    assert _relerr(g, rgrads[t]) <= tol, (t, N, dmode)
-                n_checked += 1
-            assert n_checked > 20
+                verdicts.append(_grad_verdict(dtype, out[t], g, ref[t], rgrads[t],
+                                              [(ref_p[t], rgrads_p[t]), (ref64[t], rgrads64[t])]))
+            st = check_trees(f"ternary grad N={N} mode={dmode} {np.dtype(dtype).name}", dtype, verdicts,
+                             min_strict=0.8)          # N = 1: a single sample per tree
+            assert st["n_strict"] + st["n_loose"] > 20
 
 
 def test_native_float32_handlers_are_accurate_to_a_few_ulp():
@@ -670,13 +757,14 @@ def test_fused_loss_gradient_matches_oracle(dtype, mode, weighted, oracle):
     ref_p, rgrads_p, _ = oracle.eval_grad_population(nodes, offsets, ops.opcodes, np.nextafter(X, dtype(np.inf)), omode)
     ref64, rgrads64, _ = oracle.eval_grad_population(nodes, offsets, ops.opcodes, X.astype(np.float64), omode)
     w64 = np.ones(N) if w is None else w.astype(np.float64)
-    n_checked = 0
+    n_checked = n_chaotic = 0
     for t in np.nonzero(rok)[0]:
         G = rgrads[t].shape[0]
         cond = max(_relerr(ref_p[t], ref[t]), _relerr(rgrads_p[t], rgrads[t]) if G else 0.0)
         if dtype == np.float32:
             cond = max(cond, _relerr(ref[t], ref64[t]), _relerr(rgrads[t], rgrads64[t]) if G else 0.0)
-        if not np.isfinite(cond):
+        if not np.isfinite(cond) or 30 * cond > 1e-2:
+            n_chaotic += 1
             continue
         tol = max(2e-4 if dtype == np.float32 else 1e-6, 30 * cond)
         r = ref[t].astype(np.float64) - y.astype(np.float64)
@@ -690,7 +778,7 @@ def test_fused_loss_gradient_matches_oracle(dtype, mode, weighted, oracle):
             got = grad[off[t]:off[t + 1]]
             assert np.all(np.abs(got - want) <= tol * np.maximum(scale, 1e-30)), (t, mode, got, want)
             n_checked += 1
-    assert n_checked > 10
+    assert n_checked > 10 and n_chaotic <= max(2, 0.12 * int(rok.sum()))
 
 
 @pytest.mark.parametrize("P_,N", [(64, 4096), (400, 8192)])   # the second takes the sliced D2H pipeline
@@ -741,18 +829,10 @@ def test_full_size_config2_properties(oracle):
     # (c) idempotence
     out2, ok2 = pop.eval(Xd.T)
     assert torch.equal(ok, ok2) and bool(((out2 == out) | (torch.isnan(out2) & torch.isnan(out))).all())
-    # (d) ok flag == "all finite" for finite inputs whenever the oracle agrees, on a sample of trees
-    sel = np.arange(0, 1000, 25)
-    sn, so = _subset(nodes, offsets, sel)
-    ref, rok = oracle.eval_population(sn, so, ops.opcodes, X)
-    _, rok_elem = oracle.eval_population(sn, so, ops.opcodes, X, oracle.DEFAULT_FLAGS | oracle.ELEMENTWISE)
-    o = out.cpu().numpy()
     okh = ok.cpu().numpy().astype(bool)
-    _flags_agree(okh[sel], rok, rok_elem, "config2")
-    ref64, _ = oracle.eval_population(sn, so, ops.opcodes, X.astype(np.float64))
-    for i, t in enumerate(sel):
-        if rok[i]:
-            assert _relerr(o[t], ref[i]) <= max(1e-4, 30 * _relerr(ref[i], ref64[i]))
+    # (d) all 1 000 trees against the oracle (flags exactly, values in the classes of parity_util)
+    errs, ok_again = _check_population(oracle, nodes, offsets, ops, X, np.float32, label="C2 full size", pop=pop)
+    assert (ok_again == okh).all() and len(errs) > 600
     fin = torch.isfinite(out).all(dim=1).cpu().numpy()
     assert (okh <= fin).all()       # complete => every output finite
 

@@ -1,0 +1,254 @@
+"""GPU parity at BASELINE.json sizes, gradients of EVERY operator of include/dex_ops.def, and
+eval_diff populations — all against the CPU oracle, through the C ABI.  Needs a GPU (`-m gpu`).
+
+Sizes: C2 in full is in test_gpu_parity.py::test_full_size_config2_properties; here C3 (gradients
+of 250 of the C2 trees at the full 2^16 samples), one C4 shard shape (600 depth-12 trees, 10
+features, 2^14 samples), C5 (parametric, the full 2^18 samples on 250 of the 1 000 trees).  The
+oracle evaluates each of them in seconds on the box's host cores.
+"""
+import numpy as np
+import pytest
+
+import dexb200
+from dexb200 import device as D
+from dexb200 import treegen
+from tests.parity_util import FAILED, RTOL, check_trees, part_verdict, relerr, same_nonfinite, tree_verdict
+from tests.test_gpu_parity import _check_population, _flags_agree, _grad_verdict, _subset
+
+pytestmark = pytest.mark.gpu
+
+
+def _grad_yardsticks(oracle, nodes, offsets, ops, X, mode):
+    """The oracle's (value, gradient) under the conditioning perturbations of tests/parity_util.py:
+    X one ulp up / down, Float64 arithmetic (Float32 inputs only), every transcendental result one
+    ulp up / down."""
+    dtype = X.dtype.type
+    ys = []
+    for direction in (np.inf, -np.inf):
+        r, g, _ = oracle.eval_grad_population(nodes, offsets, ops.opcodes, np.nextafter(X, dtype(direction)), mode)
+        ys.append((r, g))
+    if dtype == np.float32:
+        r, g, _ = oracle.eval_grad_population(nodes, offsets, ops.opcodes, X.astype(np.float64), mode)
+        ys.append((r, g))
+    for n in (1, -1):
+        try:
+            oracle.set_ulp_nudge(n)
+            r, g, _ = oracle.eval_grad_population(nodes, offsets, ops.opcodes, X, mode)
+        finally:
+            oracle.set_ulp_nudge(0)
+        ys.append((r, g))
+    return ys
+
+
+# ---------------------------------------------------------------------------------------
+# BASELINE.json sizes
+# ---------------------------------------------------------------------------------------
+def test_config3_gradients_at_full_sample_count(oracle):
+    """configs[2]: eval_grad_tree_array d/dX on the C2 population, 2^16 samples; every 4th tree."""
+    ops = dexb200.OperatorEnum(treegen.OPSET_A)
+    nodes, offsets = treegen.gen_population(1000, 8, 2, 4, 5, seed=0)
+    sn, so = _subset(nodes, offsets, np.arange(0, 1000, 4))
+    N = 1 << 16
+    X = np.random.default_rng(0).standard_normal((5, N)).astype(np.float32)
+    pop = D.Population(None, ops, np.float32, wire=(sn, so))
+    out, grad, off, ok = pop.eval_grad(X, D.GRAD_FEATURES)
+    out, grad, ok = out.cpu().numpy(), grad.cpu().numpy(), ok.cpu().numpy().astype(bool)
+    mode = oracle.GRAD_FEATURES
+    ref, rgrads, rok = oracle.eval_grad_population(sn, so, ops.opcodes, X, mode)
+    _, _, rok_elem = oracle.eval_grad_population(sn, so, ops.opcodes, X, mode | oracle.GRAD_ELEMENTWISE)
+    _flags_agree(ok, rok, rok_elem, "C3")
+    yards = _grad_yardsticks(oracle, sn, so, ops, X, mode)
+    verdicts = []
+    for t in np.nonzero(rok)[0]:
+        g = grad[off[t]:off[t + 1]].reshape(N, 5).T
+        verdicts.append(_grad_verdict(np.float32, out[t], g, ref[t], rgrads[t], [(y[t], yg[t]) for y, yg in yards]))
+    st = check_trees("C3 full sample count (250 trees x 2^16)", np.float32, verdicts, min_strict=0.75,
+                     ids=[int(t) for t in np.nonzero(rok)[0]])
+    assert st["n_complete"] > 100
+
+
+def test_config4_shard_shape(oracle):
+    """configs[3]: depth-12 trees, 10 features; 600 trees x 2^14 samples of one shard."""
+    ops = dexb200.OperatorEnum(treegen.OPSET_A)
+    nodes, offsets = treegen.gen_population(600, 12, 2, 4, 10, seed=0)
+    X = np.random.default_rng(3).standard_normal((10, 1 << 14)).astype(np.float32)
+    errs, ok = _check_population(oracle, nodes, offsets, ops, X, np.float32, label="C4 shard shape (600 x 2^14)",
+                                 min_strict=0.65)      # depth-12 trees: more poles per tree
+    assert len(errs) > 100
+
+
+def test_config5_parametric_at_full_sample_count(oracle):
+    """configs[4]: ParametricExpression, 3 parameters x 10 classes, 2^18 samples; every 4th tree."""
+    ops = dexb200.OperatorEnum(treegen.OPSET_A)
+    n_params, n_classes, F, N = 3, 10, 5, 1 << 18
+    nodes, offsets = treegen.gen_population(1000, 8, 2, 4, F, seed=0, n_params=n_params)
+    sn, so = _subset(nodes, offsets, np.arange(0, 1000, 4))
+    P_ = len(so) - 1
+    rng = np.random.default_rng(5)
+    X = rng.standard_normal((F, N)).astype(np.float32)
+    params = rng.standard_normal((P_, n_params, n_classes)).astype(np.float32)
+    cls0 = rng.integers(0, n_classes, N)
+    pop = D.Population(None, ops, np.float32, wire=(sn, so))
+    out, ok = pop.eval_parametric(X, params, cls0)
+    out, ok = out.cpu().numpy(), ok.cpu().numpy().astype(bool)
+    ref, rok = oracle.eval_parametric_population(sn, so, ops.opcodes, X, params, cls0)
+    _, rok_elem = oracle.eval_parametric_population(sn, so, ops.opcodes, X, params, cls0,
+                                                    oracle.DEFAULT_FLAGS | oracle.ELEMENTWISE)
+    _flags_agree(ok, rok, rok_elem, "C5")
+    yards = [oracle.eval_parametric_population(sn, so, ops.opcodes, X.astype(np.float64), params.astype(np.float64), cls0)[0]]
+    for direction in (np.inf, -np.inf):
+        yards.append(oracle.eval_parametric_population(sn, so, ops.opcodes, np.nextafter(X, np.float32(direction)), params, cls0)[0])
+    for n in (1, -1):
+        try:
+            oracle.set_ulp_nudge(n)
+            yards.append(oracle.eval_parametric_population(sn, so, ops.opcodes, X, params, cls0)[0])
+        finally:
+            oracle.set_ulp_nudge(0)
+    verdicts = [tree_verdict(np.float32, [(out[t], ref[t], [y[t] for y in yards])]) for t in np.nonzero(rok)[0]]
+    st = check_trees("C5 full sample count (250 trees x 2^18)", np.float32, verdicts, min_strict=0.8,
+                     ids=[int(t) for t in np.nonzero(rok)[0]])
+    assert st["n_complete"] > 80
+
+
+# ---------------------------------------------------------------------------------------
+# gradients of every operator of the table (the reference gets them from Zygote for ANY
+# operator, ext/DynamicExpressionsZygoteExt.jl:7-15, src/EvaluateDerivative.jl:340-365)
+# ---------------------------------------------------------------------------------------
+def _operator_trees(code, deg, dtype):
+    """Trees exercising operator index 1 of its degree in leaf / accumulator / constant / stack
+    forms.  Operator sets: {1: (op, 'cos'), 2: ('*', '+', op)} etc. built by the caller."""
+    N_ = dexb200.Node
+    x1, x2, x3 = (N_(feature=k, T=dtype) for k in (1, 2, 3))
+    c = lambda v: N_(val=v, T=dtype)
+    return N_, x1, x2, x3, c
+
+
+def _all_operator_cases(dtype):
+    """[(label, OperatorEnum, trees)] for every opcode of include/dex_ops.def."""
+    cases = []
+    for code, (sym, deg, name) in sorted(dexb200.OPCODE_INFO.items()):
+        N_, x1, x2, x3, c = _operator_trees(code, deg, dtype)
+        if deg == 1:
+            ops = dexb200.OperatorEnum({1: (name,), 2: ("*", "+")})
+            mul, add = 1, 2
+            inner = lambda: N_(mul, x1, x2)
+            trees = {"leaf": N_(1, x1), "acc": N_(1, inner()), "const": N_(add, x1, N_(1, c(0.7))),
+                     "acc+const": N_(1, N_(add, inner(), c(0.25))), "nested": N_(1, N_(1, x2)),
+                     "slot": N_(add, N_(1, inner()), N_(1, N_(add, x2, x3)))}
+        elif deg == 2:
+            base = ("*", "+")
+            ops = dexb200.OperatorEnum({2: base + (name,)}) if name not in base else dexb200.OperatorEnum({2: base})
+            op = (base + (name,)).index(name) + 1
+            mul, add = 1, 2
+            inner = lambda: N_(mul, x1, x2)
+            other = lambda: N_(add, x2, x3)
+            trees = {"RR": N_(op, x1, x2), "RR_same": N_(op, x1, x1), "AR": N_(op, inner(), x3), "RA": N_(op, x3, inner()),
+                     "AC": N_(op, inner(), c(1.5)), "CA": N_(op, c(0.75), inner()), "RC": N_(op, x1, c(2.5)),
+                     "CR": N_(op, c(2.5), x3), "CC": N_(add, x1, N_(op, c(0.5), c(1.5))),
+                     "slot_acc": N_(op, inner(), other()), "acc_slot": N_(op, other(), inner())}
+        else:
+            ops = dexb200.OperatorEnum({2: ("*", "+"), 3: (name,)})
+            mul, add = 1, 2
+            inner = lambda: N_(mul, x1, x2)
+            other = lambda: N_(add, x2, x3)
+            t = lambda a, b, cc: N_(op=1, children=(a, b, cc))
+            trees = {"leaves": t(x1, x2, x3), "ops": t(inner(), other(), N_(mul, x3, x1)),
+                     "mixed1": t(c(0.5), x2, inner()), "mixed2": t(inner(), c(1.25), x3),
+                     "mixed3": t(x3, other(), c(2.0)), "consts": N_(add, x1, t(c(0.5), c(0.25), c(1.5)))}
+        cases.append((sym, ops, trees))
+    return cases
+
+
+# input ranges chosen so that every operator has a range on which it is finite and smooth:
+# (0.1, 0.9): |x| < 1 for asin / acos / atanh, positive for log / sqrt;  (1.1, 2): acosh;
+# signed normal: the failure paths and sign-dependent branches
+X_RANGES = [("unit", lambda r, n: r.uniform(0.1, 0.9, (3, n))), ("above1", lambda r, n: r.uniform(1.1, 2.0, (3, n))),
+            ("normal", lambda r, n: r.standard_normal((3, n)))]
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("mode", ["features", "constants", "both"])
+def test_gradient_of_every_operator_in_the_table(dtype, mode, oracle):
+    """Every opcode of include/dex_ops.def x operand forms x gradient modes vs the oracle."""
+    omode = {"features": oracle.GRAD_FEATURES, "constants": oracle.GRAD_CONSTANTS, "both": oracle.GRAD_BOTH}[mode]
+    dmode = {"features": D.GRAD_FEATURES, "constants": D.GRAD_CONSTANTS, "both": D.GRAD_BOTH}[mode]
+    rng = np.random.default_rng(123)
+    N = 520
+    tol = 3e-5 if dtype == np.float32 else 1e-10
+    covered, never_ok = 0, []
+    n_strict = n_total = 0
+    for sym, ops, trees in _all_operator_cases(dtype):
+        labels = list(trees)
+        nodes, offsets = dexb200.to_wire_population([trees[k] for k in labels])
+        pop = D.Population(None, ops, dtype, wire=(nodes, offsets))
+        compared = set()
+        for rname, gen in X_RANGES:
+            X = gen(rng, N).astype(dtype)
+            out, grad, off, ok = pop.eval_grad(X, dmode)
+            out, grad, ok = out.cpu().numpy(), grad.cpu().numpy(), ok.cpu().numpy().astype(bool)
+            ref, rgrads, rok = oracle.eval_grad_population(nodes, offsets, ops.opcodes, X, omode)
+            _, _, rok_elem = oracle.eval_grad_population(nodes, offsets, ops.opcodes, X, omode | oracle.GRAD_ELEMENTWISE)
+            _flags_agree(ok, rok, rok_elem, f"{sym}/{rname}/{mode}")
+            yards = _grad_yardsticks(oracle, nodes, offsets, ops, X, omode)
+            for t in np.nonzero(rok)[0]:
+                G = rgrads[t].shape[0]
+                g = grad[off[t]:off[t + 1]].reshape(N, G).T
+                v = _grad_verdict(dtype, out[t], g, ref[t], rgrads[t], [(y[t], yg[t]) for y, yg in yards])
+                assert v[0] != FAILED, (sym, labels[t], rname, mode, v)
+                n_strict += v[0] == 0 and v[1] <= tol
+                n_total += 1
+                compared.add(labels[t])
+        if compared:
+            covered += 1
+        else:
+            never_ok.append(sym)
+    assert not never_ok, f"operators whose trees were never complete on any input range: {never_ok}"
+    assert covered == len(dexb200.OPCODE_INFO)
+    # the bulk agrees to a few ulp (not just the north_star tolerance)
+    assert n_strict >= 0.9 * n_total, (n_strict, n_total)
+
+
+# ---------------------------------------------------------------------------------------
+# eval_diff_tree_array for populations (src/EvaluateDerivative.jl:40-168): never checks,
+# so rows keep the Inf / NaN of the reference's arithmetic
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_eval_diff_population_matches_oracle(dtype, oracle):
+    spec = {1: ("cos", "exp", "sin", "sqrt", "log"), 2: ("+", "-", "*", "/")}
+    ops = dexb200.OperatorEnum(spec)
+    F, N, P_ = 4, 600, 160
+    nodes, offsets = treegen.gen_population(P_, 7, 5, 4, F, seed=77, dtype=dtype)
+    rng = np.random.default_rng(8)
+    X = rng.standard_normal((F, N)).astype(dtype)
+    X[1, 17] = np.inf
+    X[2, 99] = -np.inf
+    X[0, 300] = np.nan
+    X[3, 5] = 0.0
+    pop = D.Population(None, ops, dtype, wire=(nodes, offsets))
+    n_pattern = n_values = 0
+    for direction in range(F):
+        out, dout, ok = pop.eval_diff(X, direction)
+        out, dout, ok = out.cpu().numpy(), dout.cpu().numpy(), ok.cpu().numpy()
+        assert ok.all()                                    # eval_diff never reports failure (:68-85)
+        pairs = []
+        for t in range(P_):
+            w = nodes[offsets[t]:offsets[t + 1]]
+            ry, rd, rok = oracle.eval_diff_tree_array(w, ops.opcodes, X, direction)
+            assert rok
+            ry64, rd64, _ = oracle.eval_diff_tree_array(w, ops.opcodes, X.astype(np.float64), direction)
+            ryp, rdp, _ = oracle.eval_diff_tree_array(w, ops.opcodes, np.nextafter(X, dtype(np.inf)), direction)
+            # the non-finite pattern is part of the answer wherever the oracle's own pattern does not
+            # depend on the precision or on a 1-ulp nudge
+            stable = same_nonfinite(np.asarray(ry64, dtype=dtype), ry) and same_nonfinite(np.asarray(rd64, dtype=dtype), rd) \
+                and same_nonfinite(ryp, ry) and same_nonfinite(rdp, rd)
+            if stable:
+                assert same_nonfinite(out[t], ry), (t, direction, "value pattern")
+                assert same_nonfinite(dout[t], rd), (t, direction, "derivative pattern")
+                n_pattern += 1
+            fin = np.isfinite(ry) & np.isfinite(rd) & np.isfinite(out[t]) & np.isfinite(dout[t])
+            if not fin.any():
+                continue
+            pairs.append(tree_verdict(dtype, [(out[t], ry, (ry64, ryp), fin), (dout[t], rd, (rd64, rdp), fin)]))
+            n_values += 1
+        check_trees(f"eval_diff direction {direction} {np.dtype(dtype).name}", dtype, pairs, min_strict=0.8)
+    assert n_pattern > 2 * P_ and n_values > 2 * P_

@@ -125,3 +125,44 @@ def test_constant_numbering_is_leaf_order(oracle):
             else:
                 lo = v
         np.testing.assert_allclose(g[k], (hi - lo) / 2e-6, rtol=1e-5, atol=1e-6)
+
+
+def test_oracle_partials_match_finite_differences(oracle):
+    """The reference takes operator partials from Zygote (ext/DynamicExpressionsZygoteExt.jl:7-15),
+    i.e. the analytic derivative; the oracle's closed forms (dex_oracle_ops.inc) are pinned here
+    for EVERY opcode of include/dex_ops.def against central differences of the oracle's own
+    Float64 operator values at points where the operator is smooth."""
+    import dexb200
+    rng = np.random.default_rng(0)
+    # piecewise-constant operators: derivative 0 away from the jumps
+    flat = {"ROUND", "FLOOR", "CEIL", "TRUNC", "SIGN", "GREATER", "LESS", "LOGICAL_OR", "LOGICAL_AND",
+            "GREATER_EQ", "LESS_EQ"}
+    domains = {"ASIN": (-0.9, 0.9), "ACOS": (-0.9, 0.9), "ATANH": (-0.9, 0.9), "ACOSH": (1.2, 3.0),
+               "SAFE_ACOSH": (1.2, 3.0), "LOG": (0.2, 3.0), "LOG2": (0.2, 3.0), "LOG10": (0.2, 3.0),
+               "LOG1P": (-0.8, 3.0), "SAFE_LOG": (0.2, 3.0), "SAFE_LOG2": (0.2, 3.0), "SAFE_LOG10": (0.2, 3.0),
+               "SAFE_LOG1P": (-0.8, 3.0), "SQRT": (0.2, 3.0), "SAFE_SQRT": (0.2, 3.0), "POW": (0.3, 2.5),
+               "INV": (0.3, 2.5)}
+    n_checked = 0
+    for code, (sym, deg, name) in sorted(dexb200.OPCODE_INFO.items()):
+        lo, hi = domains.get(sym, (-2.0, 2.0))
+        for _ in range(40):
+            a = [float(v) for v in rng.uniform(lo, hi, 3)]
+            # keep away from kinks / jumps / poles of the piecewise operators
+            if min(abs(a[0] - a[1]), abs(a[1] - a[2]), abs(a[0] - a[2]), abs(a[0]), abs(a[1]), abs(a[2])) < 0.05:
+                continue
+            if sym in flat and any(abs(v - round(v)) < 0.05 for v in a):
+                continue
+            if sym in ("MOD",) and abs(a[0] / a[1] - round(a[0] / a[1])) < 0.05:
+                continue
+            if sym == "CLAMP" and not (a[1] < a[2]):
+                continue
+            g = oracle.partials(code, *a)
+            for k in range(deg):
+                h = 1e-6
+                p, m = list(a), list(a)
+                p[k] += h
+                m[k] -= h
+                fd = (oracle.apply(code, *p) - oracle.apply(code, *m)) / (2 * h)
+                assert abs(g[k] - fd) <= 1e-6 * max(1.0, abs(fd)) + 1e-7, (sym, k, a, g[k], fd)
+            n_checked += 1
+    assert n_checked > 30 * len(dexb200.OPCODE_INFO) * 0.5
