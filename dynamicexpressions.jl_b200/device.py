@@ -426,6 +426,21 @@ class Population:
                                                  EVAL_EARLY_EXIT if early_exit else 0))
         return out, ok
 
+    def eval_parametric_prepared(self, X, params_cm, classes_i32, n_params, n_classes, *, early_exit=True,
+                                 out=None, ok=None):
+        """As :meth:`eval_parametric` for callers that keep their arguments in the library's own
+        layout on the device (no per-call conversion or range check): ``params_cm`` is the
+        per-tree column-major (P, n_classes, n_params) block, ``classes_i32`` the 0-based int32
+        class of every sample (the caller guarantees 0 <= class < n_classes)."""
+        Xd, F, N, ldx = as_device_matrix(X, self.ctx.device, self.dtype_code)
+        out, ok = self._outputs(N, out, ok)
+        self.ctx.use_current_stream()
+        self.ctx.check(lib().dex_eval_parametric(self.ctx.h, self.h, _ptr(Xd), F, N, ldx, _ptr(params_cm),
+                                                 int(n_params), int(n_classes), _ptr(classes_i32), _ptr(out),
+                                                 out.stride(0) if self.n_trees else N, _ptr(ok),
+                                                 EVAL_EARLY_EXIT if early_exit else 0))
+        return out, ok
+
     def grad_offsets(self, F, N, mode):
         off = np.zeros(self.n_trees + 1, dtype=np.int64)
         rc = lib().dex_grad_offsets(self.h, F, N, mode, _ptr(off))

@@ -42,22 +42,46 @@ class _OpTable(C.Structure):
 
 
 _lib = None
+_flags = "gcc -O3 -march=x86-64-v3 (AVX2) -ffp-contract=off -fopenmp"
+
+
+def use_native_build():
+    """Switch to a `-march=native` build made on THIS machine (bench.py's CPU-baseline legs: the
+    timed stand-in should use the host's full vector width).  Falls back to the portable
+    x86-64-v3 build when gcc is missing or the build fails.  Returns the flags in use."""
+    global _lib, _flags
+    out = os.path.join(_HERE, "_build", "libdexoracle_native.so")
+    try:
+        subprocess.check_call(["make", "-C", _HERE, "-s", "-B", "MARCH=native", "OUT=_build/libdexoracle_native.so"],
+                              stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        native = C.CDLL(out)
+        _lib = None
+        _bind(native)
+        _lib = native
+        _flags = "gcc -O3 -march=native -ffp-contract=off -fopenmp, built on this host"
+    except Exception:
+        pass
+    return _flags
+
+
+def _bind(l):
+    l.dexo_apply_f64.restype = C.c_double
+    l.dexo_apply_f64.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double]
+    l.dexo_apply_f32.restype = C.c_float
+    l.dexo_apply_f32.argtypes = [C.c_int, C.c_float, C.c_float, C.c_float]
+    l.dexo_partials_f64.restype = None
+    l.dexo_partials_f64.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, C.POINTER(C.c_double)]
+    l.dexo_count_constants.restype = C.c_int32
+    l.dexo_count_constants.argtypes = [C.c_void_p, C.c_int64]
 
 
 def lib():
     global _lib
     if _lib is None:
         build()
-        _lib = C.CDLL(_SO)
-        _lib.dexo_apply_f64.restype = C.c_double
-        _lib.dexo_apply_f64.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double]
-        _lib.dexo_apply_f32.restype = C.c_float
-        _lib.dexo_apply_f32.argtypes = [C.c_int, C.c_float, C.c_float, C.c_float]
-        _lib.dexo_partials_f64.restype = None
-        _lib.dexo_partials_f64.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double,
-                                           C.POINTER(C.c_double)]
-        _lib.dexo_count_constants.restype = C.c_int32
-        _lib.dexo_count_constants.argtypes = [C.c_void_p, C.c_int64]
+        l = C.CDLL(_SO)
+        _bind(l)
+        _lib = l
     return _lib
 
 
