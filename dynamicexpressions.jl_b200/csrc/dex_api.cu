@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <new>
 #include <string>
 #include <type_traits>
@@ -68,14 +69,67 @@ struct dex_population {
     // all device arrays above live in ONE allocation (eleven cudaMalloc/cudaFree pairs per packed
     // population cost more than flattening it): d_blob owns, the typed pointers are views
     void* d_blob = nullptr;
-    uint8_t* d_fold_ok[2] = {nullptr, nullptr};
+    size_t blob_cap = 0;
+    uint8_t* d_fold_ok[2] = {nullptr, nullptr};   // views into d_blob
     bool fold_valid[2] = {false, false};
-    std::map<int32_t, int32_t*> chunk_tables;  // n_chunks -> device table
+    // tree-chunk tables (n_chunks + 1 tree indices, balanced by tape length): two slots inside
+    // d_blob, keyed by n_chunks; a third key overwrites the older slot (stream-ordered upload)
+    int32_t* d_chunk_slot[2] = {nullptr, nullptr};
+    int32_t chunk_key[2] = {-1, -1};
+    int chunk_next = 0;
     std::map<int32_t, std::vector<int32_t>> chunk_tables_host;
-    std::map<std::string, int64_t*> grad_off_tables;
 };
 
 namespace {
+
+// ---- device block pool -------------------------------------------------------------------------
+// cudaMalloc / cudaFree cost 0.1 - 5 ms each (mapping and unmapping physical memory, an implicit
+// device synchronisation) — more than flattening a 1 000-tree population.  Callers whose trees
+// change every generation pack and destroy populations continuously, so population storage comes
+// from a per-device free list of blocks that is never returned to the driver below a cap.
+struct DevPool {
+    std::mutex m;
+    std::multimap<size_t, void*> free_blocks;   // capacity -> block
+    size_t cached = 0;
+};
+constexpr int kMaxDevices = 64;
+constexpr size_t kPoolCap = (size_t)1 << 30;    // bytes kept per device
+DevPool g_pool[kMaxDevices];
+
+size_t pool_round(size_t bytes) {   // 64 KiB granules up to 1 MiB, then 1 MiB granules
+    const size_t g = bytes <= ((size_t)1 << 20) ? ((size_t)64 << 10) : ((size_t)1 << 20);
+    return ((std::max<size_t>(bytes, 1) + g - 1) / g) * g;
+}
+cudaError_t pool_alloc(int dev, size_t bytes, void** out, size_t* cap) {
+    *cap = pool_round(bytes);
+    if (dev >= 0 && dev < kMaxDevices) {
+        DevPool& p = g_pool[dev];
+        std::lock_guard<std::mutex> lk(p.m);
+        auto it = p.free_blocks.lower_bound(*cap);
+        if (it != p.free_blocks.end() && it->first <= 2 * *cap + ((size_t)1 << 20)) {
+            *out = it->second;
+            *cap = it->first;
+            p.cached -= it->first;
+            p.free_blocks.erase(it);
+            return cudaSuccess;
+        }
+    }
+    return cudaMalloc(out, *cap);
+}
+// the caller guarantees that no device work still uses the block
+void pool_free(int dev, void* ptr, size_t cap) {
+    if (!ptr) return;
+    if (dev >= 0 && dev < kMaxDevices) {
+        DevPool& p = g_pool[dev];
+        std::lock_guard<std::mutex> lk(p.m);
+        if (p.cached + cap <= kPoolCap) {
+            p.free_blocks.emplace(cap, ptr);
+            p.cached += cap;
+            return;
+        }
+    }
+    cudaFree(ptr);
+}
 
 int set_err(dex_ctx* ctx, int code, const std::string& msg) {
     if (ctx) ctx->last_error = msg;
@@ -187,16 +241,19 @@ int upload_population(dex_ctx* ctx, dex_population* pop) {
     struct Item { void** dst; const void* src; size_t bytes, padded, off; };
     std::vector<Item> items;
     size_t total = 0;
-    auto add = [&](auto** dptr, const auto& vec) {
-        using U = typename std::remove_reference<decltype(vec)>::type::value_type;
+    auto add_raw = [&](void** dptr, const void* src, size_t bytes, size_t elems, size_t esz) {
         Item it;
-        it.dst = reinterpret_cast<void**>(dptr);
-        it.src = vec.data();
-        it.bytes = vec.size() * sizeof(U);
-        it.padded = (((std::max<size_t>(vec.size(), 1) + 64) * sizeof(U)) + 255) & ~(size_t)255;
+        it.dst = dptr;
+        it.src = src;
+        it.bytes = bytes;
+        it.padded = (((std::max<size_t>(elems, 1) + 64) * esz) + 255) & ~(size_t)255;
         it.off = total;
         total += it.padded;
         items.push_back(it);
+    };
+    auto add = [&](auto** dptr, const auto& vec) {
+        using U = typename std::remove_reference<decltype(vec)>::type::value_type;
+        add_raw(reinterpret_cast<void**>(dptr), vec.data(), vec.size() * sizeof(U), vec.size(), sizeof(U));
     };
     add(&pop->d_tape, h.tape);
     add(&pop->d_tape_off, h.tape_off);
@@ -209,39 +266,52 @@ int upload_population(dex_ctx* ctx, dex_population* pop) {
     add(&pop->d_ctape, f.ctape);
     add(&pop->d_seg, f.seg);
     add(&pop->d_seg_off, f.seg_off);
-    CU(ctx, cudaMalloc(&pop->d_blob, total));
+    const size_t uploaded = total;     // everything above is copied from the host image
+    const size_t nt = (size_t)h.n_trees;
+    for (int k = 0; k < 2; ++k) add_raw(reinterpret_cast<void**>(&pop->d_fold_ok[k]), nullptr, 0, nt, 1);
+    for (int k = 0; k < 2; ++k) add_raw(reinterpret_cast<void**>(&pop->d_chunk_slot[k]), nullptr, 0, nt + 1, sizeof(int32_t));
+    cudaError_t e = pool_alloc(ctx->device, total, &pop->d_blob, &pop->blob_cap);
+    if (e != cudaSuccess) { cudaGetLastError(); return set_err(ctx, DEX_ERR_NOMEM, std::string("population storage: ") + cudaGetErrorString(e)); }
+    // one pinned staging image, one copy
+    int rc = ensure_pinned(ctx, uploaded);
+    if (rc) return rc;
+    char* stage = static_cast<char*>(ctx->pinned);
     for (const Item& it : items) {
         *it.dst = static_cast<char*>(pop->d_blob) + it.off;
-        if (it.bytes) CU(ctx, cudaMemcpyAsync(*it.dst, it.src, it.bytes, cudaMemcpyHostToDevice, ctx->stream));
+        if (it.bytes) std::memcpy(stage + it.off, it.src, it.bytes);
     }
+    if (uploaded) CU(ctx, cudaMemcpyAsync(pop->d_blob, stage, uploaded, cudaMemcpyHostToDevice, ctx->stream));
     return DEX_OK;
 }
 
 // tree-index ranges with balanced tape length
 int chunk_table(dex_ctx* ctx, dex_population* pop, int32_t n_chunks, const int32_t** out) {
-    const int32_t key = n_chunks;
-    auto it = pop->chunk_tables.find(key);
-    if (it != pop->chunk_tables.end()) { *out = it->second; return DEX_OK; }
-    const PackedPopulation& h = *pop->h.folded;
-    std::vector<int32_t> tab((size_t)n_chunks + 1, 0);
-    // cost of trees [0, t) = tape instructions + a fixed per-tree cost of one
-    const std::vector<int64_t>& toff = h.tape_off;
-    auto cum = [&](int64_t t) { return toff[(size_t)t] + t; };
-    const int64_t total = cum(h.n_trees);
-    int64_t t = 0;
-    for (int32_t c = 1; c < n_chunks; ++c) {
-        const int64_t target = (total * c) / n_chunks;
-        while (t < h.n_trees && cum(t) < target) ++t;
-        tab[c] = (int32_t)t;
+    for (int k = 0; k < 2; ++k)
+        if (pop->chunk_key[k] == n_chunks) { *out = pop->d_chunk_slot[k]; return DEX_OK; }
+    std::vector<int32_t>& tab = pop->chunk_tables_host[n_chunks];
+    if (tab.empty()) {
+        const PackedPopulation& h = *pop->h.folded;
+        tab.assign((size_t)n_chunks + 1, 0);
+        // cost of trees [0, t) = tape instructions + a fixed per-tree cost of one
+        const std::vector<int64_t>& toff = h.tape_off;
+        auto cum = [&](int64_t t) { return toff[(size_t)t] + t; };
+        const int64_t total = cum(h.n_trees);
+        int64_t t = 0;
+        for (int32_t c = 1; c < n_chunks; ++c) {
+            const int64_t target = (total * c) / n_chunks;
+            while (t < h.n_trees && cum(t) < target) ++t;
+            tab[c] = (int32_t)t;
+        }
+        tab[n_chunks] = (int32_t)h.n_trees;
     }
-    tab[n_chunks] = (int32_t)h.n_trees;
-    int32_t* d = nullptr;
-    CU(ctx, cudaMalloc(reinterpret_cast<void**>(&d), tab.size() * sizeof(int32_t)));
-    CU(ctx, cudaMemcpyAsync(d, tab.data(), tab.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
-    CU(ctx, cudaStreamSynchronize(ctx->stream));  // tab is a stack temporary
-    pop->chunk_tables[key] = d;
-    pop->chunk_tables_host[key] = tab;
-    *out = d;
+    const int slot = pop->chunk_next;
+    pop->chunk_next ^= 1;
+    // pageable source: the runtime stages it before returning, and the copy is ordered on the
+    // stream behind any kernel that still reads the slot's previous table
+    CU(ctx, cudaMemcpyAsync(pop->d_chunk_slot[slot], tab.data(), tab.size() * sizeof(int32_t), cudaMemcpyHostToDevice,
+                            ctx->stream));
+    pop->chunk_key[slot] = n_chunks;
+    *out = pop->d_chunk_slot[slot];
     return DEX_OK;
 }
 
@@ -267,8 +337,6 @@ int ensure_folded(dex_ctx* ctx, dex_population* pop, int rule, const uint8_t** f
     *fold_ok = nullptr;
     const PackedPopulation& f = *pop->h.folded;
     if (f.seg.empty()) return DEX_OK;          // nothing to fold: the prepass presets ok[] = 1
-    if (!pop->d_fold_ok[rule])
-        CU(ctx, cudaMalloc(reinterpret_cast<void**>(&pop->d_fold_ok[rule]), (size_t)std::max<int64_t>(f.n_trees, 1)));
     if (!pop->fold_valid[rule]) {
         cudaError_t e = launch_fold(f.dtype, rule == 1, pop->d_ftape, pop->d_ctape, pop->d_seg, pop->d_seg_off,
                                     f.n_trees, pop->d_fold_ok[rule], ctx->stream);
@@ -548,10 +616,10 @@ int dex_population_destroy(dex_population* pop) {
     if (!pop) return DEX_OK;
     if (pop->device >= 0) {
         cudaSetDevice(pop->device);
-        cudaFree(pop->d_blob);
-        cudaFree(pop->d_fold_ok[0]); cudaFree(pop->d_fold_ok[1]);
-        for (auto& kv : pop->chunk_tables) cudaFree(kv.second);
-        for (auto& kv : pop->grad_off_tables) cudaFree(kv.second);
+        // as cudaFree would: nothing on the device still reads the tapes once this returns, so the
+        // block can be handed to the next population straight away
+        if (pop->d_blob) cudaDeviceSynchronize();
+        pool_free(pop->device, pop->d_blob, pop->blob_cap);
     }
     delete pop;
     return DEX_OK;

@@ -163,6 +163,11 @@ template <int K> struct VOp1<DEX_OP_COS, float, K> {
 };
 #endif
 
+// operand positions of the specialised binary handlers whose feature ROW may carry a check flag
+// (dex_flatten.cpp pick_handler): the divisor of /, either operand of max / min
+template <int OPC> struct RowChk { static constexpr bool a = OPC == DEX_OP_MAX || OPC == DEX_OP_MIN;
+                                   static constexpr bool b = a || OPC == DEX_OP_DIV; };
+
 template <typename T> __device__ __forceinline__ T const_of(const uint4& ins);
 template <> __device__ __forceinline__ float const_of<float>(const uint4& ins) { return __uint_as_float(ins.z); }
 template <> __device__ __forceinline__ double const_of<double>(const uint4& ins) { return __hiloint2double((int)ins.w, (int)ins.z); }
@@ -357,7 +362,7 @@ __global__ void __launch_bounds__(DEX_MAX_THREADS, DEX_MIN_CTAS) eval_kernel(con
                 case H_LOAD_C: {
 #pragma unroll
                     for (int k = 0; k < K; ++k) acc.v[k] = c;
-                    if (w0 & F_CHK_CONST) nf[0] = m_fma(c, T(0), nf[0]);
+                    if (w0 & F_CHK_A) nf[0] = m_fma(c, T(0), nf[0]);
                 } HANDLER_END
 #define UNARY_HANDLERS(S)                                                          \
     case H_##S##_A: {                                                              \
@@ -375,22 +380,24 @@ __global__ void __launch_bounds__(DEX_MAX_THREADS, DEX_MIN_CTAS) eval_kernel(con
     case H_##S##_AR: {                                                             \
         V y;                                                                       \
         ld_row<T, U>(y, rb, CS);                                                   \
+        if (RowChk<DEX_OP_##S>::b && (w0 & F_CHK_B)) check<T, U>(nf, y);           \
         VOp2<DEX_OP_##S, T, K>::f(acc.v, acc.v, y.v);                              \
     } HANDLER_END
 #define BIN_RA(S)                                                                  \
     case H_##S##_RA: {                                                             \
         V x;                                                                       \
         ld_row<T, U>(x, ra, CS);                                                   \
+        if (RowChk<DEX_OP_##S>::a && (w0 & F_CHK_A)) check<T, U>(nf, x);           \
         VOp2<DEX_OP_##S, T, K>::f(acc.v, x.v, acc.v);                              \
     } HANDLER_END
 #define BIN_AC(S)                                                                  \
     case H_##S##_AC: {                                                             \
-        if (w0 & F_CHK_CONST) nf[0] = m_fma(c, T(0), nf[0]);                       \
+        if (w0 & F_CHK_B) nf[0] = m_fma(c, T(0), nf[0]);                           \
         VOp2<DEX_OP_##S, T, K>::f(acc.v, acc.v, cv.v);                             \
     } HANDLER_END
 #define BIN_CA(S)                                                                  \
     case H_##S##_CA: {                                                             \
-        if (w0 & F_CHK_CONST) nf[0] = m_fma(c, T(0), nf[0]);                       \
+        if (w0 & F_CHK_A) nf[0] = m_fma(c, T(0), nf[0]);                           \
         VOp2<DEX_OP_##S, T, K>::f(acc.v, cv.v, acc.v);                             \
     } HANDLER_END
 #define BIN_RR(S)                                                                  \
@@ -398,20 +405,24 @@ __global__ void __launch_bounds__(DEX_MAX_THREADS, DEX_MIN_CTAS) eval_kernel(con
         V x, y;                                                                    \
         ld_row<T, U>(x, ra, CS);                                                   \
         ld_row<T, U>(y, rb, CS);                                                   \
+        if (RowChk<DEX_OP_##S>::a && (w0 & F_CHK_A)) check<T, U>(nf, x);           \
+        if (RowChk<DEX_OP_##S>::b && (w0 & F_CHK_B)) check<T, U>(nf, y);           \
         VOp2<DEX_OP_##S, T, K>::f(acc.v, x.v, y.v);                                \
     } HANDLER_END
 #define BIN_RC(S)                                                                  \
     case H_##S##_RC: {                                                             \
         V x;                                                                       \
         ld_row<T, U>(x, ra, CS);                                                   \
-        if (w0 & F_CHK_CONST) nf[0] = m_fma(c, T(0), nf[0]);                       \
+        if (RowChk<DEX_OP_##S>::a && (w0 & F_CHK_A)) check<T, U>(nf, x);           \
+        if (w0 & F_CHK_B) nf[0] = m_fma(c, T(0), nf[0]);                           \
         VOp2<DEX_OP_##S, T, K>::f(acc.v, x.v, cv.v);                               \
     } HANDLER_END
 #define BIN_CR(S)                                                                  \
     case H_##S##_CR: {                                                             \
         V y;                                                                       \
         ld_row<T, U>(y, rb, CS);                                                   \
-        if (w0 & F_CHK_CONST) nf[0] = m_fma(c, T(0), nf[0]);                       \
+        if (w0 & F_CHK_A) nf[0] = m_fma(c, T(0), nf[0]);                           \
+        if (RowChk<DEX_OP_##S>::b && (w0 & F_CHK_B)) check<T, U>(nf, y);           \
         VOp2<DEX_OP_##S, T, K>::f(acc.v, cv.v, y.v);                               \
     } HANDLER_END
 #define COMM_HANDLERS(S) BIN_AR(S) BIN_AC(S) BIN_RR(S) BIN_RC(S)

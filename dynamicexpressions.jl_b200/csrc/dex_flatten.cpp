@@ -465,7 +465,11 @@ struct Flattener {
             }
         }
         if (deg == 2) {
-            if (a_chk_row || b_chk_row) return H_GENERIC;  // checked feature operand of a binary op: rare
+            // a checked feature operand: only positions that can hide a non-finite value keep the
+            // flag (the divisor of /, either operand of max / min, ...); the specialised handlers
+            // of / max min test it, any other operator takes the generic handler
+            if (a_chk_row && !(e.op == DEX_OP_MAX || e.op == DEX_OP_MIN)) return H_GENERIC;
+            if (b_chk_row && !(e.op == DEX_OP_DIV || e.op == DEX_OP_MAX || e.op == DEX_OP_MIN)) return H_GENERIC;
             switch (e.op) {
 #define X(S)                                                              \
     case DEX_OP_##S:                                                      \
@@ -540,7 +544,7 @@ struct Flattener {
             if (swapped && (e.op == DEX_OP_MAX || e.op == DEX_OP_MIN)) ins.w0 |= F_SWAPPED;
             if (e.a.chk) ins.w0 |= F_CHK_A;
             if (e.b.chk) ins.w0 |= F_CHK_B;
-            if ((e.a.chk && e.a.src == SRC_CONST) || (e.b.chk && e.b.src == SRC_CONST)) ins.w0 |= F_CHK_CONST;
+            if (e.flags & F_CHK_OUT) ins.w0 |= HANDLER_CHK;
             if (e.push_slot >= 0) ins.w0 |= F_PUSH | HANDLER_PUSH | ((uint32_t)e.push_slot << PUSH_ROW_SHIFT);
             // feature and parameter rows are rebased behind the stack rows once max_stack is known
             uint32_t ra = e.a.row, rb = e.b.row;

@@ -80,12 +80,52 @@ template <int QADD> __device__ __forceinline__ float fast_sincosf(float x) {
     const unsigned par = (__float_as_uint(m) & 1u) ^ (QADD ? 1u : 0u);
     return __uint_as_float(__float_as_uint(sp) ^ (par << 31));
 }
+// Arguments beyond the Cody-Waite range (|x| > 105615) up to 2^48, and +-Inf: reduction in DOUBLE
+// (x is exact in double; q = rint(x 2/pi) by the 1.5 * 2^52 magic number, whose low word is q mod
+// 2^32; r = x - q pi/2 with pi/2 in two doubles, error < 1e-17 for |q| < 2^48), then the classic
+// sine / cosine kernels on [-pi/4, pi/4] chosen by the quadrant.  Branch-free and convergent: the
+// CUDA library's Payne-Hanek path, taken lane by lane, cost ~10 % of a whole population launch
+// (cos(exp(...)) reaches such arguments in a few percent of the warps).  Inf gives NaN.  The packed
+// PTX forms (gen_interp_ptx.py `sincos_medium`) are operation-for-operation identical.
+template <int QADD> __device__ __forceinline__ float medium_sincosf(float x) {
+    const double xd = (double)x;
+    const double t = fma(xd, 0.63661977236758138, 6755399441055744.0);
+    const int lo = __double2loint(t);
+    const double qd = t - 6755399441055744.0;
+    double r = fma(qd, -1.5707963267948966, xd);
+    r = fma(qd, -6.123233995736766e-17, r);
+    const float rf = (float)r;
+    const float z = rf * rf;
+    float sp = fmaf(z, -1.9515295891e-4f, 8.3321608736e-3f);
+    sp = fmaf(sp, z, -1.6666654611e-1f);
+    sp = sp * z;
+    sp = fmaf(sp, rf, rf);
+    float cp = fmaf(z, 2.443315711809948e-5f, -1.388731625493765e-3f);
+    cp = fmaf(cp, z, 4.166664568298827e-2f);
+    cp = cp * z;
+    const float t2 = fmaf(z, -0.5f, 1.0f);
+    cp = fmaf(cp, z, t2);
+    const int n = lo + QADD;
+    const float v = (n & 1) ? cp : sp;
+    return __uint_as_float(__float_as_uint(v) ^ (((unsigned)n & 2u) << 30));
+}
+// 2^48 < |x| < Inf: the library (Payne-Hanek)
+__device__ __forceinline__ bool sincos_needs_library(float x) {
+    const float a = fabsf(x);
+    return a > 281474976710656.0f && a < CUDART_INF_F;
+}
 __device__ __forceinline__ float m_sin(float x) {
-    if (fabsf(x) > 105615.0f) return slow_sinf(x);   // false for NaN: the fast path propagates it
+    if (fabsf(x) > 105615.0f) {   // false for NaN: the fast path propagates it
+        if (sincos_needs_library(x)) return slow_sinf(x);
+        return medium_sincosf<0>(x);
+    }
     return fast_sincosf<0>(x);
 }
 __device__ __forceinline__ float m_cos(float x) {
-    if (fabsf(x) > 105615.0f) return slow_cosf(x);
+    if (fabsf(x) > 105615.0f) {
+        if (sincos_needs_library(x)) return slow_cosf(x);
+        return medium_sincosf<1>(x);
+    }
     return fast_sincosf<1>(x);
 }
 __device__ __forceinline__ double m_sin(double x) { return slow_sin(x); }

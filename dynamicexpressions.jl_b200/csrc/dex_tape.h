@@ -29,12 +29,9 @@ namespace dex {
 // ---- evaluation tape -------------------------------------------------------------
 // 16 bytes, fetched as one uint4 (x=w0, y=w1, z/w = constant).
 //   w0 [ 5: 0] handler  HANDLER id (H_*), 0 = generic
-//      [ 6]    copy of PUSH: the Float32 jump table has one entry per (handler, PUSH)
+//      [ 6]    copy of PUSH: the Float32 jump tables have one entry per (handler, PUSH)
 //              so that the push costs nothing when it does not happen
-//      [ 7]    SWAPPED  the flattener exchanged the operands of max / min (to reach an
-//              (ACC|ROW, ROW|CONST) handler form): values are symmetric, but the reference's
-//              partials (x > y, !(x > y)) break ties by operand ORDER, so the gradient
-//              interpreters apply them to the original order
+//      [ 7]    copy of CHK_OUT (reserved for a table variant; see gen_interp_ptx.py)
 //      [15: 8] opcode   builtin opcode of include/dex_ops.def (IDENTITY doubles as LOAD)
 //      [17:16] srcA     SRC_*
 //      [19:18] srcB     SRC_*   (ternary: third operand is always ACC)
@@ -46,8 +43,11 @@ namespace dex {
 //                       folding, /root/reference/src/Evaluate.jl:1059-1067)
 //      [25]    GUARD    unary: result = isfinite(arg) ? op(arg) : Inf
 //                       (/root/reference/src/Evaluate.jl:722, 737, 754, 787)
-//      [26]    CHK_CONST  the inline constant participates (= CHK_A/CHK_B of the
-//                       constant operand; what the specialised handlers test)
+//      [26]    SWAPPED  the flattener exchanged the operands of max / min (to reach an
+//                       (ACC|ROW, ROW|CONST) handler form): values are symmetric, but the
+//                       reference's partials (x > y, !(x > y)) break ties by operand ORDER, so
+//                       the gradient interpreters apply them to the original order
+//      CHK_A / CHK_B apply to whatever the operand is: a feature ROW or the inline constant
 //      [31:27] push_row  stack slot the PUSH stores to (a tree of n nodes needs about
 //                       log2(n) slots in Sethi-Ullman order, so five bits are ample)
 //   w1 [15: 0] rowA  (ROW: smem row; PARAM: parameter index)
@@ -63,14 +63,13 @@ static_assert(sizeof(Instr) == 16, "tape instruction must be 16 bytes");
 
 enum : uint32_t { SRC_ACC = 0, SRC_ROW = 1, SRC_CONST = 2, SRC_PARAM = 3 };
 enum : uint32_t {
-    F_SWAPPED = 1u << 7,
     F_PUSH = 1u << 20,
     F_CHK_OUT = 1u << 21,
     F_CHK_A = 1u << 22,
     F_CHK_B = 1u << 23,
     F_ALWAYS = 1u << 24,
     F_GUARD = 1u << 25,
-    F_CHK_CONST = 1u << 26,
+    F_SWAPPED = 1u << 26,
 };
 constexpr int MAX_STACK_ROWS = 31;   // push_row is 5 bits
 constexpr int MAX_ROWS = 65535;      // row fields are 16 bits
@@ -108,7 +107,7 @@ enum Handler : uint32_t {
 #undef X
     H__COUNT
 };
-constexpr uint32_t HANDLER_MASK = 63u, HANDLER_PUSH = 64u;
+constexpr uint32_t HANDLER_MASK = 63u, HANDLER_PUSH = 64u, HANDLER_CHK = 128u;
 static_assert(H__COUNT <= HANDLER_PUSH - 1, "handler ids must fit six bits (one slot is reserved)");
 
 // ---- host-side description of a packed population ----------------------------------

@@ -13,8 +13,7 @@ from dexb200 import device as D
 from oracle.oracle import _np_ops
 
 SRC_ACC, SRC_ROW, SRC_CONST, SRC_PARAM = 0, 1, 2, 3
-F_PUSH, F_CHK_OUT, F_CHK_A, F_CHK_B, F_ALWAYS, F_GUARD, F_CHK_CONST = (1 << 20, 1 << 21, 1 << 22,
-                                                                        1 << 23, 1 << 24, 1 << 25, 1 << 26)
+F_PUSH, F_CHK_OUT, F_CHK_A, F_CHK_B, F_ALWAYS, F_GUARD = (1 << 20, 1 << 21, 1 << 22, 1 << 23, 1 << 24, 1 << 25)
 
 
 def handler_name(h):
@@ -47,6 +46,8 @@ def run_tape(ins, X, max_stack, opcode_info, dtype, early_exit=True, params=None
     for w in ins:
         w0, w1 = int(w[0]), int(w[1])
         rowA, rowB, push_row = w1 & 0xFFFF, w1 >> 16, w0 >> 27
+        # the jump-table variant bits mirror the flags (csrc/dex_tape.h)
+        assert bool(w0 & 64) == bool(w0 & F_PUSH) and bool(w0 & 128) == bool(w0 & F_CHK_OUT)
         if w0 & F_PUSH:
             rows[push_row] = acc
         c = const_of(w)
@@ -60,7 +61,7 @@ def run_tape(ins, X, max_stack, opcode_info, dtype, early_exit=True, params=None
                 va = rows[rowA].copy() if pat == "R" else cvec
                 if pat == "R" and (w0 & F_CHK_A) and bad(va):
                     ok = False
-                if pat == "C" and (w0 & F_CHK_CONST) and bad(cvec):
+                if pat == "C" and (w0 & F_CHK_A) and bad(cvec):
                     ok = False
                 assert opcode_info[code][0] == "IDENTITY"
                 r = va
@@ -78,12 +79,16 @@ def run_tape(ins, X, max_stack, opcode_info, dtype, early_exit=True, params=None
                 else:
                     srcs = {"A": SRC_ACC, "R": SRC_ROW, "C": SRC_CONST}
                     assert ((w0 >> 16) & 3) == srcs[pat[0]] and ((w0 >> 18) & 3) == srcs[pat[1]]
-                    assert not (w0 & F_CHK_A and pat[0] == "R") and not (w0 & F_CHK_B and pat[1] == "R")
+                    # a checked feature ROW is specialised only where the handlers test it
+                    assert not (w0 & F_CHK_A and pat[0] == "R") or opname in ("MAX", "MIN")
+                    assert not (w0 & F_CHK_B and pat[1] == "R") or opname in ("DIV", "MAX", "MIN")
+                    assert not (w0 & F_CHK_A and pat[0] == "A") and not (w0 & F_CHK_B and pat[1] == "A")
                     va = {"A": acc, "R": rows[rowA], "C": cvec}[pat[0]].copy()
                     vb = {"A": acc, "R": rows[rowB], "C": cvec}[pat[1]].copy()
-                    if "C" in pat and (w0 & F_CHK_CONST) and bad(cvec):
+                    if (w0 & F_CHK_A) and bad(va):
                         ok = False
-                    assert bool(w0 & F_CHK_CONST) == bool(("C" in pat) and (w0 & (F_CHK_A | F_CHK_B)))
+                    if (w0 & F_CHK_B) and bad(vb):
+                        ok = False
                     with np.errstate(all="ignore"):
                         r = b[opname](va, vb)
             acc = np.asarray(r, dtype=dtype)

@@ -86,7 +86,7 @@ def test_pack_validation_errors():
 def test_max_min_operand_exchange_is_recorded_for_the_gradient():
     """The flattener brings commutative operators into (ACC|ROW, ROW|CONST) order.  For max / min
     the reference's partials (x > y, !(x > y)) break ties by operand order, so an exchange must be
-    visible to the gradient interpreters: bit 7 of w0 (csrc/dex_tape.h)."""
+    visible to the gradient interpreters: bit 26 of w0 (csrc/dex_tape.h)."""
     ctx = D.host_context()
     ops = dexb200.OperatorEnum({1: ("cos",), 2: ("max", "min", "+")})
     N = dexb200.Node
@@ -99,7 +99,7 @@ def test_max_min_operand_exchange_is_recorded_for_the_gradient():
     pop = D.Population(trees, ops, np.float32, ctx=ctx)
     ins, off = pop.tape()
     last = ins[off[1:] - 1, 0]
-    assert [int(w >> 7) & 1 for w in last] == [1, 0, 1, 0, 0]
+    assert [int(w >> 26) & 1 for w in last] == [1, 0, 1, 0, 0]
 
 
 def test_population_info_and_constants_roundtrip():

@@ -668,6 +668,45 @@ def test_native_float32_handlers_are_accurate_to_a_few_ulp():
             np.testing.assert_allclose(y, f(lhs, rhs), rtol=2e-7, atol=1e-37, err_msg=f"{name}/{form}")
 
 
+@pytest.mark.parametrize("name", ["sin", "cos"])
+def test_sin_cos_beyond_the_cody_waite_range(name):
+    """|x| > 105615: reduction in double (dex::medium_sincosf), served by the PTX loop without
+    leaving the warp.  Against float64 numpy (exact argument reduction); a sample's result must
+    not depend on which code path its warp neighbours force (small / medium / library / Inf)."""
+    rng = np.random.default_rng(7)
+    n = 8192
+    big = (10.0 ** rng.uniform(5.03, 14.4, n) * rng.choice([-1.0, 1.0], n)).astype(np.float32)
+    small = (rng.standard_normal(n) * 1000).astype(np.float32)
+    huge = (10.0 ** rng.uniform(14.5, 38, n)).astype(np.float32)                  # library path
+    f = np.sin if name == "sin" else np.cos
+    ops = dexb200.OperatorEnum({1: (name,), 2: ("*",)})
+    N_ = dexb200.Node
+    for form, tree in (("R", N_(1, N_(feature=1))), ("A", N_(1, N_(1, N_(feature=1), N_(feature=2))))):
+        alone = {}
+        for label, x in (("big", big), ("small", small), ("huge", huge)):
+            X = np.stack([x, np.ones_like(x)])
+            y, ok = dexb200.eval_tree_array(tree, X, ops)
+            assert ok, (name, form, label)
+            np.testing.assert_allclose(y, f(x.astype(np.float64)), rtol=6e-7, atol=2e-9, err_msg=f"{name}/{form}/{label}")
+            alone[label] = y
+        # interleaved: every warp sees all kinds; each sample keeps its own result bit for bit
+        mix = np.empty(3 * n, np.float32)
+        mix[0::3], mix[1::3], mix[2::3] = big, small, huge
+        X = np.stack([mix, np.ones_like(mix)])
+        y, ok = dexb200.eval_tree_array(tree, X, ops)
+        assert ok
+        assert np.array_equal(y[0::3], alone["big"]) and np.array_equal(y[1::3], alone["small"]) \
+            and np.array_equal(y[2::3], alone["huge"])
+        # Inf -> NaN, flagged incomplete; the other samples of the warp are unaffected
+        mix2 = mix.copy()
+        mix2[5::97] = np.inf
+        y2, ok2 = dexb200.eval_tree_array(tree, np.stack([mix2, np.ones_like(mix2)]), ops)
+        assert not ok2 and np.isnan(y2[5::97]).all()
+        keep = np.ones(3 * n, bool)
+        keep[5::97] = False
+        assert np.array_equal(y2[keep], y[keep])
+
+
 def test_set_constants_equals_repack(oracle):
     ops = dexb200.OperatorEnum(treegen.OPSET_A)
     nodes, offsets = treegen.gen_population(80, 6, 2, 4, 3, seed=41)
