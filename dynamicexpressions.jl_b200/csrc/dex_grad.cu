@@ -134,6 +134,12 @@ template <typename T, int K> struct VA {
 #pragma unroll
         for (int k = 0; k < K; ++k) d[k] = a[k] + b[k];
     }
+    // d = a * b + c, fused (the derivative combination p0 dA + p1 dB keeps one rounding less
+    // than the reference's separate products; same form as the generated PTX loops)
+    static __device__ __forceinline__ void fma(T (&d)[K], const T (&a)[K], const T (&b)[K], const T (&c)[K]) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) d[k] = m_fma(a[k], b[k], c[k]);
+    }
     static __device__ __forceinline__ void adds(T (&d)[K], const T (&a)[K], T s) {
 #pragma unroll
         for (int k = 0; k < K; ++k) d[k] = a[k] + s;
@@ -165,6 +171,10 @@ template <int K> struct VA<float, K> {
     static __device__ __forceinline__ void add(float (&d)[K], const float (&a)[K], const float (&b)[K]) {
 #pragma unroll
         for (int k = 0; k < K; k += 2) { const float2 r = __fadd2_rn(f2(a + k), f2(b + k)); d[k] = r.x; d[k + 1] = r.y; }
+    }
+    static __device__ __forceinline__ void fma(float (&d)[K], const float (&a)[K], const float (&b)[K], const float (&c)[K]) {
+#pragma unroll
+        for (int k = 0; k < K; k += 2) { const float2 r = __ffma2_rn(f2(a + k), f2(b + k), f2(c + k)); d[k] = r.x; d[k + 1] = r.y; }
     }
     static __device__ __forceinline__ void adds(float (&d)[K], const float (&a)[K], float s) {
         const float2 ss = make_float2(s, s);
@@ -325,7 +335,7 @@ __device__ __forceinline__ void combine_bin(T (&ad)[GC][VK<T, U>::K], const T (&
                 for (int k = 0; k < K; ++k) d[k] = e;
             }
         } else if (CLS == CL_VAR) {
-            if (!spA && !spB) { T t[K]; A::mul(d, p0, a); A::mul(t, p1, b); A::add(d, d, t); }
+            if (!spA && !spB) { T t[K]; A::mul(t, p1, b); A::fma(d, p0, a, t); }
             else if (!spA) { A::mul(d, p0, a); if (g == ib) A::add(d, d, p1); }
             else if (!spB) { A::mul(d, p1, b); if (g == ia) A::add(d, p0, d); }
             else {
@@ -336,9 +346,8 @@ __device__ __forceinline__ void combine_bin(T (&ad)[GC][VK<T, U>::K], const T (&
             }
         } else {   // CL_GEN: every product is formed, also with the zeros of a one-hot
             T t[K];
-            A::mul(d, p0, a);
-            A::mul(t, p1, b);
-            A::add(d, d, t);
+            if (KA == DK_LEAF && KB != DK_LEAF) { A::mul(t, p0, a); A::fma(d, p1, b, t); }
+            else { A::mul(t, p1, b); A::fma(d, p0, a, t); }
         }
 #pragma unroll
         for (int k = 0; k < K; ++k) ad[g][k] = d[k];
