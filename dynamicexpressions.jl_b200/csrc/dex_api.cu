@@ -760,9 +760,9 @@ int dex_eval_parametric(dex_ctx* ctx, const dex_population* pop, const void* X_d
     if (!out_dev && nsamples > 0 && pop->h.n_trees > 0) return set_err(ctx, DEX_ERR_INVALID, "null out");
     if (n_params < 0 || n_classes < 1 || !classes_dev || (n_params > 0 && !params_dev))
         return set_err(ctx, DEX_ERR_INVALID, "bad parameter arguments");
-    if (pop->h.max_parameter >= n_params)
-        return set_err(ctx, DEX_ERR_RANGE, "population uses parameter " + std::to_string(pop->h.max_parameter + 1) +
-                                               " (1-based) but only " + std::to_string(n_params) + " were passed");
+    if (pop->h.n_param_rows > n_params)
+        return set_err(ctx, DEX_ERR_RANGE, "population uses (or was packed for) " + std::to_string(pop->h.n_param_rows) +
+                                               " parameters but only " + std::to_string(n_params) + " were passed");
     // a dummy non-null params pointer keeps the parametric kernel selected when n_params == 0
     return finish_call(ctx, run_eval(ctx, pop, X_dev, nfeatures, nsamples, ldx, out_dev, ldo, ok_dev, eval_flags,
                                      params_dev ? params_dev : X_dev, n_params, n_classes, classes_dev, nullptr,
@@ -822,12 +822,28 @@ struct LossSpec {            // fused loss + gradient of the loss (dex_eval_loss
     double* grad;
 };
 
-static int run_grad(dex_ctx* ctx, const dex_population* cpop, const void* X, int32_t F, int64_t N,
+struct ParamSpec {           // ParametricExpression arguments of a gradient call
+    const void* params;
+    int32_t n_params, n_classes;
+    const int32_t* classes;
+};
+
+// FX: rows of the caller's X.  With parameters the leaf rows of the launch are the n_param_rows
+// gathered parameter rows followed by the FX features (F below counts both).
+static int run_grad(dex_ctx* ctx, const dex_population* cpop, const void* X, int32_t FX, int64_t N,
                     int64_t ldx, int mode, int32_t direction, void* out, int64_t ldo, void* grad,
-                    const int64_t* grad_offsets_host, uint8_t* ok, const LossSpec* ls = nullptr) {
+                    const int64_t* grad_offsets_host, uint8_t* ok, const LossSpec* ls = nullptr,
+                    const ParamSpec* ps = nullptr) {
     dex_population* pop = const_cast<dex_population*>(cpop);
     const PackedPopulation& h = pop->h;
-    if (h.max_parameter >= 0) return set_err(ctx, DEX_ERR_UNSUPPORTED, "derivatives of parametric populations are not implemented");
+    if (!ps && h.max_parameter >= 0)
+        return set_err(ctx, DEX_ERR_INVALID, "population has parameter leaves: use dex_eval_grad_parametric");
+    if (ps && ps->n_params != h.n_param_rows)
+        return set_err(ctx, DEX_ERR_INVALID,
+                       "gradients of a parametric population need one row per parameter: pack it with "
+                       "DEX_PACK_PARAM_ROWS(" + std::to_string(ps->n_params) + ") (it has " +
+                           std::to_string(h.n_param_rows) + " parameter rows)");
+    const int32_t F = FX + (ps ? h.n_param_rows : 0);
     if (h.n_trees == 0) return DEX_OK;
     if (N == 0) return preset_ok_empty(ctx, pop, mode == DEX_GRAD_FEATURES && F > 0 ? 1 : -1, ok);
     int Gmax = 1;
@@ -864,6 +880,10 @@ static int run_grad(dex_ctx* ctx, const dex_population* cpop, const void* X, int
     a.n_trees = h.n_trees; a.max_stack = img.max_stack;
     a.X = X; a.xt = ctx->xt; a.F = F; a.N = N; a.ldx = ldx; a.mode = mode; a.direction = direction;
     a.out = out; a.ldo = ldo; a.grad = grad; a.ok = ok; a.grad_off = nullptr;
+    if (ps) {
+        a.params = ps->params; a.classes = ps->classes;
+        a.n_params = ps->n_params; a.n_classes = ps->n_classes; a.n_param_rows = h.n_param_rows;
+    }
     double* wsum = nullptr;
     int64_t stride = 0;
     if (mode >= 0) {
@@ -936,6 +956,23 @@ int dex_eval_grad(dex_ctx* ctx, const dex_population* pop, const void* X_dev, in
     if (!grad_dev && grad_offsets_host[pop->h.n_trees] > 0) return set_err(ctx, DEX_ERR_INVALID, "null grad");
     return finish_call(ctx, run_grad(ctx, pop, X_dev, nfeatures, nsamples, ldx, mode, 0, out_dev, ldo, grad_dev,
                                      grad_offsets_host, ok_dev));
+}
+
+int dex_eval_grad_parametric(dex_ctx* ctx, const dex_population* pop, const void* X_dev, int32_t nfeatures,
+                             int64_t nsamples, int64_t ldx, const void* params_dev, int32_t n_params,
+                             int32_t n_classes, const int32_t* classes_dev, int mode, void* out_dev,
+                             int64_t ldo, void* grad_dev, const int64_t* grad_offsets_host, uint8_t* ok_dev) {
+    int rc = ensure_device(ctx);
+    if (rc) return rc;
+    if ((rc = check_eval_args(ctx, pop, X_dev, nfeatures, nsamples, ldx, out_dev, ldo, ok_dev))) return rc;
+    if (mode < 0 || mode > 2) return set_err(ctx, DEX_ERR_INVALID, "mode must be DEX_GRAD_CONSTANTS/FEATURES/BOTH");
+    if ((!out_dev && nsamples > 0 && pop->h.n_trees > 0) || !grad_offsets_host) return set_err(ctx, DEX_ERR_INVALID, "null out / grad_offsets");
+    if (!grad_dev && grad_offsets_host[pop->h.n_trees] > 0) return set_err(ctx, DEX_ERR_INVALID, "null grad");
+    if (n_params < 0 || n_classes < 1 || !classes_dev || (n_params > 0 && !params_dev))
+        return set_err(ctx, DEX_ERR_INVALID, "bad parameter arguments");
+    ParamSpec ps{params_dev, n_params, n_classes, classes_dev};
+    return finish_call(ctx, run_grad(ctx, pop, X_dev, nfeatures, nsamples, ldx, mode, 0, out_dev, ldo, grad_dev,
+                                     grad_offsets_host, ok_dev, nullptr, &ps));
 }
 
 int dex_eval_diff(dex_ctx* ctx, const dex_population* pop, const void* X_dev, int32_t nfeatures,

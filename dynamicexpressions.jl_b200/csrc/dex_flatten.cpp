@@ -641,7 +641,9 @@ struct Flattener {
 
     static int finish(PackedPopulation& out, const std::vector<uint8_t>& rebase, std::string& err) {
         // row layout: [0, max_stack) operand stack, then one row per parameter, then the features
-        out.n_param_rows = out.max_parameter + 1;
+        // rows reserved for parameters: those the trees use, or the count the caller announced
+        // (DEX_PACK_PARAM_ROWS: gradient blocks have one row per parameter of the expression)
+        out.n_param_rows = std::max<int32_t>(out.max_parameter + 1, (out.pack_flags >> 8) & 0xffff);
         const uint32_t pbase = (uint32_t)out.max_stack;
         const uint32_t base = pbase + (uint32_t)out.n_param_rows;
         if (out.max_feature >= 0 && (int64_t)out.max_feature + base > MAX_ROWS) {

@@ -97,6 +97,10 @@ template <typename T> struct GK {
     const T* w;
     double* partial;          // [n_tiles][partial_stride]: n_trees losses, then the gradient entries
     int64_t partial_stride;
+    // ParametricExpression: F counts ALL leaf rows (n_param_rows gathered rows, then the features)
+    const T* params;
+    const int32_t* classes;
+    int32_t n_params, n_classes, n_param_rows;
 };
 
 template <typename T> __device__ __forceinline__ T gconst_of(const uint4& ins);
@@ -418,10 +422,12 @@ __global__ void __launch_bounds__(DEX_GRAD_THREADS, DEX_GRAD_MIN_CTAS) grad_kern
     T* xs = rows + (size_t)S * (1 + GC) * TILE;   // feature rows
     const int64_t s0 = (int64_t)blockIdx.x * TILE;
 
-    // stage the feature rows of this tile (XT is tile-padded: always in range, 16 B aligned)
-    for (int idx = tid; idx < a.F * (TILE / C); idx += nthr) {
+    // stage the feature rows of this tile (XT is tile-padded: always in range, 16 B aligned);
+    // they sit behind the parameter rows, which every tree fills for itself
+    const int NPR = a.n_param_rows;
+    for (int idx = tid; idx < (a.F - NPR) * (TILE / C); idx += nthr) {
         const int f = idx / (TILE / C), q = idx - f * (TILE / C);
-        *reinterpret_cast<uint4*>(xs + (size_t)f * TILE + q * C) =
+        *reinterpret_cast<uint4*>(xs + (size_t)(NPR + f) * TILE + q * C) =
             __ldg(reinterpret_cast<const uint4*>(a.X + (size_t)f * a.ldx + s0 + q * C));
     }
     __syncthreads();
@@ -471,6 +477,20 @@ __global__ void __launch_bounds__(DEX_GRAD_THREADS, DEX_GRAD_MIN_CTAS) grad_kern
         if (!DIFF && a.grad_off) go = a.grad_off[t + 1 < (int)a.n_trees ? t + 1 : t];
         const int G = DIFF ? 1 : mode_feat ? F : mode_const ? nconst : F + nconst;
         T nf = T(0);
+        if (NPR > 0) {
+            // ParametricExpression: this tree's per-sample parameters parameters[p, classes[j]]
+            // (src/ParametricExpression.jl:380-384) into the parameter rows; each thread fills and
+            // later reads only its own columns, so no barrier
+            const T* ptree = a.params + (size_t)t * a.n_params * a.n_classes;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                int64_t gs = s0 + (int64_t)(k / C) * CS + (int64_t)tid * C + (k % C);
+                if (gs >= a.N) gs = a.N - 1;
+                const int cl = __ldg(a.classes + gs) * a.n_params;
+                for (int p = 0; p < NPR; ++p)
+                    const_cast<T*>(myx)[(size_t)p * TILE + (k / C) * CS + (k % C)] = __ldg(ptree + cl + p);
+            }
+        }
         const int npass = G <= GC ? 1 : (G + GC - 1) / GC;
         for (int pass = 0; pass < npass; ++pass) {
             const int g0 = pass * GC;
@@ -857,6 +877,8 @@ GK<T> make_args(const GradArgs& g, const int32_t* chunk_start, int64_t Npad) {
     a.F = g.F; a.max_stack = g.max_stack; a.mode = g.mode; a.direction = g.direction;
     a.y = static_cast<const T*>(g.y); a.w = static_cast<const T*>(g.w);
     a.partial = g.partial; a.partial_stride = g.partial_stride;
+    a.params = static_cast<const T*>(g.params); a.classes = g.classes;
+    a.n_params = g.n_params; a.n_classes = g.n_classes; a.n_param_rows = g.n_param_rows;
     return a;
 }
 
@@ -925,13 +947,14 @@ cudaError_t launch_grad_ex(const GradArgs& g, const int32_t* chunk_start, int n_
     const int64_t n_tiles = (g.N + sh.tile - 1) / sh.tile;
     const int64_t Npad = n_tiles * sh.tile;
     const int64_t cover = std::max<int64_t>(Npad, g.n_trees);
+    const int FX = g.F - g.n_param_rows;     // rows of the caller's X
     if (g.dtype == DEX_F32)
         gtranspose_pad_kernel<float><<<(unsigned)((cover + 255) / 256), 256, 0, stream>>>(
-            static_cast<const float*>(g.X), g.ldx, g.F, g.N, static_cast<float*>(g.xt), Npad, g.ok, g.n_trees,
+            static_cast<const float*>(g.X), g.ldx, FX, g.N, static_cast<float*>(g.xt), Npad, g.ok, g.n_trees,
             const_cast<Instr*>(g.tape), g.ctape, g.seg, g.seg_off, g.fold_ok);
     else
         gtranspose_pad_kernel<double><<<(unsigned)((cover + 255) / 256), 256, 0, stream>>>(
-            static_cast<const double*>(g.X), g.ldx, g.F, g.N, static_cast<double*>(g.xt), Npad, g.ok, g.n_trees,
+            static_cast<const double*>(g.X), g.ldx, FX, g.N, static_cast<double*>(g.xt), Npad, g.ok, g.n_trees,
             const_cast<Instr*>(g.tape), g.ctape, g.seg, g.seg_off, g.fold_ok);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return err;

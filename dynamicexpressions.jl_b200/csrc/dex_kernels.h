@@ -93,6 +93,15 @@ struct GradArgs {
     const void* w;              // device, N weights or null
     double* partial;            // device, n_tiles x partial_stride
     int64_t partial_stride;     // n_trees + total gradient entries
+    // ParametricExpression (null params => plain trees): the per-sample parameter rows
+    // parameters[p, classes[j]] are leaf rows in FRONT of the features, exactly the
+    // vcat(indexed_parameters, X) of /root/reference/src/ParametricExpression.jl:380-385, so
+    // d/d(parameter row) are the first n_param_rows feature directions
+    const void* params;         // device, per tree (n_params x n_classes) column-major
+    const int32_t* classes;     // device, N
+    int32_t n_params;
+    int32_t n_classes;
+    int32_t n_param_rows;
 };
 // chunk_start: device table of n_chunks + 1 tree indices; Gmax: largest gradient count of any tree
 cudaError_t launch_grad_ex(const GradArgs& a, const int32_t* chunk_start, int n_chunks, int Gmax,

@@ -53,6 +53,8 @@ ABI = {
     "dex_eval_parametric": (C.c_int, [_P, _P, _P, _I32, _I64, _I64, _P, _I32, _I32, _P, _P, _I64,
                                       _U8P, C.c_int]),
     "dex_eval_grad": (C.c_int, [_P, _P, _P, _I32, _I64, _I64, C.c_int, _P, _I64, _P, _P, _U8P]),
+    "dex_eval_grad_parametric": (C.c_int, [_P, _P, _P, _I32, _I64, _I64, _P, _I32, _I32, _P, C.c_int, _P, _I64, _P,
+                                           _P, _U8P]),
     "dex_grad_offsets": (C.c_int, [_P, _I32, _I64, C.c_int, _P]),
     "dex_eval_diff": (C.c_int, [_P, _P, _P, _I32, _I64, _I64, _I32, _P, _P, _I64, _U8P]),
     "dex_eval_loss": (C.c_int, [_P, _P, _P, _I32, _I64, _I64, _P, _P, _P, _U8P, C.c_int]),
@@ -303,7 +305,7 @@ class Population:
     """A packed population of trees on one device (``dex_population``)."""
 
     def __init__(self, trees, operators: OperatorEnum, dtype=np.float32, *, ctx: Context = None,
-                 bumper=False, use_fused=True, wire=None):
+                 bumper=False, use_fused=True, wire=None, n_params=0):
         self.ctx = ctx or Context.get()
         self.operators = operators
         self.dtype_code = _dtype_code(dtype)
@@ -316,7 +318,9 @@ class Population:
         nodes = np.ascontiguousarray(nodes, dtype=WIRE_DTYPE)
         offsets = np.ascontiguousarray(offsets, dtype=np.int64)
         self.n_trees = len(offsets) - 1
-        flags = (PACK_BUMPER if bumper else 0) | (PACK_FUSED if use_fused else 0)
+        # n_params: size(parameters, 1) of a ParametricExpression (DEX_PACK_PARAM_ROWS): every
+        # parameter gets its row and gradient direction even when the trees do not use all of them
+        flags = (PACK_BUMPER if bumper else 0) | (PACK_FUSED if use_fused else 0) | ((int(n_params) & 0xffff) << 8)
         h = _P()
         self.ctx.check(lib().dex_population_pack(self.ctx.h, self.ctx.optable(operators), _ptr(nodes),
                                                  _ptr(offsets), self.n_trees, self.dtype_code, flags,
@@ -460,6 +464,36 @@ class Population:
         self.ctx.check(lib().dex_eval_grad(self.ctx.h, self.h, _ptr(Xd), F, N, ldx, mode, _ptr(out),
                                            out.stride(0) if self.n_trees else N, _ptr(grad),
                                            _ptr(off), _ptr(ok)))
+        return out, grad, off, ok
+
+    def eval_grad_parametric(self, X, parameters, classes0, mode=GRAD_FEATURES):
+        """Batched ``eval_grad_tree_array`` of ParametricExpressions, as the reference differentiates
+        them: the per-sample parameter rows ``parameters[:, classes]`` are the first ``n_params``
+        feature directions, the rows of X follow, then the constants.  Returns
+        (out[P, N], grad_flat, offsets, ok[P]); tree t's block is ``(N, G_t)`` row-major = the
+        reference's ``(G_t, N)`` column-major matrix."""
+        import torch
+        Xd, F, N, ldx = as_device_matrix(X, self.ctx.device, self.dtype_code)
+        dev = f"cuda:{self.ctx.device}"
+        tdt = _torch_dtype(self.dtype_code)
+        params = torch.as_tensor(parameters, dtype=tdt)
+        if params.dim() == 2:
+            params = params.unsqueeze(0)
+        P, n_params, n_classes = params.shape
+        assert P == self.n_trees
+        pd = params.to(dev).permute(0, 2, 1).contiguous()
+        cl = torch.as_tensor(classes0).to(device=dev, dtype=torch.int32).contiguous()
+        assert cl.numel() == N
+        if N and (int(cl.min()) < 0 or int(cl.max()) >= n_classes):
+            raise DexError(-5, "class index out of range")
+        out, ok = self._outputs(N, None, None)
+        off = self.grad_offsets(n_params + F, N, mode)
+        grad = torch.empty(int(off[-1]), dtype=out.dtype, device=out.device)
+        self.ctx.use_current_stream()
+        self.ctx.check(lib().dex_eval_grad_parametric(self.ctx.h, self.h, _ptr(Xd), F, N, ldx, _ptr(pd), n_params,
+                                                      n_classes, _ptr(cl), mode, _ptr(out),
+                                                      out.stride(0) if self.n_trees else N, _ptr(grad), _ptr(off),
+                                                      _ptr(ok)))
         return out, grad, off, ok
 
     def eval_diff(self, X, direction0):

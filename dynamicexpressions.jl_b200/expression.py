@@ -90,6 +90,41 @@ class ParametricExpression:
             out[...] = float("nan")
         return out
 
+    def eval_grad_tree_array(self, X, classes, operators=None, *, variable=False):
+        """``eval_grad_tree_array(convert(Node, ex), vcat(parameters[:, classes], X), operators;
+        variable)`` — how the reference differentiates a ParametricExpression
+        (/root/reference/src/ParametricExpression.jl:305-350, /root/reference/src/ChainRules.jl:56-77):
+        the per-sample parameter rows are the first ``n_params`` feature directions, the rows of X
+        follow, then the constants.  Returns (y[N], grad[G, N], complete)."""
+        from .evaluate import _mode_of
+        X = _prep(X)
+        ops = operators if operators is not None else self.operators
+        cl = np.asarray(classes.cpu() if _is_torch(classes) else classes)
+        assert len(cl) == X.shape[1] and (cl.size == 0 or (cl.min() >= 1 and cl.max() <= self.parameters.shape[1]))
+        dt = _resolve_dtype([self.tree], X)
+        pop = D.Population([self.tree], ops, dt, ctx=D.Context.get(_device_of(X)), n_params=self.parameters.shape[0])
+        out, grad, off, ok = pop.eval_grad_parametric(X, np.asarray(self.parameters, dtype=dt)[None], cl.astype(np.int64) - 1,
+                                                      _mode_of(variable))
+        N = out.shape[1]
+        G = int(off[1]) // N if N else 0
+        g = grad.view(N, G).T
+        host = not _is_torch(X)
+        return _to_host(out[0], host), (g.cpu().numpy() if host else g), bool(ok[0])
+
+    def parameter_gradient(self, X, classes, dY, operators=None):
+        """d (sum_j dY[j] * y[j]) / d parameters, shape (n_params, n_classes): the scatter-add of the
+        per-sample parameter-row gradients over the samples of each class (what Zygote's pullback
+        through ``parameters[:, classes]`` produces)."""
+        y, g, ok = self.eval_grad_tree_array(X, classes, operators, variable=True)
+        n_params, n_classes = self.parameters.shape
+        g = np.asarray(g.cpu() if _is_torch(g) else g)[:n_params]
+        cl = np.asarray(classes.cpu() if _is_torch(classes) else classes).astype(np.int64) - 1
+        out = np.zeros((n_params, n_classes), dtype=g.dtype)
+        np.add.at(out.T, cl, (g * np.asarray(dY)[None, :]).T)
+        if not ok:
+            out[...] = float("nan")
+        return out
+
 
 def eval_parametric_trees_array(exprs, X, classes, operators=None, *, eval_context=None, **kws):
     """Batched ParametricExpression evaluation: every expression has its own
@@ -106,7 +141,7 @@ def eval_parametric_trees_array(exprs, X, classes, operators=None, *, eval_conte
     assert classes.size == 0 or classes.min() >= 1
     dt = _resolve_dtype([e.tree for e in exprs], X)
     pop = D.Population([e.tree for e in exprs], ops, dt, ctx=D.Context.get(_device_of(X)),
-                       bumper=ctx.bumper, use_fused=ctx.use_fused)
+                       bumper=ctx.bumper, use_fused=ctx.use_fused, n_params=exprs[0].parameters.shape[0])
     params = np.stack([np.asarray(e.parameters, dtype=dt) for e in exprs])
     out, ok = pop.eval_parametric(X, params, classes.astype(np.int64) - 1, early_exit=ctx.early_exit)
     host = not _is_torch(X)

@@ -66,6 +66,10 @@ enum {
                              (/root/reference/ext/DynamicExpressionsBumperExt.jl:11-89)    */
     DEX_PACK_DEFAULT = 1
 };
+/* ParametricExpression populations whose gradients will be taken: OR this into pack_flags with
+ * n = size(parameters, 1), so that every parameter of the expression has its row (and its
+ * gradient direction) even when the trees do not use all of them.                       */
+#define DEX_PACK_PARAM_ROWS(n) (((int)(n) & 0xffff) << 8)
 
 /* gradient modes: `variable` of eval_grad_tree_array
  * (/root/reference/src/EvaluateDerivative.jl:193-228)                                */
@@ -165,6 +169,20 @@ int dex_eval_parametric(dex_ctx* ctx, const dex_population* pop, const void* X_d
 int dex_eval_grad(dex_ctx* ctx, const dex_population* pop, const void* X_dev, int32_t nfeatures,
                   int64_t nsamples, int64_t ldx, int mode, void* out_dev, int64_t ldo,
                   void* grad_dev, const int64_t* grad_offsets_host, uint8_t* ok_dev);
+/* Batched eval_grad_tree_array of ParametricExpressions: the reference differentiates
+ *   eval_tree_array(convert(Node, ex), vcat(parameters[:, classes], X), operators)
+ * (/root/reference/src/ParametricExpression.jl:305-350, 380-389 through the pullback of
+ * /root/reference/src/ChainRules.jl:56-77), in which the per-sample parameter rows are the FIRST
+ * n_params "features".  Same here, without materialising that matrix: the feature directions are
+ * [d/d parameter row 0 .. n_params-1, d/dX row 0 .. nfeatures-1], then the constants; G_t =
+ * n_params + nfeatures | n_constants(t) | both, by mode.  grad_offsets_host =
+ * dex_grad_offsets(pop, n_params + nfeatures, nsamples, mode).  The population must have been
+ * packed with DEX_PACK_PARAM_ROWS(n_params) unless its trees use every parameter.
+ * d loss / d parameters[p, c] is the sum over the samples of class c of dY[j] * grad[p, j].     */
+int dex_eval_grad_parametric(dex_ctx* ctx, const dex_population* pop, const void* X_dev, int32_t nfeatures,
+                             int64_t nsamples, int64_t ldx, const void* params_dev, int32_t n_params,
+                             int32_t n_classes, const int32_t* classes_dev, int mode, void* out_dev,
+                             int64_t ldo, void* grad_dev, const int64_t* grad_offsets_host, uint8_t* ok_dev);
 /* fills offsets[n_trees+1] for the layout above */
 int dex_grad_offsets(const dex_population* pop, int32_t nfeatures, int64_t nsamples, int mode,
                      int64_t* offsets_host);

@@ -252,3 +252,86 @@ def test_eval_diff_population_matches_oracle(dtype, oracle):
             n_values += 1
         check_trees(f"eval_diff direction {direction} {np.dtype(dtype).name}", dtype, pairs, min_strict=0.8)
     assert n_pattern > 2 * P_ and n_values > 2 * P_
+
+
+# ---------------------------------------------------------------------------------------
+# derivatives of ParametricExpressions: the reference differentiates
+# eval_tree_array(convert(Node, ex), vcat(parameters[:, classes], X)) with variable = :both
+# (src/ParametricExpression.jl:305-350, 380-389; src/ChainRules.jl:56-77)
+# ---------------------------------------------------------------------------------------
+def _converted(wire, n_params):
+    """convert(Node, ex): parameter p -> feature p, feature f -> feature f + n_params (LeafConverter)."""
+    w = wire.copy()
+    leaf = w["degree"] == 0
+    isf, isp = leaf & (w["kind"] == 1), leaf & (w["kind"] == 2)
+    w["feature"][isf] += n_params
+    w["kind"][isp] = 1
+    return w
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("mode", ["features", "constants", "both"])
+def test_parametric_gradients_match_the_converted_tree(dtype, mode, oracle):
+    spec = {1: ("cos", "exp", "sin"), 2: ("+", "-", "*", "/")}
+    ops = dexb200.OperatorEnum(spec)
+    P_, n_params, n_classes, F, N = 90, 4, 7, 3, 900          # the trees use parameters 0..2 of 4
+    nodes, offsets = treegen.gen_population(P_, 7, 3, 4, F, seed=91, n_params=3, dtype=dtype)
+    rng = np.random.default_rng(13)
+    X = rng.standard_normal((F, N)).astype(dtype)
+    params = rng.standard_normal((P_, n_params, n_classes)).astype(dtype)
+    cls0 = rng.integers(0, n_classes, N)
+    omode = {"features": oracle.GRAD_FEATURES, "constants": oracle.GRAD_CONSTANTS, "both": oracle.GRAD_BOTH}[mode]
+    dmode = {"features": D.GRAD_FEATURES, "constants": D.GRAD_CONSTANTS, "both": D.GRAD_BOTH}[mode]
+    pop = D.Population(None, ops, dtype, wire=(nodes, offsets), n_params=n_params)
+    out, grad, off, ok = pop.eval_grad_parametric(X, params, cls0, dmode)
+    out, grad, ok = out.cpu().numpy(), grad.cpu().numpy(), ok.cpu().numpy().astype(bool)
+    verdicts, n_with = [], 0
+    for t in range(P_):
+        w = _converted(nodes[offsets[t]:offsets[t + 1]], n_params)
+        Xv = np.vstack([params[t][:, cls0], X])                 # vcat(indexed_parameters, X)
+        so = np.array([0, len(w)])
+        ref, rg, rok = oracle.eval_grad_population(w, so, ops.opcodes, Xv, omode)
+        _, _, rok_e = oracle.eval_grad_population(w, so, ops.opcodes, Xv, omode | oracle.GRAD_ELEMENTWISE)
+        assert rok[0] <= rok_e[0] and ok[t] == rok_e[0], (t, ok[t], rok[0], rok_e[0])
+        if not rok[0]:
+            continue
+        G = rg[0].shape[0]
+        assert off[t + 1] - off[t] == G * N
+        g = grad[off[t]:off[t + 1]].reshape(N, G).T
+        yards = _grad_yardsticks(oracle, w, so, ops, Xv, omode)
+        verdicts.append(_grad_verdict(dtype, out[t], g, ref[0], rg[0], [(y[0], yg[0]) for y, yg in yards]))
+        n_with += 1
+        if mode != "constants":
+            assert not g[3].any()                               # the unused 4th parameter: a zero row
+    check_trees(f"parametric grad/{mode}/{np.dtype(dtype).name}", dtype, verdicts, min_strict=0.8)
+    assert n_with > 25
+    # without the announced parameter count the library refuses (one gradient row per parameter)
+    short = D.Population(None, ops, dtype, wire=(nodes, offsets))
+    with pytest.raises(D.DexError, match="PARAM_ROWS"):
+        short.eval_grad_parametric(X, params, cls0, dmode)
+    with pytest.raises(D.DexError, match="parametric"):
+        pop.eval_grad(X, dmode)
+
+
+def test_parametric_expression_gradient_api(oracle):
+    """ParametricExpression.eval_grad_tree_array / parameter_gradient through the host mirror, on the
+    reference's own example tree sin(x) + y + p1 * p2 (test/test_parametric_expression.jl:103-128)."""
+    ops = dexb200.OperatorEnum({1: ("sin",), 2: ("+", "*")})
+    N_ = dexb200.Node
+    tree = N_(1, N_(1, N_(1, N_(feature=1)), N_(feature=2)), N_(2, N_(parameter=1), N_(parameter=2)))
+    P = np.array([[1.0, 1.0, 0.8], [2.0, 3.0, 5.0]])
+    X = np.array([[0.0, np.pi / 2, np.pi, 1.2], [0.0, 0.0, 1.5, 0.1]])
+    cls = np.array([1, 1, 2, 3])
+    ex = dexb200.ParametricExpression(tree, operators=ops, parameters=P)
+    y, g, ok = ex.eval_grad_tree_array(X, cls, variable=True)
+    assert ok and g.shape == (4, 4)
+    np.testing.assert_allclose(y, [2, 3, 4.5, 5.032039085967226], rtol=1e-12)
+    p1, p2 = P[0, cls - 1], P[1, cls - 1]
+    np.testing.assert_allclose(g, np.stack([p2, p1, np.cos(X[0]), np.ones(4)]), rtol=1e-12, atol=1e-15)
+    dY = np.array([1.0, 2.0, 3.0, 4.0])
+    dP = ex.parameter_gradient(X, cls, dY)
+    want = np.zeros((2, 3))
+    for j in range(4):
+        want[0, cls[j] - 1] += dY[j] * p2[j]
+        want[1, cls[j] - 1] += dY[j] * p1[j]
+    np.testing.assert_allclose(dP, want, rtol=1e-12)
