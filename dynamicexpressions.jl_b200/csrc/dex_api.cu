@@ -987,9 +987,12 @@ int dex_eval_diff(dex_ctx* ctx, const dex_population* pop, const void* X_dev, in
                                      nullptr, ok_dev));
 }
 
-int dex_eval_host(dex_ctx* ctx, const dex_population* pop, const void* X_host, int32_t nfeatures,
-                  int64_t nsamples, int64_t ldx, void* out_host, int64_t ldo, uint8_t* ok_host,
-                  int eval_flags) {
+// Enqueues everything of dex_eval_host (H2D of X, kernels, D2H of results and flags) without
+// waiting for it; host_eval_wait() completes it.  Split so that one host thread can keep several
+// devices busy (dex_shard_eval_host).
+static int host_eval_enqueue(dex_ctx* ctx, const dex_population* pop, const void* X_host, int32_t nfeatures,
+                             int64_t nsamples, int64_t ldx, void* out_host, int64_t ldo, uint8_t* ok_host,
+                             int eval_flags) {
     int rc = ensure_device(ctx);
     if (rc) return rc;
     if (!pop || !out_host || !ok_host || (!X_host && nfeatures > 0 && nsamples > 0)) return set_err(ctx, DEX_ERR_INVALID, "null argument");
@@ -1010,7 +1013,6 @@ int dex_eval_host(dex_ctx* ctx, const dex_population* pop, const void* X_host, i
         uint8_t* dK0 = static_cast<uint8_t*>(ctx->dev_io);
         if ((rc = preset_ok_empty(ctx, const_cast<dex_population*>(pop), 0, dK0))) return rc;
         CU(ctx, cudaMemcpyAsync(ok_host, dK0, (size_t)P, cudaMemcpyDeviceToHost, ctx->stream));
-        CU(ctx, cudaStreamSynchronize(ctx->stream));
         return DEX_OK;
     }
     // device staging: X | out | ok
@@ -1034,8 +1036,82 @@ int dex_eval_host(dex_ctx* ctx, const dex_population* pop, const void* X_host, i
         CU(ctx, cudaMemcpy2DAsync(out_host, (size_t)ldo * es, dO, (size_t)N * es, (size_t)N * es, (size_t)P,
                                   cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaMemcpyAsync(ok_host, dK, (size_t)P, cudaMemcpyDeviceToHost, ctx->stream));
+    return DEX_OK;
+}
+static int host_eval_wait(dex_ctx* ctx) {
+    CU(ctx, cudaSetDevice(ctx->device));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    return DEX_OK;
+}
+
+int dex_eval_host(dex_ctx* ctx, const dex_population* pop, const void* X_host, int32_t nfeatures,
+                  int64_t nsamples, int64_t ldx, void* out_host, int64_t ldo, uint8_t* ok_host,
+                  int eval_flags) {
+    int rc = host_eval_enqueue(ctx, pop, X_host, nfeatures, nsamples, ldx, out_host, ldo, ok_host, eval_flags);
+    if (rc) return rc;
+    return host_eval_wait(ctx);
+}
+
+// Sample-sharded evaluation over several devices from ONE host thread: device d
+// evaluates the contiguous column block [N d / R, N (d+1) / R) of X against its own copy of the
+// population and its rows land in place in the caller's (n_trees x nsamples) result.  Everything
+// is enqueued on every device before anything is waited for, so the devices run concurrently; no
+// collective is involved (the gather IS the strided device-to-host copy).
+int dex_shard_eval_host(dex_ctx* const* ctxs, const dex_population* const* pops, int32_t n_devices,
+                        const void* X_host, int32_t nfeatures, int64_t nsamples, int64_t ldx, void* out_host,
+                        int64_t ldo, uint8_t* ok_host, int eval_flags) {
+    if (!ctxs || !pops || n_devices < 1) return DEX_ERR_INVALID;
+    for (int d = 0; d < n_devices; ++d)
+        if (!ctxs[d] || !pops[d]) return DEX_ERR_INVALID;
+    dex_ctx* c0 = ctxs[0];
+    const int64_t P = pops[0]->h.n_trees;
+    const size_t es = pops[0]->h.dtype == DEX_F32 ? 4 : 8;
+    for (int d = 1; d < n_devices; ++d)
+        if (pops[d]->h.n_trees != P || pops[d]->h.dtype != pops[0]->h.dtype)
+            return set_err(c0, DEX_ERR_INVALID, "the per-device populations differ (pack the same trees on every device)");
+    if (ldo < nsamples) return set_err(c0, DEX_ERR_INVALID, "ldo < nsamples");
+    std::vector<uint8_t> flags((size_t)n_devices * (size_t)std::max<int64_t>(P, 1), 1);
+    int rc = DEX_OK;
+    int issued = 0;
+    for (int d = 0; d < n_devices && rc == DEX_OK; ++d) {
+        const int64_t s = nsamples * d / n_devices, e = nsamples * (d + 1) / n_devices;
+        rc = host_eval_enqueue(ctxs[d], pops[d], static_cast<const char*>(X_host) + (size_t)s * (size_t)ldx * es, nfeatures,
+                               e - s, ldx, static_cast<char*>(out_host) + (size_t)s * es, ldo,
+                               flags.data() + (size_t)d * (size_t)std::max<int64_t>(P, 1), eval_flags);
+        if (rc != DEX_OK && ctxs[d] != c0) set_err(c0, rc, std::string("device ") + std::to_string(d) + ": " + ctxs[d]->last_error);
+        ++issued;
+    }
+    for (int d = 0; d < issued; ++d) {
+        const int rw = host_eval_wait(ctxs[d]);
+        if (rc == DEX_OK && rw != DEX_OK) rc = rw;
+    }
+    if (rc != DEX_OK) return rc;
+    // a tree is complete iff it is complete on every shard
+    for (int64_t t = 0; t < P; ++t) {
+        uint8_t k = 1;
+        for (int d = 0; d < n_devices; ++d) k &= flags[(size_t)d * (size_t)P + (size_t)t];
+        ok_host[t] = k;
+    }
+    return DEX_OK;
+}
+
+// plain copies on the context's stream, for hosts that have no CUDA binding of their own (the
+// Julia extension holds device buffers as raw pointers from dex_device_alloc)
+int dex_copy_to_device(dex_ctx* ctx, void* dst_dev, const void* src_host, int64_t bytes) {
+    int rc = ensure_device(ctx);
+    if (rc) return rc;
+    if (bytes < 0 || (bytes > 0 && (!dst_dev || !src_host))) return set_err(ctx, DEX_ERR_INVALID, "null pointer / negative size");
+    if (bytes) CU(ctx, cudaMemcpyAsync(dst_dev, src_host, (size_t)bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return DEX_OK;
+}
+// returns after the bytes have landed (synchronises the context's stream)
+int dex_copy_to_host(dex_ctx* ctx, void* dst_host, const void* src_dev, int64_t bytes) {
+    int rc = ensure_device(ctx);
+    if (rc) return rc;
+    if (bytes < 0 || (bytes > 0 && (!dst_host || !src_dev))) return set_err(ctx, DEX_ERR_INVALID, "null pointer / negative size");
+    if (bytes) CU(ctx, cudaMemcpyAsync(dst_host, src_dev, (size_t)bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
     return DEX_OK;
 }
 

@@ -60,6 +60,9 @@ ABI = {
     "dex_eval_loss": (C.c_int, [_P, _P, _P, _I32, _I64, _I64, _P, _P, _P, _U8P, C.c_int]),
     "dex_eval_loss_grad": (C.c_int, [_P, _P, _P, _I32, _I64, _I64, _P, _P, C.c_int, _P, _P, _P, _U8P]),
     "dex_eval_host": (C.c_int, [_P, _P, _P, _I32, _I64, _I64, _P, _I64, _U8P, C.c_int]),
+    "dex_shard_eval_host": (C.c_int, [_P, _P, _I32, _P, _I32, _I64, _I64, _P, _I64, _U8P, C.c_int]),
+    "dex_copy_to_device": (C.c_int, [_P, _P, _P, _I64]),
+    "dex_copy_to_host": (C.c_int, [_P, _P, _P, _I64]),
     "dex_host_alloc": (C.c_int, [C.POINTER(_P), _I64]),
     "dex_host_free": (C.c_int, [_P]),
     "dex_device_alloc": (C.c_int, [_P, C.POINTER(_P), _I64]),
@@ -550,3 +553,15 @@ class Population:
         self.ctx.check(lib().dex_eval_host(self.ctx.h, self.h, _ptr(X_host), F, N, F, _ptr(out_host),
                                            N, _ptr(ok_host), EVAL_EARLY_EXIT if early_exit else 0))
         return out_host, ok_host
+
+
+def shard_eval_host(pops, X_host, out_host, ok_host, *, early_exit=True):
+    """``dex_shard_eval_host``: one process, one :class:`Population` (same trees) per device; device d
+    evaluates its column block of ``X_host`` ((N, F) row-major) and the rows land in ``out_host``."""
+    N, F = X_host.shape
+    n = len(pops)
+    ctxs = (_P * n)(*[p.ctx.h for p in pops])
+    hs = (_P * n)(*[p.h for p in pops])
+    pops[0].ctx.check(lib().dex_shard_eval_host(ctxs, hs, n, _ptr(X_host), F, N, F, _ptr(out_host), N, _ptr(ok_host),
+                                                EVAL_EARLY_EXIT if early_exit else 0))
+    return out_host, ok_host

@@ -222,6 +222,22 @@ int dex_eval_host(dex_ctx* ctx, const dex_population* pop, const void* X_host, i
                   int64_t nsamples, int64_t ldx, void* out_host, int64_t ldo, uint8_t* ok_host,
                   int eval_flags);
 
+/* The same over several devices of ONE process (the reference is
+ * single-device: callers write `[eval_tree_array(t, X, ops) for t in trees]`).  ctxs[d] / pops[d]:
+ * one context and one packed copy of the SAME trees per device.  Device d evaluates the contiguous
+ * column block [N d / R, N (d+1) / R) of X and its rows land in place in out_host; all devices are
+ * enqueued before any is waited for.  ok_host[t] = complete on every shard.                    */
+int dex_shard_eval_host(dex_ctx* const* ctxs, const dex_population* const* pops, int32_t n_devices,
+                        const void* X_host, int32_t nfeatures, int64_t nsamples, int64_t ldx, void* out_host,
+                        int64_t ldo, uint8_t* ok_host, int eval_flags);
+
+/* plain copies on the context's stream for hosts without a CUDA binding of their own (a Julia
+ * extension holding dex_device_alloc'ed buffers as raw pointers): to_device is asynchronous (the
+ * source must stay valid until the next synchronising call), to_host returns when the bytes
+ * have landed                                                                                */
+int dex_copy_to_device(dex_ctx* ctx, void* dst_dev, const void* src_host, int64_t bytes);
+int dex_copy_to_host(dex_ctx* ctx, void* dst_host, const void* src_dev, int64_t bytes);
+
 /* pinned (page-locked) host buffers, so the copies of the *_host entry points run at full
  * PCIe speed and asynchronously */
 int dex_host_alloc(void** out, int64_t bytes);

@@ -80,3 +80,24 @@ def test_sharded_gather_and_fused_peer_gather_match_single_gpu(N):
         assert r["ok_nccl"] and r["ok_fused"], f"rank {r['rank']}: reduced flags differ"
         if r["rank"] == 0:
             assert r["fused"], "fused peer-memory gather differs from the unsharded evaluation"
+
+
+def test_single_process_shard_eval_over_two_devices():
+    """dex_shard_eval_host: one host thread, one context + packed population per device; the rows
+    of every column block land in place and equal the one-device evaluation bit for bit."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    import dexb200
+    from dexb200 import device as D, treegen
+    ops = dexb200.OperatorEnum(treegen.OPSET_A)
+    nodes, offsets = treegen.gen_population(300, 7, 2, 4, 5, seed=4)
+    N = 50_000 + 13
+    Xh = np.random.default_rng(3).standard_normal((N, 5)).astype(np.float32)
+    pops = [D.Population(None, ops, np.float32, wire=(nodes, offsets), ctx=D.Context.get(d)) for d in (0, 1)]
+    out = np.empty((300, N), np.float32)
+    ok = np.empty(300, np.uint8)
+    D.shard_eval_host(pops, Xh, out, ok)
+    ref = np.empty((300, N), np.float32)
+    rok = np.empty(300, np.uint8)
+    pops[0].eval_host(Xh, ref, rok)
+    assert ((out == ref) | (np.isnan(out) & np.isnan(ref))).all() and (ok == rok).all()
