@@ -392,7 +392,7 @@ int run_eval(dex_ctx* ctx, const dex_population* cpop, const void* X, int32_t F,
     // after a tree switch is a page walk, and a 42 GB result costs +70 % time).
     const int64_t want = (int64_t)ctx->sm_count * 8 * 4;
     int64_t n_chunks = std::max<int64_t>(1, (want + n_tiles - 1) / n_tiles);
-    int64_t chunk_instr = 128;
+    int64_t chunk_instr = y ? 256 : 128;
     if (const char* env = getenv("DEXB200_CHUNK_INSTR")) chunk_instr = std::max<int64_t>(1, atoll(env));
     n_chunks = std::max<int64_t>(n_chunks, ((int64_t)h.tape.size() + chunk_instr - 1) / chunk_instr);
     n_chunks = std::min<int64_t>(n_chunks, std::min<int64_t>(h.n_trees, 65535));
@@ -413,6 +413,9 @@ int run_eval(dex_ctx* ctx, const dex_population* cpop, const void* X, int32_t F,
     a.early_exit = (eval_flags & DEX_EVAL_EARLY_EXIT) ? 1 : 0;
     a.params = params; a.n_params = n_params; a.n_classes = n_classes; a.classes = classes;
     a.y = y; a.w = w; a.loss_partial = loss_partial;
+    // per-tree CTA barrier of the store path: -3 % on C6, +4 % on C2, +3 % on C4 — off (the fused
+    // loss, whose epilogue is longer, always re-aligns: DEX_LOSS_SYNC in dex_eval.cu)
+    a.sync_tree = getenv("DEXB200_SYNC_TREE") ? 1 : 0;
     int launches = 0;
     if (n_slices <= 1 || !out_host) {
         cudaError_t e = launch_eval(a, ctx->stream, ctx->sm_count, &launches);
@@ -780,8 +783,11 @@ int dex_eval_loss(dex_ctx* ctx, const dex_population* pop, const void* X_dev, in
     if (pop->h.n_trees == 0) return DEX_OK;
     int threads; size_t smem;
     const int64_t n_tiles = eval_num_tiles(pop->h.dtype, nfeatures, pop->h.folded->max_stack + pop->h.n_param_rows, std::max<int64_t>(nsamples, 1), &threads, &smem);
-    // scratch: [sum of weights (256 B slot)] [per-tile partial sums]
-    if ((rc = ensure_scratch(ctx, 256 + (size_t)n_tiles * (size_t)pop->h.n_trees * sizeof(double)))) return rc;
+    // scratch: [sum of weights (256 B slot)] [partial sums: one per (tile, warp slot, tree); warps a
+    // smaller CTA does not have leave their zero]
+    constexpr int64_t kWarpSlots = 8;   // DEX_MAX_THREADS / 32 (dex_eval.cu)
+    const size_t partial_bytes = (size_t)n_tiles * kWarpSlots * (size_t)pop->h.n_trees * sizeof(double);
+    if ((rc = ensure_scratch(ctx, 256 + partial_bytes))) return rc;
     double* wsum = static_cast<double*>(ctx->scratch);
     double* partial = reinterpret_cast<double*>(static_cast<char*>(ctx->scratch) + 256);
     if (weights_dev && nsamples > 0) {
@@ -789,10 +795,11 @@ int dex_eval_loss(dex_ctx* ctx, const dex_population* pop, const void* X_dev, in
         if (e != cudaSuccess) return cuda_err(ctx, e, "weight sum");
         ctx->launches += 1;
     }
+    if (threads < 256 && nsamples > 0) CU(ctx, cudaMemsetAsync(partial, 0, partial_bytes, ctx->stream));
     if ((rc = run_eval(ctx, pop, X_dev, nfeatures, nsamples, ldx, nullptr, 0, ok_dev, eval_flags, nullptr, 0,
                        0, nullptr, y_dev, weights_dev, partial, nullptr)))
         return rc;
-    cudaError_t e = launch_loss_grad_reduce(partial, nsamples > 0 ? n_tiles : 0, pop->h.n_trees, pop->h.n_trees,
+    cudaError_t e = launch_loss_grad_reduce(partial, nsamples > 0 ? n_tiles * kWarpSlots : 0, pop->h.n_trees, pop->h.n_trees,
                                             nsamples > 0 ? 1.0 / (double)nsamples : 0.0,
                                             (weights_dev && nsamples > 0) ? wsum : nullptr, loss_dev, nullptr,
                                             ctx->stream);

@@ -48,6 +48,7 @@ struct EvalArgs {
     const void* y;              // device, N
     const void* w;              // device, N or null
     double* loss_partial;       // device, n_tiles x n_trees partial sums (deterministic 2-stage)
+    int32_t sync_tree;          // barrier per tree (short tapes: see dex_eval.cu KArgs)
     int32_t skip_prepass;       // the transposed copy of X and ok[] are already prepared (slice > 0)
     // launch shape chosen by the launcher
     int32_t threads;
