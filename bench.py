@@ -340,6 +340,12 @@ def run_configs(local_rank, flush, peak, reps=3):
     ms, clk = device_time(lambda: pop.eval_grad(X.T, D.GRAD_FEATURES), reps + 2, flush, local_rank)
     emit("C3", "configs[2]: eval_grad_tree_array d/dX (G=5) of the C2 population, Float32, 2^16 samples", ms, clk,
          pop.info["n_nodes"] * N, P * N * (F * 4 + (1 + F) * 4))
+    o2 = torch.empty((P, N), device=dev)
+    k2 = torch.empty(P, device=dev, dtype=torch.uint8)
+    ms, clk = device_time(lambda: pop.eval(X.T, out=o2, ok=k2, early_exit=False), reps + 2, flush, local_rank)
+    emit("C2-no-early-exit", "the C2 population with EvalContext(early_exit = false)", ms, clk,
+         pop.info["n_nodes"] * N, P * N * (F * 4 + 4))
+    del o2
     y = torch.randn(N, device=dev, generator=g)
     ms, clk = device_time(lambda: pop.eval_loss_grad(X.T, y, D.GRAD_CONSTANTS), reps + 2, flush, local_rank)
     emit("C2-loss-grad", "fused MSE + d/dconstants on the C2 population (what constant optimisation consumes)", ms, clk,

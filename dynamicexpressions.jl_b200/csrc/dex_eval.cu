@@ -235,6 +235,14 @@ __device__ __forceinline__ void check(float (&nf)[2], const Vec<float, U>& r) {
 }
 #endif
 
+// result = isfinite(argument) ? result : Inf, per sample (the GUARD flag; early_exit = false only)
+template <typename T, int U>
+__device__ __forceinline__ void guard_inf(Vec<T, U>& r, const Vec<T, U>& x) {
+#pragma unroll
+    for (int k = 0; k < Vec<T, U>::K; ++k)
+        if (!t_finite(x.v[k])) r.v[k] = t_inf<T>();
+}
+
 // NT: CTA size fixed at compile time (the full-size 256-thread launch: row and chunk strides
 // become immediates of the shared-memory accesses) or 0 = read blockDim.x.
 template <typename T, int U, bool FAST, bool PARAM, bool LOSS, int NT = 0>
@@ -357,28 +365,37 @@ __global__ void __launch_bounds__(DEX_MAX_THREADS, DEX_MIN_CTAS) eval_kernel(con
             for (int k = 0; k < K; ++k) cv.v[k] = c;
             if (w0 & F_PUSH) st_row<T, U>(my + (size_t)push_row(w0) * TILE, CS, acc);
 
-            const uint32_t h = FAST ? (w0 & HANDLER_MASK) : (uint32_t)H_GENERIC;
+            // early_exit = false (FAST == false) runs the same specialised handlers: the flag
+            // checks then apply only to ALWAYS instructions, and the two fused unary kernels of the
+            // reference substitute Inf where their inner value is invalid (GUARD,
+            // /root/reference/src/Evaluate.jl:722, 737, 754, 787)
+            const uint32_t h = w0 & HANDLER_MASK;
+            const bool con = FAST ? true : (early || (w0 & F_ALWAYS));   // checks are on
 #define HANDLER_END break;
             switch (h) {
                 // ---- specialised handlers: one indirect branch, no operand decoding ----
                 case H_LOAD_R: {
                     ld_row<T, U>(acc, ra, CS);
-                    if (w0 & F_CHK_A) check<T, U>(nf, acc);
+                    if (con && (w0 & F_CHK_A)) check<T, U>(nf, acc);
                 } HANDLER_END
                 case H_LOAD_C: {
 #pragma unroll
                     for (int k = 0; k < K; ++k) acc.v[k] = c;
-                    if (w0 & F_CHK_A) nf[0] = m_fma(c, T(0), nf[0]);
+                    if (con && (w0 & F_CHK_A)) nf[0] = m_fma(c, T(0), nf[0]);
                 } HANDLER_END
 #define UNARY_HANDLERS(S)                                                          \
     case H_##S##_A: {                                                              \
+        V x;                                                                       \
+        if (!FAST) x = acc;                                                        \
         VOp1<DEX_OP_##S, T, K>::f(acc.v, acc.v);                                   \
+        if (!FAST && (w0 & F_GUARD)) guard_inf<T, U>(acc, x);                      \
     } HANDLER_END                                                                  \
     case H_##S##_R: {                                                              \
         V x;                                                                       \
         ld_row<T, U>(x, ra, CS);                                                   \
-        if (w0 & F_CHK_A) check<T, U>(nf, x);                                      \
+        if (con && (w0 & F_CHK_A)) check<T, U>(nf, x);                             \
         VOp1<DEX_OP_##S, T, K>::f(acc.v, x.v);                                     \
+        if (!FAST && (w0 & F_GUARD)) guard_inf<T, U>(acc, x);                      \
     } HANDLER_END
                 DEX_FAST_UNARY(UNARY_HANDLERS)
 #undef UNARY_HANDLERS
@@ -386,24 +403,24 @@ __global__ void __launch_bounds__(DEX_MAX_THREADS, DEX_MIN_CTAS) eval_kernel(con
     case H_##S##_AR: {                                                             \
         V y;                                                                       \
         ld_row<T, U>(y, rb, CS);                                                   \
-        if (RowChk<DEX_OP_##S>::b && (w0 & F_CHK_B)) check<T, U>(nf, y);           \
+        if (RowChk<DEX_OP_##S>::b && con && (w0 & F_CHK_B)) check<T, U>(nf, y);           \
         VOp2<DEX_OP_##S, T, K>::f(acc.v, acc.v, y.v);                              \
     } HANDLER_END
 #define BIN_RA(S)                                                                  \
     case H_##S##_RA: {                                                             \
         V x;                                                                       \
         ld_row<T, U>(x, ra, CS);                                                   \
-        if (RowChk<DEX_OP_##S>::a && (w0 & F_CHK_A)) check<T, U>(nf, x);           \
+        if (RowChk<DEX_OP_##S>::a && con && (w0 & F_CHK_A)) check<T, U>(nf, x);           \
         VOp2<DEX_OP_##S, T, K>::f(acc.v, x.v, acc.v);                              \
     } HANDLER_END
 #define BIN_AC(S)                                                                  \
     case H_##S##_AC: {                                                             \
-        if (w0 & F_CHK_B) nf[0] = m_fma(c, T(0), nf[0]);                           \
+        if (con && (w0 & F_CHK_B)) nf[0] = m_fma(c, T(0), nf[0]);                        \
         VOp2<DEX_OP_##S, T, K>::f(acc.v, acc.v, cv.v);                             \
     } HANDLER_END
 #define BIN_CA(S)                                                                  \
     case H_##S##_CA: {                                                             \
-        if (w0 & F_CHK_A) nf[0] = m_fma(c, T(0), nf[0]);                           \
+        if (con && (w0 & F_CHK_A)) nf[0] = m_fma(c, T(0), nf[0]);                        \
         VOp2<DEX_OP_##S, T, K>::f(acc.v, cv.v, acc.v);                             \
     } HANDLER_END
 #define BIN_RR(S)                                                                  \
@@ -411,24 +428,24 @@ __global__ void __launch_bounds__(DEX_MAX_THREADS, DEX_MIN_CTAS) eval_kernel(con
         V x, y;                                                                    \
         ld_row<T, U>(x, ra, CS);                                                   \
         ld_row<T, U>(y, rb, CS);                                                   \
-        if (RowChk<DEX_OP_##S>::a && (w0 & F_CHK_A)) check<T, U>(nf, x);           \
-        if (RowChk<DEX_OP_##S>::b && (w0 & F_CHK_B)) check<T, U>(nf, y);           \
+        if (RowChk<DEX_OP_##S>::a && con && (w0 & F_CHK_A)) check<T, U>(nf, x);           \
+        if (RowChk<DEX_OP_##S>::b && con && (w0 & F_CHK_B)) check<T, U>(nf, y);           \
         VOp2<DEX_OP_##S, T, K>::f(acc.v, x.v, y.v);                                \
     } HANDLER_END
 #define BIN_RC(S)                                                                  \
     case H_##S##_RC: {                                                             \
         V x;                                                                       \
         ld_row<T, U>(x, ra, CS);                                                   \
-        if (RowChk<DEX_OP_##S>::a && (w0 & F_CHK_A)) check<T, U>(nf, x);           \
-        if (w0 & F_CHK_B) nf[0] = m_fma(c, T(0), nf[0]);                           \
+        if (RowChk<DEX_OP_##S>::a && con && (w0 & F_CHK_A)) check<T, U>(nf, x);           \
+        if (con && (w0 & F_CHK_B)) nf[0] = m_fma(c, T(0), nf[0]);                        \
         VOp2<DEX_OP_##S, T, K>::f(acc.v, x.v, cv.v);                               \
     } HANDLER_END
 #define BIN_CR(S)                                                                  \
     case H_##S##_CR: {                                                             \
         V y;                                                                       \
         ld_row<T, U>(y, rb, CS);                                                   \
-        if (w0 & F_CHK_A) nf[0] = m_fma(c, T(0), nf[0]);                           \
-        if (RowChk<DEX_OP_##S>::b && (w0 & F_CHK_B)) check<T, U>(nf, y);           \
+        if (con && (w0 & F_CHK_A)) nf[0] = m_fma(c, T(0), nf[0]);                        \
+        if (RowChk<DEX_OP_##S>::b && con && (w0 & F_CHK_B)) check<T, U>(nf, y);           \
         VOp2<DEX_OP_##S, T, K>::f(acc.v, cv.v, y.v);                               \
     } HANDLER_END
 #define COMM_HANDLERS(S) BIN_AR(S) BIN_AC(S) BIN_RR(S) BIN_RC(S)
@@ -512,7 +529,7 @@ __global__ void __launch_bounds__(DEX_MAX_THREADS, DEX_MIN_CTAS) eval_kernel(con
                     if (!chk) return;  // CHK_OUT below is unconditional for FAST
                 } break;
             }
-            if (w0 & F_CHK_OUT) check<T, U>(nf, acc);
+            if (con && (w0 & F_CHK_OUT)) check<T, U>(nf, acc);
         };
 #undef HANDLER_END
 
