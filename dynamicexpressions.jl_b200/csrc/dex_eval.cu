@@ -246,7 +246,7 @@ __device__ __forceinline__ void guard_inf(Vec<T, U>& r, const Vec<T, U>& x) {
 // NT: CTA size fixed at compile time (the full-size 256-thread launch: row and chunk strides
 // become immediates of the shared-memory accesses) or 0 = read blockDim.x.
 template <typename T, int U, bool FAST, bool PARAM, bool LOSS, int NT = 0>
-__global__ void __launch_bounds__(DEX_MAX_THREADS, DEX_MIN_CTAS) eval_kernel(const KArgs<T> a) {
+__global__ void __launch_bounds__(DEX_MAX_THREADS, (U == 1 && sizeof(T) == 4) ? 4 : DEX_MIN_CTAS) eval_kernel(const KArgs<T> a) {
     using V = Vec<T, U>;
     constexpr int C = V::C;
     constexpr int K = V::K;
@@ -533,23 +533,32 @@ __global__ void __launch_bounds__(DEX_MAX_THREADS, DEX_MIN_CTAS) eval_kernel(con
         };
 #undef HANDLER_END
 
-        if constexpr (DEX_PTX_INTERP && FAST && sizeof(T) == 4 && U == 2) {
+        if constexpr (DEX_PTX_INTERP && FAST && sizeof(T) == 4 && (U == 2 || U == 1)) {
             // Float32 hot path: the instruction loop as one inline-PTX block with a real jump
-            // table (gen_interp_ptx.py).  It returns at the end of the tape or at the first
-            // instruction it does not implement natively, which `step` then executes.
+            // table (gen_interp_ptx.py, one block per U).  It returns at the end of the tape or at
+            // the first instruction it does not implement natively, which `step` then executes.
             const uint32_t my_s = (uint32_t)__cvta_generic_to_shared(my);
             const uint32_t tile_b = (uint32_t)TILE * 4u, cs_b = (uint32_t)CS * 4u;
             int pc = 0;
             float* av = reinterpret_cast<float*>(acc.v);
             float* nfv = reinterpret_cast<float*>(nf);
             while (pc < n) {
-                asm volatile(
+                if constexpr (U == 2) {
+                    asm volatile(
 #include "dex_interp_f32.inc"
-                    : "+r"(pc), "+f"(av[0]), "+f"(av[1]), "+f"(av[2]), "+f"(av[3]), "+f"(av[4]), "+f"(av[5]),
-                      "+f"(av[6]), "+f"(av[7]), "+f"(nfv[0]), "+f"(nfv[1]), "+r"(ins0.x), "+r"(ins0.y),
-                      "+r"(ins0.z), "+r"(ins0.w)
-                    : "l"(ip), "r"(n), "r"(my_s), "r"(tile_b), "r"(cs_b)
-                    : "memory");
+                        : "+r"(pc), "+f"(av[0]), "+f"(av[1]), "+f"(av[2]), "+f"(av[3]), "+f"(av[4]), "+f"(av[5]),
+                          "+f"(av[6]), "+f"(av[7]), "+f"(nfv[0]), "+f"(nfv[1]), "+r"(ins0.x), "+r"(ins0.y),
+                          "+r"(ins0.z), "+r"(ins0.w)
+                        : "l"(ip), "r"(n), "r"(my_s), "r"(tile_b), "r"(cs_b)
+                        : "memory");
+                } else {
+                    asm volatile(
+#include "dex_interp_f32_u1.inc"
+                        : "+r"(pc), "+f"(av[0]), "+f"(av[1]), "+f"(av[2]), "+f"(av[3]), "+f"(nfv[0]), "+f"(nfv[1]),
+                          "+r"(ins0.x), "+r"(ins0.y), "+r"(ins0.z), "+r"(ins0.w)
+                        : "l"(ip), "r"(n), "r"(my_s), "r"(tile_b), "r"(cs_b)
+                        : "memory");
+                }
                 if (pc < n) {   // early exit: ins0 is already two instructions ahead
                     step(__ldg(ip + pc));
                     ++pc;
@@ -705,22 +714,37 @@ cudaError_t launch_typed(const EvalArgs& e, cudaStream_t stream, int threads, si
 
 }  // namespace
 
-// samples per thread: U chunks of 16 bytes
+// samples per thread: U chunks of 16 bytes.  U = 2 (8 floats) amortises the dispatch over twice
+// the arithmetic.  A U = 1 variant of the PTX loop exists (half the shared memory per CTA, 63
+// registers -> 4 CTAs = 32 warps per SM instead of 16-24) for inputs with many rows, but the extra
+// dispatches cost more than the occupancy gains: C4 shard (10 features + 4 stack rows) 19.1 -> 20.6
+// ms, C2 0.30 -> 0.36 ms, C6 40.9 -> 51.7 ms.  It is kept behind DEXB200_EVAL_U=1 for experiments and
+// for shapes whose rows do not fit otherwise.  Float64 always uses U = 2 (4 doubles).
 constexpr int EVAL_U = DEX_EVAL_U;
+constexpr size_t U1_ROWS = (size_t)1 << 30;      // rows from which a Float32 launch takes U = 1: never
+
+static int eval_pick_u(int dtype, size_t rows) {
+    if (const char* env = getenv("DEXB200_EVAL_U")) {   // tuning knob for experiments
+        const int v = atoi(env);
+        if (v == 1 || v == 2) return dtype == DEX_F32 ? v : EVAL_U;
+    }
+    return (dtype == DEX_F32 && rows >= U1_ROWS) ? 1 : EVAL_U;
+}
 
 size_t eval_xt_bytes(int dtype, int32_t F, int32_t max_stack, int64_t N) {
     int threads;
     size_t smem;
     const int64_t n_tiles = eval_num_tiles(dtype, F, max_stack, N, &threads, &smem);
-    const int64_t tile = (int64_t)threads * (dtype == DEX_F32 ? 4 : 2) * EVAL_U;
+    const int u = eval_pick_u(dtype, (size_t)F + (size_t)max_stack);
+    const int64_t tile = (int64_t)threads * (dtype == DEX_F32 ? 4 : 2) * u;
     return (size_t)std::max<int64_t>(n_tiles * tile, 1) * (size_t)std::max(F, 1) * (dtype == DEX_F32 ? 4 : 8);
 }
 
 int64_t eval_num_tiles(int dtype, int32_t F, int32_t max_stack, int64_t N, int* threads_out,
                        size_t* smem_out) {
-    const int K = (dtype == DEX_F32 ? 4 : 2) * EVAL_U;
     const size_t es = dtype == DEX_F32 ? 4 : 8;
     const size_t rows = (size_t)F + (size_t)max_stack;
+    const int K = (dtype == DEX_F32 ? 4 : 2) * eval_pick_u(dtype, rows);
     int threads = 256;
     bool forced = false;
     if (const char* env = getenv("DEXB200_THREADS")) {   // tuning knob for experiments
@@ -748,7 +772,8 @@ cudaError_t launch_eval(const EvalArgs& e, cudaStream_t stream, int sm_count, in
     const int64_t n_tiles = eval_num_tiles(e.dtype, e.F, e.max_stack + e.n_param_rows, e.N, &threads, &smem);
     if (smem > SMEM_LIMIT) return cudaErrorInvalidConfiguration;
     if (e.n_trees == 0 || e.N == 0) return cudaSuccess;
-    const int64_t tile = (int64_t)threads * (e.dtype == DEX_F32 ? 4 : 2) * EVAL_U;
+    const int u = eval_pick_u(e.dtype, (size_t)e.F + (size_t)e.max_stack + (size_t)e.n_param_rows);
+    const int64_t tile = (int64_t)threads * (e.dtype == DEX_F32 ? 4 : 2) * u;
     const int64_t Npad = n_tiles * tile;
     const int64_t cover = std::max<int64_t>(Npad, e.n_trees);
     cudaError_t err = cudaSuccess;
@@ -768,8 +793,9 @@ cudaError_t launch_eval(const EvalArgs& e, cudaStream_t stream, int sm_count, in
     EvalArgs k = e;   // the interpreter reads the staged copy
     k.X = e.xt;
     k.ldx = Npad;
-    err = e.dtype == DEX_F32 ? launch_typed<float, EVAL_U>(k, stream, threads, smem, n_tiles)
-                             : launch_typed<double, EVAL_U>(k, stream, threads, smem, n_tiles);
+    err = e.dtype == DEX_F64 ? launch_typed<double, EVAL_U>(k, stream, threads, smem, n_tiles)
+          : u == 1           ? launch_typed<float, 1>(k, stream, threads, smem, n_tiles)
+                             : launch_typed<float, EVAL_U>(k, stream, threads, smem, n_tiles);
     if (err == cudaSuccess && launches) *launches += 1;
     return err;
 }
