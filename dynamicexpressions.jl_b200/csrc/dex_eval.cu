@@ -549,14 +549,14 @@ __global__ void __launch_bounds__(DEX_MAX_THREADS, (U == 1 && sizeof(T) == 4) ? 
                         : "+r"(pc), "+f"(av[0]), "+f"(av[1]), "+f"(av[2]), "+f"(av[3]), "+f"(av[4]), "+f"(av[5]),
                           "+f"(av[6]), "+f"(av[7]), "+f"(nfv[0]), "+f"(nfv[1]), "+r"(ins0.x), "+r"(ins0.y),
                           "+r"(ins0.z), "+r"(ins0.w)
-                        : "l"(ip), "r"(n), "r"(my_s), "r"(tile_b), "r"(cs_b)
+                        : "l"(ip), "r"(n), "r"(my_s), "r"(tile_b), "r"(cs_b), "l"(__cvta_generic_to_global(k_inv_pio4))
                         : "memory");
                 } else {
                     asm volatile(
 #include "dex_interp_f32_u1.inc"
                         : "+r"(pc), "+f"(av[0]), "+f"(av[1]), "+f"(av[2]), "+f"(av[3]), "+f"(nfv[0]), "+f"(nfv[1]),
                           "+r"(ins0.x), "+r"(ins0.y), "+r"(ins0.z), "+r"(ins0.w)
-                        : "l"(ip), "r"(n), "r"(my_s), "r"(tile_b), "r"(cs_b)
+                        : "l"(ip), "r"(n), "r"(my_s), "r"(tile_b), "r"(cs_b), "l"(__cvta_generic_to_global(k_inv_pio4))
                         : "memory");
                 }
                 if (pc < n) {   // early exit: ins0 is already two instructions ahead

@@ -670,14 +670,16 @@ def test_native_float32_handlers_are_accurate_to_a_few_ulp():
 
 @pytest.mark.parametrize("name", ["sin", "cos"])
 def test_sin_cos_beyond_the_cody_waite_range(name):
-    """|x| > 105615: reduction in double (dex::medium_sincosf), served by the PTX loop without
-    leaving the warp.  Against float64 numpy (exact argument reduction); a sample's result must
-    not depend on which code path its warp neighbours force (small / medium / library / Inf)."""
+    """|x| > 105615 up to the largest float: integer Payne-Hanek reduction (dex::large_sincosf),
+    served by the PTX loop without leaving the warp and without a library call.  Against float64
+    numpy (exact argument reduction); a sample's result must not depend on which code path its
+    warp neighbours force."""
     rng = np.random.default_rng(7)
     n = 8192
     big = (10.0 ** rng.uniform(5.03, 14.4, n) * rng.choice([-1.0, 1.0], n)).astype(np.float32)
     small = (rng.standard_normal(n) * 1000).astype(np.float32)
-    huge = (10.0 ** rng.uniform(14.5, 38, n)).astype(np.float32)                  # library path
+    huge = (10.0 ** rng.uniform(14.5, 38.5, n) * rng.choice([-1.0, 1.0], n)).astype(np.float32)
+    huge[:4] = [np.finfo(np.float32).max, -np.finfo(np.float32).max, 2.0 ** 120, -(2.0 ** 100)]
     f = np.sin if name == "sin" else np.cos
     ops = dexb200.OperatorEnum({1: (name,), 2: ("*",)})
     N_ = dexb200.Node
@@ -697,13 +699,18 @@ def test_sin_cos_beyond_the_cody_waite_range(name):
         assert ok
         assert np.array_equal(y[0::3], alone["big"]) and np.array_equal(y[1::3], alone["small"]) \
             and np.array_equal(y[2::3], alone["huge"])
+        # the C++ handlers (early_exit = false) give the same bits as the PTX loop
+        y3, _ = dexb200.eval_tree_array(tree, X, ops, eval_context=dexb200.EvalContext(early_exit=False))
+        assert np.array_equal(y3, y)
         # Inf -> NaN, flagged incomplete; the other samples of the warp are unaffected
         mix2 = mix.copy()
         mix2[5::97] = np.inf
+        mix2[6::97] = -np.inf
         y2, ok2 = dexb200.eval_tree_array(tree, np.stack([mix2, np.ones_like(mix2)]), ops)
-        assert not ok2 and np.isnan(y2[5::97]).all()
+        assert not ok2 and np.isnan(y2[5::97]).all() and np.isnan(y2[6::97]).all()
         keep = np.ones(3 * n, bool)
         keep[5::97] = False
+        keep[6::97] = False
         assert np.array_equal(y2[keep], y[keep])
 
 
