@@ -665,6 +665,7 @@ const char* dex_handler_name(int h) {
 #define X(S) #S "_AR", #S "_RA", #S "_AC", #S "_CA", #S "_RR", #S "_RC", #S "_CR",
         DEX_FAST_BIN_NC(X)
 #undef X
+        "KEEP",
     };
     static_assert(sizeof(names) / sizeof(names[0]) == H__COUNT, "handler name table out of sync");
     return (h >= 0 && h < (int)H__COUNT) ? names[h] : nullptr;

@@ -378,6 +378,8 @@ __global__ void __launch_bounds__(DEX_MAX_THREADS, (U == 1 && sizeof(T) == 4) ? 
                     ld_row<T, U>(acc, ra, CS);
                     if (con && (w0 & F_CHK_A)) check<T, U>(nf, acc);
                 } HANDLER_END
+                case H_KEEP: {   // the PUSH above was the point
+                } HANDLER_END
                 case H_LOAD_C: {
 #pragma unroll
                     for (int k = 0; k < K; ++k) acc.v[k] = c;

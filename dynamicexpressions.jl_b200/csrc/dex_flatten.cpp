@@ -34,6 +34,13 @@ struct Flattener {
     std::vector<uint8_t> isconst;  // subtree has no feature/parameter leaf
     std::vector<int32_t> need;     // stack slots needed with ACC free
     std::vector<int32_t> cord;     // constant ordinal of leaf i (tree-local), -1 otherwise
+    // shared subexpressions (evaluation image only): nodes of the chosen repeated subtree carry its
+    // group id at their root; the first occurrence in evaluation order computes it and KEEPs the
+    // value in row cse_row, the others load it (GraphNode sharing, /root/reference/src/Node.jl:137-166,
+    // which the reference's evaluators expand: /root/reference/ext/DynamicExpressionsBumperExt.jl:42)
+    std::vector<int32_t> cse_group;   // per node: 0 = root of an occurrence of the shared subtree, -1 otherwise
+    bool cse_done = false;            // the shared value sits in its row
+    int cse_row = -1;
     PackedPopulation& out;
     std::string& err;
     int64_t tree_index = 0;
@@ -301,6 +308,24 @@ struct Flattener {
         if (rec > MAX_RECURSION) return fail(DEX_ERR_UNSUPPORTED, "tree too deep");
         if (depth >= MAX_STACK_ROWS) return fail(DEX_ERR_UNSUPPORTED, "operand stack deeper than " + std::to_string(MAX_STACK_ROWS));
         if (foldable(i, allow_fold) && !const_mode) return emit_load_fold(i, push_slot, rec);
+        if (cse_row >= 0 && cse_group[(size_t)i] == 0) {
+            if (cse_done) {     // a later occurrence: the value (already validated) comes from its row
+                const bool keep = elide;
+                elide = false;
+                emit(DEX_OP_IDENTITY, slot(cse_row), acc(), 0u, push_slot);
+                elide = keep;
+                return DEX_OK;
+            }
+            cse_group[(size_t)i] = -1;                     // generate it normally ...
+            if (int rc0 = gen(i, push_slot, depth, const_mode, unchecked_leaves, rec + 1, allow_fold)) return rc0;
+            cse_group[(size_t)i] = 0;
+            const bool keep = elide;
+            elide = false;
+            emit(DEX_OP_IDENTITY, acc(), acc(), 0u, cse_row);   // ... and KEEP it (PUSH to its row)
+            elide = keep;
+            cse_done = true;
+            return DEX_OK;
+        }
         const dex_node& x = nd[i];
         const int op = opcode(i);
         // constant subtrees are folded by _eval_tree_array (src/Evaluate.jl:347-354) — but the
@@ -445,6 +470,72 @@ struct Flattener {
         return DEX_OK;
     }
 
+    // ---- shared subexpressions --------------------------------------------------------------
+    // Picks the repeated subtree of this tree that saves the most instructions, if any: operator subtrees of >= 4 nodes that are not constant, compared record by
+    // record.  One group per tree and only where its row fits the usual three stack rows: an extra
+    // shared-memory row for the whole population would cost more occupancy than the reuse saves.
+    static constexpr int CSE_MIN_NODES = 4;
+    static constexpr int CSE_ROW_BUDGET = 3;
+    static bool same_record(const dex_node& a, const dex_node& b) {
+        return a.degree == b.degree && a.kind == b.kind && a.op == b.op && a.feature == b.feature &&
+               std::memcmp(&a.val, &b.val, sizeof(double)) == 0;
+    }
+    void find_shared_subtree() {
+        cse_row = -1;
+        cse_done = false;
+        if (!fold || bumper || !fused || n < 2 * CSE_MIN_NODES + 1) return;
+        if (need[0] + 1 > CSE_ROW_BUDGET) return;
+        // hash of every subtree, children folded in preorder (a subtree is a contiguous record range)
+        std::vector<uint64_t> h((size_t)n);
+        for (int64_t i = n - 1; i >= 0; --i) {
+            const dex_node& x = nd[i];
+            uint64_t v;
+            std::memcpy(&v, &x.val, 8);
+            uint64_t k = 0x9e3779b97f4a7c15ull ^ ((uint64_t)x.degree << 56) ^ ((uint64_t)x.kind << 48) ^
+                         ((uint64_t)x.op << 40) ^ ((uint64_t)x.feature << 16) ^ (x.degree == 0 ? v * 0xff51afd7ed558ccdull : 0);
+            int64_t c = i + 1;
+            for (int d = 0; d < x.degree; ++d) {
+                k = (k ^ h[(size_t)c]) * 0xc4ceb9fe1a85ec53ull;
+                k ^= k >> 29;
+                c += size[(size_t)c];
+            }
+            h[(size_t)i] = k;
+        }
+        std::vector<std::pair<uint64_t, int64_t>> cand;
+        for (int64_t i = 1; i < n; ++i)
+            if (nd[i].degree > 0 && size[(size_t)i] >= CSE_MIN_NODES && !isconst[(size_t)i]) cand.emplace_back(h[(size_t)i], i);
+        std::sort(cand.begin(), cand.end());
+        int64_t best = -1, best_gain = 0;
+        std::vector<int64_t> best_occ, occ;
+        for (size_t a = 0; a < cand.size();) {
+            size_t b = a;
+            while (b < cand.size() && cand[b].first == cand[a].first) ++b;
+            if (b - a >= 2) {
+                // occurrences identical to the first one, not nested in each other
+                const int64_t i0 = cand[a].second, sz = size[(size_t)i0];
+                occ.assign(1, i0);
+                for (size_t k = a + 1; k < b; ++k) {
+                    const int64_t j = cand[k].second;
+                    if (size[(size_t)j] != sz || j < occ.back() + sz) continue;
+                    bool eq = true;
+                    for (int64_t q = 0; q < sz && eq; ++q) eq = same_record(nd[i0 + q], nd[j + q]);
+                    if (eq) occ.push_back(j);
+                }
+                // instructions saved: every later occurrence costs one load instead of (about) one
+                // instruction per operator node, and the first one an extra KEEP
+                int64_t nops = 0;
+                for (int64_t q = 0; q < sz; ++q) nops += nd[i0 + q].degree > 0;
+                const int64_t gain = ((int64_t)occ.size() - 1) * (nops - 1) - 1;
+                if (occ.size() >= 2 && gain > best_gain) { best_gain = gain; best = i0; best_occ = occ; }
+            }
+            a = b;
+        }
+        if (best < 0) return;
+        cse_group.assign((size_t)n, -1);
+        for (int64_t j : best_occ) cse_group[(size_t)j] = 0;
+        cse_row = need[0];           // above every row the operand stack of this tree can use
+    }
+
     // ---- lowering: EIns -> device encoding -------------------------------------------------
     static uint32_t pick_handler(const EIns& e, bool a_chk_row, bool b_chk_row) {
         const uint32_t sa = e.a.src, sb = e.b.src;
@@ -454,7 +545,7 @@ struct Flattener {
             if (e.op == DEX_OP_IDENTITY) {
                 if (sa == SRC_ROW) return H_LOAD_R;
                 if (sa == SRC_CONST) return H_LOAD_C;
-                return H_GENERIC;
+                return H_KEEP;
             }
             if (sa == SRC_CONST) return H_GENERIC;
             switch (e.op) {
@@ -618,12 +709,32 @@ struct Flattener {
             max_slot = 0;
             cur.clear();
             last = -1;
+            find_shared_subtree();
+            const size_t seg_mark = out.seg.size(), ctape_mark = out.ctape.size();
+            const int scalar_mark = scalar_slots;
             if (nd[0].degree == 0) {
                 // a bare leaf: deg0_eval then the final is_valid_array (:304-308); Bumper
                 // checks constants only (ext/...BumperExt.jl:29)
                 emit_load(0, true, false, -1);
             } else if ((rc = gen(0, -1, 0, false, false, 0))) {
                 return rc;
+            }
+            if (cse_row >= 0) {
+                // the shared value's row must be out of the operand stack's reach; if the stack ever
+                // pushed there (it cannot, by the Sethi-Ullman bound), flatten again without sharing
+                bool clash = false;
+                for (const EIns& e : cur)
+                    if (e.push_slot == cse_row && !(e.op == DEX_OP_IDENTITY && e.a.src == SRC_ACC)) clash = true;
+                if (clash) {
+                    cse_row = -1;
+                    max_slot = 0;
+                    cur.clear();
+                    last = -1;
+                    out.seg.resize(seg_mark);          // drop the scalar segments of the first attempt
+                    out.ctape.resize(ctape_mark);
+                    scalar_slots = scalar_mark;
+                    if ((rc = gen(0, -1, 0, false, false, 0))) return rc;
+                }
             }
             lower(cur, false);
             out.seg_off.push_back((int64_t)out.seg.size() / 3);

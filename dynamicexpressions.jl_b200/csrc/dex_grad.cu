@@ -274,6 +274,7 @@ constexpr FastOpTable make_fast_op_table() {
     FastOpTable t{};
     t.v[H_LOAD_R] = FO_LOAD;
     t.v[H_LOAD_C] = FO_LOAD;
+    t.v[H_KEEP] = FO_LOAD;      // identity on ACC (value and derivatives unchanged)
 #define X(S) t.v[H_##S##_A] = FO_##S; t.v[H_##S##_R] = FO_##S;
     DEX_FAST_UNARY(X)
 #undef X

@@ -105,6 +105,8 @@ enum Handler : uint32_t {
 #define X(S) H_##S##_AR, H_##S##_RA, H_##S##_AC, H_##S##_CA, H_##S##_RR, H_##S##_RC, H_##S##_CR,
     DEX_FAST_BIN_NC(X)
 #undef X
+    H_KEEP,    // ACC unchanged: with PUSH it stores ACC to a row that outlives the operand stack
+               // discipline (a shared subexpression, dex_flatten.cpp)
     H__COUNT
 };
 constexpr uint32_t HANDLER_MASK = 63u, HANDLER_PUSH = 64u, HANDLER_CHK = 128u;

@@ -56,6 +56,9 @@ def run_tape(ins, X, max_stack, opcode_info, dtype, early_exit=True, params=None
         code = (w0 >> 8) & 0xFF
         if h != 0:
             name = handler_name(h)
+            if name == "KEEP":          # ACC unchanged (the PUSH above stored it): a shared subexpression
+                assert opcode_info[code][0] == "IDENTITY" and (w0 & F_PUSH) and not (w0 & F_CHK_OUT)
+                continue
             opname, pat = name.rsplit("_", 1)
             if opname == "LOAD":
                 va = rows[rowA].copy() if pat == "R" else cvec

@@ -239,6 +239,69 @@ def _random_wire(rng, ops, F, max_nodes):
     return dexb200.to_wire(t)
 
 
+def _shared_trees(dtype):
+    """Trees in which one operator subtree (>= 4 nodes) occurs several times — GraphNode sharing of the
+    reference (src/Node.jl:137-166), which its evaluators expand; here the SAME Python object is
+    referenced from several parents and `to_wire` expands it likewise."""
+    N = dexb200.Node
+    x1, x2, x3 = (N(feature=k, T=dtype) for k in (1, 2, 3))
+    c = lambda v: N(val=v, T=dtype)
+    # operators: 1: cos exp ; 2: + - * /
+    S = N(3, N(1, x1, c(0.5)), N(1, x2))                      # (x1 + 0.5) * cos(x2)         6 nodes
+    D2 = N(4, x1, N(1, x3, c(2.0)))                           # x1 / (x3 + 2)               5 nodes
+    E = N(2, N(1, x2, x3))                                    # exp(x2 + x3)                4 nodes
+    return [
+        N(1, S, N(1, S)),                                     # S + cos(S)
+        N(4, N(1, S), N(1, S, c(3.0))),                       # cos(S) / (S + 3): reuse as divisor operand
+        N(3, N(2, D2), D2),                                   # exp(D2) * D2: the shared value can be Inf / NaN
+        N(2, N(1, E, N(3, E, E))),                            # exp(E + E * E): three occurrences
+        N(1, N(1, S, D2), N(3, S, D2)),                       # two repeated subtrees: one of them is shared
+        N(1, N(1, N(1, N(1, S, x1), x2), x3), S),             # deep left spine
+    ]
+
+
+@pytest.mark.parametrize("cname", ALL_CTX)
+def test_shared_subexpressions_are_computed_once(cname, oracle):
+    """The evaluation image KEEPs the value of a repeated subtree in a row and loads it at the later
+    occurrences; values and `complete` flags stay those of the expanded tree for every policy."""
+    hctx = D.host_context()
+    ops = dexb200.OperatorEnum({1: ("cos", "exp"), 2: ("+", "-", "*", "/")})
+    c = CONTEXTS[cname]
+    rng = np.random.default_rng(3)
+    n_keep = 0
+    for dtype in (np.float32, np.float64):
+        for k, tree in enumerate(_shared_trees(dtype)):
+            w = dexb200.to_wire(tree)
+            pop = D.Population([tree], ops, dtype, ctx=hctx, bumper=c.get("bumper", False), use_fused=c.get("use_fused", True))
+            f = pop.folded()
+            keeps = [ins for ins in f["tape"] if D.lib().dex_handler_name(int(ins[0]) & 63) == b"KEEP"]
+            n_keep += len(keeps)
+            if cname in ("default", "no_early_exit"):
+                # tree 2's shared subtree is two instructions: keeping + loading it saves nothing
+                assert len(keeps) == (0 if k == 2 else 1), (k, cname)
+                if keeps:
+                    assert pop.info["n_folded_instructions"] < pop.info["n_instructions"]
+                assert pop.info["folded_max_stack"] <= 3
+            else:
+                assert not keeps                       # Bumper / unfused policies flatten the expanded tree
+            for trial in range(3):
+                X = rng.standard_normal((3, 40)).astype(dtype)
+                if trial == 1:
+                    X[rng.integers(3), rng.integers(40)] = np.inf
+                    X[2, 7] = -2.0                     # x3 + 2 == 0: the shared divisor is 0
+                if trial == 2:
+                    X[rng.integers(3), rng.integers(40)] = np.nan
+                ry, rok = oracle.eval_tree_array(w, ops.opcodes, X, _flags(oracle, c))
+                y, ok = run_folded(f, 0, X, pop.info["folded_max_stack"], dexb200.OPCODE_INFO, dtype,
+                                   early_exit=c.get("early_exit", True))
+                assert ok == rok, (k, cname, trial)
+                if rok:
+                    fin = np.isfinite(ry)
+                    np.testing.assert_allclose(y[fin], ry[fin], rtol=2e-5 if dtype == np.float32 else 1e-12)
+                    assert (np.isfinite(y) == fin).all()
+    assert (n_keep > 0) == (cname in ("default", "no_early_exit"))
+
+
 def test_parallel_flattening_equals_the_one_thread_walk(monkeypatch):
     """Large populations are flattened by several threads over tree ranges and the partial tapes
     merged (csrc/dex_flatten.cpp flatten_image): every array of both images must be identical to

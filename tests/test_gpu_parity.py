@@ -272,6 +272,39 @@ def test_edge_shapes(oracle):
             _check_population(oracle, nodes, offsets, ops, X, dtype, ctx={"early_exit": early}, label="edge")
 
 
+def test_shared_subexpressions_on_device(oracle):
+    """Repeated subtrees (GraphNode sharing) computed once: values, flags, d/dX gradients and the
+    fused loss against the oracle on the expanded trees."""
+    from tests.test_abi_and_flatten import _shared_trees
+    ops = dexb200.OperatorEnum({1: ("cos", "exp"), 2: ("+", "-", "*", "/")})
+    for dtype in (np.float32, np.float64):
+        trees = _shared_trees(dtype) * 3
+        nodes, offsets = dexb200.to_wire_population(trees)
+        X = np.random.default_rng(5).standard_normal((3, 2500)).astype(dtype)
+        errs, ok = _check_population(oracle, nodes, offsets, ops, X, dtype, label=f"shared/{np.dtype(dtype).name}")
+        _check_population(oracle, nodes, offsets, ops, X, dtype, ctx={"early_exit": False}, label="shared/no_early_exit")
+        assert ok.sum() >= 6
+        pop = D.Population(None, ops, dtype, wire=(nodes, offsets))
+        assert pop.info["n_folded_instructions"] < pop.info["n_instructions"]
+        out, grad, off, gok = pop.eval_grad(X, D.GRAD_FEATURES)
+        out, grad, gok = out.cpu().numpy(), grad.cpu().numpy(), gok.cpu().numpy().astype(bool)
+        ref, rgrads, rok = oracle.eval_grad_population(nodes, offsets, ops.opcodes, X, oracle.GRAD_FEATURES)
+        _, _, rok_e = oracle.eval_grad_population(nodes, offsets, ops.opcodes, X, oracle.GRAD_FEATURES | oracle.GRAD_ELEMENTWISE)
+        _flags_agree(gok, rok, rok_e, "shared grad")
+        ref64, rg64, _ = oracle.eval_grad_population(nodes, offsets, ops.opcodes, X.astype(np.float64), oracle.GRAD_FEATURES)
+        ref_p, rg_p, _ = oracle.eval_grad_population(nodes, offsets, ops.opcodes, np.nextafter(X, dtype(np.inf)), oracle.GRAD_FEATURES)
+        N = X.shape[1]
+        verdicts = [_grad_verdict(dtype, out[t], grad[off[t]:off[t + 1]].reshape(N, 3).T, ref[t], rgrads[t],
+                                  [(ref_p[t], rg_p[t]), (ref64[t], rg64[t])]) for t in np.nonzero(rok)[0]]
+        check_trees(f"shared grad/{np.dtype(dtype).name}", dtype, verdicts, min_strict=0.6)
+        y = np.random.default_rng(6).standard_normal(N).astype(dtype)
+        loss, lok = pop.eval_loss(X, y)
+        o, okk = pop.eval(X)
+        good = okk.cpu().numpy().astype(bool)
+        want = ((o.cpu().numpy().astype(np.float64) - y.astype(np.float64)[None]) ** 2).mean(axis=1)
+        np.testing.assert_allclose(loss.cpu().numpy()[good], want[good], rtol=1e-10)
+
+
 def test_empty_inputs():
     ops = dexb200.OperatorEnum(treegen.OPSET_A)
     nodes, offsets = treegen.gen_population(3, 4, 2, 4, 2, seed=1)
