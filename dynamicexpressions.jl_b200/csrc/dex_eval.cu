@@ -496,12 +496,27 @@ __global__ void __launch_bounds__(DEX_MAX_THREADS, (U == 1 && sizeof(T) == 4) ? 
                     // instruction cache; the early_exit-off kernel runs every instruction here
                     // and gets the fully unrolled, register-resident form.
                     V r;
-                    {
+                    const uint32_t opc = (w0 >> 8) & 0xffu;
+                    const bool guard = !FAST && (w0 & F_GUARD);
+                    if (opc == DEX_OP_POW || opc == DEX_OP_POW_ABS) {
+                        // the one generic operator that symbolic-regression operator sets use all
+                        // the time: K independent library sequences in registers instead of the
+                        // rolled loop (no local memory, no per-sample opcode dispatch)
+                        if (opc == DEX_OP_POW) {
+#pragma unroll
+                            for (int k = 0; k < K; ++k) r.v[k] = m_pow(va.v[k], vb.v[k]);
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < K; ++k) r.v[k] = m_exp(vb.v[k] * m_log(m_fabs(va.v[k])));
+                        }
+                        if (guard) {
+#pragma unroll
+                            for (int k = 0; k < K; ++k) if (!t_finite(va.v[k])) r.v[k] = t_inf<T>();
+                        }
+                    } else {
                         T la[K], lb[K], lz[K], lr[K];
 #pragma unroll
                         for (int k = 0; k < K; ++k) { la[k] = va.v[k]; lb[k] = vb.v[k]; lz[k] = acc.v[k]; }
-                        const uint32_t opc = (w0 >> 8) & 0xffu;
-                        const bool guard = !FAST && (w0 & F_GUARD);
 #pragma unroll(FAST ? 1 : K)
                         for (int k = 0; k < K; ++k) {
                             const T x = la[k], y = lb[k], z = lz[k];

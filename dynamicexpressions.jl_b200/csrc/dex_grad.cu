@@ -581,7 +581,19 @@ __global__ void __launch_bounds__(DEX_GRAD_THREADS, DEX_GRAD_MIN_CTAS) grad_kern
                     default: {
                         const int deg = op >= 128u ? 3 : (op >= 64u ? 2 : 1);
                         T p2[K];
-                        {
+                        if (op == (uint32_t)DEX_OP_POW) {
+                            // `^` is the one generic operator that symbolic-regression operator sets
+                            // use all the time: unrolled, in registers (expressions of dex_ops.cuh)
+#pragma unroll
+                            for (int k = 0; k < K; ++k) {
+                                const T xx = x[k], yy = y[k];
+                                const T v = m_pow(xx, yy);
+                                vo[k] = v;
+                                p0[k] = yy * m_pow(xx, yy - T(1));
+                                p1[k] = (xx == T(0) && yy > T(0)) ? T(0) : v * m_log(m_fabs(xx));
+                                p2[k] = T(0);
+                            }
+                        } else {
                             // rolled over the samples, operands in local memory: this rarely taken
                             // path stays small and keeps the hot code in the instruction cache
                             T lx[K], ly[K], lz[K], lv[K], l0[K], l1[K], l2[K];

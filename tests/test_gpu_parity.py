@@ -747,6 +747,43 @@ def test_sin_cos_beyond_the_cody_waite_range(name):
         assert np.array_equal(y2[keep], y[keep])
 
 
+@pytest.mark.parametrize("name", ["sin", "cos"])
+def test_sin_cos_gradients_beyond_the_cody_waite_range(name):
+    """|x| > 105615 in the gradient kernel (its PTX loop hands such a warp to the C++ handler, which
+    uses dex::large_sincosf): value and derivative against float64 numpy, and bit-equal to
+    eval_diff for the samples that take the large-argument form."""
+    rng = np.random.default_rng(17)
+    n = 4096
+    big = (10.0 ** rng.uniform(5.03, 14.4, n) * rng.choice([-1.0, 1.0], n)).astype(np.float32)
+    small = (rng.standard_normal(n) * 1000).astype(np.float32)
+    huge = (10.0 ** rng.uniform(14.5, 38.5, n) * rng.choice([-1.0, 1.0], n)).astype(np.float32)
+    huge[:2] = [np.finfo(np.float32).max, -(2.0 ** 100)]
+    mix = np.empty(3 * n, np.float32)
+    mix[0::3], mix[1::3], mix[2::3] = big, small, huge
+    f, df = (np.sin, np.cos) if name == "sin" else (np.cos, lambda v: -np.sin(v))
+    ops = dexb200.OperatorEnum({1: (name,), 2: ("*",)})
+    N_ = dexb200.Node
+    X = np.stack([mix, np.ones_like(mix)])
+    x64 = mix.astype(np.float64)
+    for form, tree in (("R", N_(1, N_(feature=1))), ("A", N_(1, N_(1, N_(feature=1), N_(feature=2))))):
+        y, g, ok = dexb200.eval_grad_tree_array(tree, X, ops, variable=True)
+        assert ok, (name, form)
+        np.testing.assert_allclose(y, f(x64), rtol=6e-7, atol=2e-9, err_msg=f"{name}/{form} value")
+        np.testing.assert_allclose(g[0], df(x64), rtol=6e-7, atol=2e-9, err_msg=f"{name}/{form} d/dx1")
+        if form == "A":     # d/dx2 of op(x1 * x2) at x2 = 1 is x1 * op'(x1)
+            ref = x64 * df(x64)
+            fin = np.abs(ref) < 3e38
+            np.testing.assert_allclose(g[1][fin], ref[fin], rtol=1e-6, atol=2e-9, err_msg=f"{name}/{form} d/dx2")
+        yd, gd, _ = dexb200.eval_diff_tree_array(tree, X, ops, 1)
+        far = np.abs(mix) > 105615.0
+        assert np.array_equal(y[far], yd[far]) and np.array_equal(g[0][far], gd[far])
+        # Inf: NaN value and derivative, incomplete
+        X2 = X.copy()
+        X2[0, 7::101] = np.inf
+        y2, g2, ok2 = dexb200.eval_grad_tree_array(tree, X2, ops, variable=True)
+        assert not ok2
+
+
 def test_set_constants_equals_repack(oracle):
     ops = dexb200.OperatorEnum(treegen.OPSET_A)
     nodes, offsets = treegen.gen_population(80, 6, 2, 4, 3, seed=41)
