@@ -31,18 +31,20 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--grad", action="store_true")
+    ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
     args = ap.parse_args()
     import torch
     import dexb200
     from dexb200 import device as D, treegen
     P, N, F = 1000, 1 << 16, 5
+    npdt, tdt = (np.float32, torch.float32) if args.dtype == "f32" else (np.float64, torch.float64)
     nodes, offsets = treegen.gen_population(P, 8, 2, 4, F, seed=0)
-    X = torch.randn((N, F), device="cuda", dtype=torch.float32).T      # (F, N) view, column-major memory
-    out = torch.empty((P, N), device="cuda", dtype=torch.float32)
+    X = torch.randn((N, F), device="cuda", dtype=tdt).T      # (F, N) view, column-major memory
+    out = torch.empty((P, N), device="cuda", dtype=tdt)
     ok = torch.empty((P,), device="cuda", dtype=torch.uint8)
     for name, spec in SETS.items():
         ops = dexb200.OperatorEnum(spec)
-        pop = D.Population(None, ops, np.float32, wire=(nodes, offsets))
+        pop = D.Population(None, ops, npdt, wire=(nodes, offsets))
         ts = []
         for _ in range(args.reps + 1):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -51,7 +53,7 @@ def main():
             b.record()
             torch.cuda.synchronize()
             ts.append(a.elapsed_time(b))
-        line = {"opset": name, "eval_ms": min(ts[1:]), "complete": float(ok.float().mean()),
+        line = {"opset": name, "dtype": args.dtype, "eval_ms": min(ts[1:]), "complete": float(ok.float().mean()),
                 "generic_instructions": pop.info["n_generic"], "instructions": pop.info["n_instructions"]}
         if args.grad:
             ts = []

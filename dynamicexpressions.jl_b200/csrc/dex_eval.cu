@@ -576,7 +576,7 @@ __global__ void __launch_bounds__(DEX_MAX_THREADS, (U == 1 && sizeof(T) == 4) ? 
                         : "l"(ip), "r"(n), "r"(my_s), "r"(tile_b), "r"(cs_b), "l"(__cvta_generic_to_global(k_inv_pio4))
                         : "memory");
                 }
-                if (pc < n) {   // early exit: ins0 is already two instructions ahead
+                if (pc < n) {   // handed over: ins0 is already two instructions ahead
                     step(__ldg(ip + pc));
                     ++pc;
                     ins0 = __ldg(ip + pc);
@@ -584,6 +584,7 @@ __global__ void __launch_bounds__(DEX_MAX_THREADS, (U == 1 && sizeof(T) == 4) ? 
             }
         } else {
             uint4 ins = __ldg(ip);
+            bool bail = false;
             for (int pc = 0; pc < n; ++pc) {
                 uint4 nxt = ins;
                 if (pc + 1 < n) nxt = __ldg(ip + pc + 1);  // prefetch the next instruction
@@ -593,6 +594,13 @@ __global__ void __launch_bounds__(DEX_MAX_THREADS, (U == 1 && sizeof(T) == 4) ? 
                 // padded, so running past this tree's end just prefetches the next tree)
                 if ((pc & 7) == 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(ip + pc + 16));
                 step(ins);
+                // early exit proper (/root/reference/src/Evaluate.jl:26-32): once a sample of this warp
+                // has tripped a check the tree is incomplete whatever follows and its row unspecified
+                // (decided one instruction late, so that the vote's latency hides behind a handler)
+                if constexpr (FAST) {
+                    if (bail) break;
+                    bail = (ins.x & F_CHK_OUT) && __any_sync(0xffffffffu, !(nf[0] + nf[1] == T(0)));
+                }
                 ins = nxt;
             }
         }

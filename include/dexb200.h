@@ -54,7 +54,11 @@ enum {
  * (/root/reference/src/Evaluate.jl:156-181).                                        */
 enum {
     DEX_EVAL_EARLY_EXIT = 1, /* early_exit=Val(true): `complete` is false when any checked
-                                intermediate is non-finite (reference default)             */
+                                intermediate is non-finite (reference default).  As in the
+                                reference (`@return_on_nonfinite_array`, Evaluate.jl:26-32),
+                                evaluation of such a tree stops early: the result (and gradient)
+                                rows of a tree whose flag is 0 are UNSPECIFIED.  Without the flag
+                                every row is computed to the end, non-finite values included.   */
     DEX_EVAL_DEFAULT = 1
 };
 

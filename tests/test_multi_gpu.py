@@ -46,13 +46,14 @@ def _worker(rank, world, port, N, q):
         torch.cuda.synchronize()
 
         def same(a, b):
-            a, b = a.cpu().numpy(), b.cpu().numpy()
-            return bool(((a == b) | (np.isnan(a) & np.isnan(b))).all())
+            return bool(torch.equal(a.cpu(), b.cpu()))
 
-        res = {"rank": rank, "nccl": same(full_nccl, ref), "ok_nccl": same(ok_nccl, ok_ref),
+        good = ok_ref.bool()    # rows of incomplete trees are unspecified (early exit), as in the reference
+        assert int(good.sum()) > 10
+        res = {"rank": rank, "nccl": same(full_nccl[good], ref[good]), "ok_nccl": same(ok_nccl, ok_ref),
                "ok_fused": same(ok_fused, ok_ref)}
         if rank == 0:
-            res["fused"] = same(full_fused, ref) and same(full_fused2, ref)
+            res["fused"] = same(full_fused[good], ref[good]) and same(full_fused2[good], ref[good])
         fg.close()
         q.put(res)
     finally:
@@ -100,4 +101,5 @@ def test_single_process_shard_eval_over_two_devices():
     ref = np.empty((300, N), np.float32)
     rok = np.empty(300, np.uint8)
     pops[0].eval_host(Xh, ref, rok)
-    assert ((out == ref) | (np.isnan(out) & np.isnan(ref))).all() and (ok == rok).all()
+    good = rok.astype(bool)     # rows of incomplete trees are unspecified (early exit)
+    assert good.sum() > 50 and (ok == rok).all() and np.array_equal(out[good], ref[good])
