@@ -605,6 +605,11 @@ def main():
     e2e_s = host_timed(lambda: pop.eval_host(X_host, out_host, ok_host))    # H2D X, kernels, D2H results + flags, sync
     e2e_value = node_ops_per_step * world / e2e_s
 
+    # ---- ... not transferring the rows of incomplete trees (DEX_EVAL_SKIP_INCOMPLETE: unspecified under
+    # early exit — the reference returns at the first non-finite node — and D2H is what e2e is bound by)
+    skip_s = host_timed(lambda: pop.eval_host(X_host, out_host, ok_host, skip_incomplete=True))
+    skip_rows = int(ok_host.sum().item())
+
     # ---- ... including the flattening + upload of the population (callers whose trees change every
     # generation): wire arrays -> dex_population_pack -> dex_eval_host -> destroy, per step
     def pack_step():
@@ -699,6 +704,12 @@ def main():
                               "h2d_bytes_per_step": int(X_host.numel() * 4 + pop.info["n_instructions"] * 32),
                               "d2h_bytes_per_step": int(N_TREES * NSAMPLES * 4 + ok_host.numel()),
                               "entry": "dex_population_pack (flatten + upload) + dex_eval_host + dex_population_destroy, every step"},
+            "e2e_skip_incomplete": {"value": node_ops_per_step * world / skip_s, "unit": UNIT, "ms_per_step": skip_s * 1e3,
+                                    "h2d_bytes_per_step": int(X_host.numel() * 4),
+                                    "d2h_bytes_per_step": int(skip_rows * NSAMPLES * 4 + 2 * ok_host.numel()),
+                                    "rows_transferred": skip_rows,
+                                    "entry": "dex_eval_host with DEX_EVAL_SKIP_INCOMPLETE: rows of trees whose flag is 0 "
+                                             "(unspecified under early exit, as in the reference) stay on the device"},
             "e2e_fused_loss": {"value": e2e_loss_value, "unit": UNIT,
                                "h2d_bytes_per_step": int(X_host.numel() * 4 + y_host.numel() * 4),
                                "d2h_bytes_per_step": int(loss_host.numel() * 8 + ok_host.numel()),

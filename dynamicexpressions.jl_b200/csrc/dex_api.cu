@@ -371,7 +371,7 @@ int run_eval(dex_ctx* ctx, const dex_population* cpop, const void* X, int32_t F,
              int64_t ldx, void* out, int64_t ldo, uint8_t* ok, int eval_flags, const void* params,
              int32_t n_params, int32_t n_classes, const int32_t* classes, const void* y,
              const void* w, double* loss_partial, int64_t* n_tiles_out, int n_slices = 1,
-             void* out_host = nullptr, int64_t ldo_host = 0) {
+             void* out_host = nullptr, int64_t ldo_host = 0, uint8_t* ok_host = nullptr) {
     dex_population* pop = const_cast<dex_population*>(cpop);
     const PackedPopulation& h = *pop->h.folded;   // evaluation runs the folded image
     if (h.n_trees == 0) return DEX_OK;
@@ -417,7 +417,7 @@ int run_eval(dex_ctx* ctx, const dex_population* cpop, const void* X, int32_t F,
     // loss, whose epilogue is longer, always re-aligns: DEX_LOSS_SYNC in dex_eval.cu)
     a.sync_tree = getenv("DEXB200_SYNC_TREE") ? 1 : 0;
     int launches = 0;
-    if (n_slices <= 1 || !out_host) {
+    if (!out_host) {
         cudaError_t e = launch_eval(a, ctx->stream, ctx->sm_count, &launches);
         ctx->launches += launches;
         if (e != cudaSuccess) return cuda_err(ctx, e, "eval kernel launch");
@@ -425,29 +425,62 @@ int run_eval(dex_ctx* ctx, const dex_population* cpop, const void* X, int32_t F,
     }
     // Host-result pipeline: the population is evaluated in slices of consecutive tree chunks;
     // the device->host copy of slice s (copy stream) overlaps the kernel of slice s+1.
+    // DEX_EVAL_SKIP_INCOMPLETE: the flags of a slice come back first and only the rows of complete
+    // trees are transferred (runs of consecutive complete trees, one strided copy each) — the
+    // others are unspecified under early exit, and device->host bandwidth is what the host entry
+    // point is bound by.
+    const bool skip = ok_host && (eval_flags & DEX_EVAL_SKIP_INCOMPLETE) && a.early_exit;
     const std::vector<int32_t>& tab = pop->chunk_tables_host[(int32_t)n_chunks];
     const size_t es = h.dtype == DEX_F32 ? 4 : 8;
-    n_slices = (int)std::min<int64_t>(n_slices, n_chunks);
-    for (int sl = 0; sl < n_slices; ++sl) {
+    n_slices = (int)std::max<int64_t>(1, std::min<int64_t>(n_slices, n_chunks));
+    auto slice_trees = [&](int sl, int64_t& t_lo, int64_t& t_hi) {
+        t_lo = tab[(size_t)(n_chunks * sl / n_slices)];
+        t_hi = tab[(size_t)(n_chunks * (sl + 1) / n_slices)];
+    };
+    auto launch_slice = [&](int sl) -> int {
         const int64_t c0 = n_chunks * sl / n_slices, c1 = n_chunks * (sl + 1) / n_slices;
         EvalArgs b = a;
         b.chunk_start = a.chunk_start + c0;
         b.n_chunks = (int32_t)(c1 - c0);
         b.skip_prepass = sl > 0;
         cudaError_t e = launch_eval(b, ctx->stream, ctx->sm_count, &launches);
-        if (e != cudaSuccess) { ctx->launches += launches; return cuda_err(ctx, e, "eval kernel launch"); }
-        const int64_t t_lo = tab[(size_t)c0], t_hi = tab[(size_t)c1];
+        if (e != cudaSuccess) return cuda_err(ctx, e, "eval kernel launch");
+        int64_t t_lo, t_hi;
+        slice_trees(sl, t_lo, t_hi);
+        if (skip && t_hi > t_lo)
+            CU(ctx, cudaMemcpyAsync(ok_host + t_lo, ok + t_lo, (size_t)(t_hi - t_lo), cudaMemcpyDeviceToHost, ctx->stream));
         CU(ctx, cudaEventRecord(ctx->ev[sl & 1], ctx->stream));
-        CU(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev[sl & 1], 0));
-        if (t_hi > t_lo)
-            CU(ctx, cudaMemcpy2DAsync(static_cast<char*>(out_host) + (size_t)t_lo * (size_t)ldo_host * es,
-                                      (size_t)ldo_host * es,
-                                      static_cast<const char*>(out) + (size_t)t_lo * (size_t)ldo * es,
-                                      (size_t)ldo * es, (size_t)N * es, (size_t)(t_hi - t_lo),
-                                      cudaMemcpyDeviceToHost, ctx->copy_stream));
+        return DEX_OK;
+    };
+    auto copy_rows = [&](int64_t t0, int64_t t1) -> int {
+        CU(ctx, cudaMemcpy2DAsync(static_cast<char*>(out_host) + (size_t)t0 * (size_t)ldo_host * es,
+                                  (size_t)ldo_host * es,
+                                  static_cast<const char*>(out) + (size_t)t0 * (size_t)ldo * es,
+                                  (size_t)ldo * es, (size_t)N * es, (size_t)(t1 - t0),
+                                  cudaMemcpyDeviceToHost, ctx->copy_stream));
+        return DEX_OK;
+    };
+    rc = launch_slice(0);
+    for (int sl = 0; sl < n_slices && rc == DEX_OK; ++sl) {
+        if (sl + 1 < n_slices && (rc = launch_slice(sl + 1))) break;     // keeps the device busy while the host waits
+        int64_t t_lo, t_hi;
+        slice_trees(sl, t_lo, t_hi);
+        if (!skip) {
+            CU(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev[sl & 1], 0));
+            if (t_hi > t_lo) rc = copy_rows(t_lo, t_hi);
+            continue;
+        }
+        CU(ctx, cudaEventSynchronize(ctx->ev[sl & 1]));     // the flags of this slice are on the host
+        for (int64_t t = t_lo; t < t_hi && rc == DEX_OK;) {
+            if (!ok_host[t]) { ++t; continue; }
+            int64_t e = t + 1;
+            while (e < t_hi && ok_host[e]) ++e;
+            rc = copy_rows(t, e);
+            t = e;
+        }
     }
     ctx->launches += launches;
-    return DEX_OK;
+    return rc;
 }
 
 }  // namespace
@@ -1038,11 +1071,8 @@ static int host_eval_enqueue(dex_ctx* ctx, const dex_population* pop, const void
     // results travel back slice by slice on the copy stream while the next slice computes
     const int n_slices = (size_t)P * (size_t)N * es >= ((size_t)8 << 20) ? 8 : 1;
     if ((rc = run_eval(ctx, pop, dX, nfeatures, N, ldx, dO, N, dK, eval_flags, nullptr, 0, 0, nullptr,
-                       nullptr, nullptr, nullptr, nullptr, n_slices, out_host, ldo)))
+                       nullptr, nullptr, nullptr, nullptr, n_slices, out_host, ldo, ok_host)))
         return rc;
-    if (n_slices == 1)
-        CU(ctx, cudaMemcpy2DAsync(out_host, (size_t)ldo * es, dO, (size_t)N * es, (size_t)N * es, (size_t)P,
-                                  cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaMemcpyAsync(ok_host, dK, (size_t)P, cudaMemcpyDeviceToHost, ctx->stream));
     return DEX_OK;
 }
@@ -1084,9 +1114,11 @@ int dex_shard_eval_host(dex_ctx* const* ctxs, const dex_population* const* pops,
     int issued = 0;
     for (int d = 0; d < n_devices && rc == DEX_OK; ++d) {
         const int64_t s = nsamples * d / n_devices, e = nsamples * (d + 1) / n_devices;
+        // (SKIP_INCOMPLETE would make the enqueue wait for each device's flags in turn: not here)
         rc = host_eval_enqueue(ctxs[d], pops[d], static_cast<const char*>(X_host) + (size_t)s * (size_t)ldx * es, nfeatures,
                                e - s, ldx, static_cast<char*>(out_host) + (size_t)s * es, ldo,
-                               flags.data() + (size_t)d * (size_t)std::max<int64_t>(P, 1), eval_flags);
+                               flags.data() + (size_t)d * (size_t)std::max<int64_t>(P, 1),
+                               eval_flags & ~DEX_EVAL_SKIP_INCOMPLETE);
         if (rc != DEX_OK && ctxs[d] != c0) set_err(c0, rc, std::string("device ") + std::to_string(d) + ": " + ctxs[d]->last_error);
         ++issued;
     }

@@ -23,6 +23,7 @@ LIB_PATH = os.environ.get("DEXB200_LIB") or os.path.join(_HERE, "lib", "libdexb2
 OK = 0
 F32, F64 = 0, 1
 EVAL_EARLY_EXIT = 1
+EVAL_SKIP_INCOMPLETE = 2
 PACK_FUSED, PACK_BUMPER = 1, 2
 GRAD_CONSTANTS, GRAD_FEATURES, GRAD_BOTH = 0, 1, 2
 
@@ -546,12 +547,15 @@ class Population:
                                                 _ptr(loss), _ptr(grad), _ptr(off), _ptr(ok)))
         return loss, grad[: int(off[-1])], off, ok
 
-    def eval_host(self, X_host, out_host, ok_host, *, early_exit=True):
+    def eval_host(self, X_host, out_host, ok_host, *, early_exit=True, skip_incomplete=False):
         """The host-buffer entry point (dex_eval_host): numpy / pinned torch CPU tensors in the
-        library's layouts — ``X_host`` is (N, F) row-major, ``out_host`` (P, N), ``ok_host`` (P,)."""
+        library's layouts — ``X_host`` is (N, F) row-major, ``out_host`` (P, N), ``ok_host`` (P,).
+        ``skip_incomplete``: rows of trees whose flag comes back 0 are not transferred
+        (DEX_EVAL_SKIP_INCOMPLETE; they are unspecified under early exit anyway)."""
         N, F = X_host.shape
+        flags = (EVAL_EARLY_EXIT if early_exit else 0) | (EVAL_SKIP_INCOMPLETE if skip_incomplete else 0)
         self.ctx.check(lib().dex_eval_host(self.ctx.h, self.h, _ptr(X_host), F, N, F, _ptr(out_host),
-                                           N, _ptr(ok_host), EVAL_EARLY_EXIT if early_exit else 0))
+                                           N, _ptr(ok_host), flags))
         return out_host, ok_host
 
 

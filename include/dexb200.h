@@ -59,6 +59,10 @@ enum {
                                 evaluation of such a tree stops early: the result (and gradient)
                                 rows of a tree whose flag is 0 are UNSPECIFIED.  Without the flag
                                 every row is computed to the end, non-finite values included.   */
+    DEX_EVAL_SKIP_INCOMPLETE = 2, /* dex_eval_host only, with EARLY_EXIT: the rows of trees whose flag
+                                is 0 are not transferred to the host at all (they are unspecified
+                                anyway, and the device->host link is what that entry point is
+                                bound by); out_host keeps whatever it held in those rows.      */
     DEX_EVAL_DEFAULT = 1
 };
 

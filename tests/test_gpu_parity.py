@@ -784,6 +784,38 @@ def test_sin_cos_gradients_beyond_the_cody_waite_range(name):
         assert not ok2
 
 
+@pytest.mark.parametrize("P_,N", [(64, 4096), (400, 8192)])   # the second takes the sliced D2H pipeline
+def test_host_entry_point_can_leave_incomplete_rows_on_the_device(P_, N):
+    """DEX_EVAL_SKIP_INCOMPLETE: flags and the rows of complete trees as usual; the rows of incomplete
+    trees are not transferred (out_host keeps what it held)."""
+    import torch
+    ops = dexb200.OperatorEnum(treegen.OPSET_A)
+    nodes, offsets = treegen.gen_population(P_, 7, 2, 4, 5, seed=62)
+    Xh = torch.from_numpy(np.random.default_rng(11).standard_normal((N, 5)).astype(np.float32)).pin_memory()
+    pop = D.Population(None, ops, np.float32, wire=(nodes, offsets))
+    out_d, ok_d = pop.eval(Xh.cuda().T)
+    okd = ok_d.cpu().numpy().astype(bool)
+    assert 0 < okd.sum() < P_
+    for pinned in (True, False):
+        out_h = torch.full((P_, N), -7.0, dtype=torch.float32)
+        ok_h = torch.full((P_,), 9, dtype=torch.uint8)
+        if pinned:
+            out_h, ok_h = out_h.pin_memory(), ok_h.pin_memory()
+        pop.eval_host(Xh, out_h, ok_h, skip_incomplete=True)
+        assert (ok_h.numpy().astype(bool) == okd).all() and set(np.unique(ok_h.numpy())) <= {0, 1}
+        a = out_h.numpy()
+        assert np.array_equal(a[okd], out_d.cpu().numpy()[okd])
+        assert (a[~okd] == -7.0).all()
+    # without early exit the flag has no effect: every row is an output
+    out_h = torch.full((P_, N), -7.0, dtype=torch.float32).pin_memory()
+    ok_h = torch.zeros(P_, dtype=torch.uint8).pin_memory()
+    C_ = D.lib().dex_eval_host
+    pop.ctx.check(C_(pop.ctx.h, pop.h, D._ptr(Xh), 5, N, 5, D._ptr(out_h), N, D._ptr(ok_h), D.EVAL_SKIP_INCOMPLETE))
+    full, _ = pop.eval(Xh.cuda().T, early_exit=False)
+    f, a = full.cpu().numpy(), out_h.numpy()
+    assert ((a == f) | (np.isnan(a) & np.isnan(f))).all()
+
+
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 def test_early_exit_leaves_the_other_trees_alone(dtype):
     """A warp that meets a non-finite checked value skips the rest of that tree's tape
