@@ -48,6 +48,7 @@ end
 
 const DEX_F32, DEX_F64 = Cint(0), Cint(1)
 const DEX_EVAL_EARLY_EXIT = Cint(1)
+const DEX_EVAL_SKIP_INCOMPLETE = Cint(2)   # dex_eval_host: rows of incomplete trees are not transferred
 const DEX_PACK_FUSED, DEX_PACK_BUMPER = Cint(1), Cint(2)
 const DEX_GRAD_CONSTANTS, DEX_GRAD_FEATURES, DEX_GRAD_BOTH = Cint(0), Cint(1), Cint(2)
 dtype_code(::Type{Float32}) = DEX_F32
@@ -164,7 +165,10 @@ end
 pack_flags(ec::Union{EvalContext,Nothing}) =
     ec === nothing ? DEX_PACK_FUSED :
     ((ec.use_fused isa Val{true} ? DEX_PACK_FUSED : Cint(0)) | (ec.bumper isa Val{true} ? DEX_PACK_BUMPER : Cint(0)))
-eval_flags(ec::Union{EvalContext,Nothing}) = (ec === nothing || ec.early_exit isa Val{true}) ? DEX_EVAL_EARLY_EXIT : Cint(0)
+# with early exit the reference hands back an unusable buffer for an incomplete tree
+# (src/Evaluate.jl:26-32); the library then does not even transfer that column
+eval_flags(ec::Union{EvalContext,Nothing}) =
+    (ec === nothing || ec.early_exit isa Val{true}) ? (DEX_EVAL_EARLY_EXIT | DEX_EVAL_SKIP_INCOMPLETE) : Cint(0)
 
 # ---- device buffers as raw pointers (dex_device_alloc / dex_copy_to_device / dex_copy_to_host) ------
 function with_device(f, ctx, bytes::Integer...)

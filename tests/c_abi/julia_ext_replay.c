@@ -123,7 +123,7 @@ int main(void) {
     /* ---- 3. eval_tree_array(trees, B200Matrix(X), operators): out :: Matrix (N x P) --------------- */
     double out[N * P];
     uint8_t ok[P];
-    int rc = dex_eval_host(ctx, pop, X, F, N, F, out, N, ok, DEX_EVAL_EARLY_EXIT);
+    int rc = dex_eval_host(ctx, pop, X, F, N, F, out, N, ok, DEX_EVAL_EARLY_EXIT | DEX_EVAL_SKIP_INCOMPLETE);   /* eval_flags(nothing) */
     if (!have_gpu) {
         printf("no CUDA device: dex_eval_host -> %d (%s)\n", rc, dex_strerror(rc));
         return rc == DEX_ERR_CUDA ? 3 : 1;
