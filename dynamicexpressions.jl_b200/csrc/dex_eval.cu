@@ -550,7 +550,7 @@ __global__ void __launch_bounds__(DEX_MAX_THREADS, (U == 1 && sizeof(T) == 4) ? 
         };
 #undef HANDLER_END
 
-        if constexpr (DEX_PTX_INTERP && FAST && sizeof(T) == 4 && (U == 2 || U == 1)) {
+        if constexpr (DEX_PTX_INTERP && sizeof(T) == 4 && (U == 2 || (U == 1 && FAST))) {
             // Float32 hot path: the instruction loop as one inline-PTX block with a real jump
             // table (gen_interp_ptx.py, one block per U).  It returns at the end of the tape or at
             // the first instruction it does not implement natively, which `step` then executes.
@@ -560,9 +560,18 @@ __global__ void __launch_bounds__(DEX_MAX_THREADS, (U == 1 && sizeof(T) == 4) ? 
             float* av = reinterpret_cast<float*>(acc.v);
             float* nfv = reinterpret_cast<float*>(nf);
             while (pc < n) {
-                if constexpr (U == 2) {
+                if constexpr (U == 2 && FAST) {
                     asm volatile(
 #include "dex_interp_f32.inc"
+                        : "+r"(pc), "+f"(av[0]), "+f"(av[1]), "+f"(av[2]), "+f"(av[3]), "+f"(av[4]), "+f"(av[5]),
+                          "+f"(av[6]), "+f"(av[7]), "+f"(nfv[0]), "+f"(nfv[1]), "+r"(ins0.x), "+r"(ins0.y),
+                          "+r"(ins0.z), "+r"(ins0.w)
+                        : "l"(ip), "r"(n), "r"(my_s), "r"(tile_b), "r"(cs_b), "l"(__cvta_generic_to_global(k_inv_pio4))
+                        : "memory");
+                } else if constexpr (U == 2) {
+                    // early_exit = false: checks only where ALWAYS is set, GUARD substitution, no skipping
+                    asm volatile(
+#include "dex_interp_f32_noexit.inc"
                         : "+r"(pc), "+f"(av[0]), "+f"(av[1]), "+f"(av[2]), "+f"(av[3]), "+f"(av[4]), "+f"(av[5]),
                           "+f"(av[6]), "+f"(av[7]), "+f"(nfv[0]), "+f"(nfv[1]), "+r"(ins0.x), "+r"(ins0.y),
                           "+r"(ins0.z), "+r"(ins0.w)
@@ -727,7 +736,8 @@ cudaError_t launch_typed(const EvalArgs& e, cudaStream_t stream, int threads, si
         kern = loss ? (param ? eval_kernel<T, U, true, true, true> : eval_kernel<T, U, true, false, true>)
                     : (param ? eval_kernel<T, U, true, true, false> : eval_kernel<T, U, true, false, false>);
     } else {
-        // early_exit off: the generic path for every instruction (GUARD, ALWAYS-only checks)
+        // early_exit off: GUARD substitution, ALWAYS-only checks, nothing skipped (Float32: the
+        // _noexit form of the PTX loop)
         kern = loss ? (param ? eval_kernel<T, U, false, true, true> : eval_kernel<T, U, false, false, true>)
                     : (param ? eval_kernel<T, U, false, true, false> : eval_kernel<T, U, false, false, false>);
     }

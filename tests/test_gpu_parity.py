@@ -663,7 +663,8 @@ def test_random_trees_with_ternary_operators_value_and_gradient(dtype, oracle):
 def test_native_float32_handlers_are_accurate_to_a_few_ulp():
     """The specialised Float32 handlers of the generated PTX loops (default early_exit=True path)
     against float64 numpy on inputs where every result is finite: a few ulp, not just the 1e-4 of
-    the population tests.  (test_every_builtin_operator runs early_exit=False = the C++ handlers.)"""
+    the population tests.  (test_every_builtin_operator runs early_exit=False: the _noexit form of the
+    loop and, for the operators it does not implement, the C++ handlers.)"""
     rng = np.random.default_rng(99)
     n = 4096
     pos = np.exp(rng.uniform(-80.0, 80.0, n)).astype(np.float32)            # wide-range positive
@@ -732,9 +733,12 @@ def test_sin_cos_beyond_the_cody_waite_range(name):
         assert ok
         assert np.array_equal(y[0::3], alone["big"]) and np.array_equal(y[1::3], alone["small"]) \
             and np.array_equal(y[2::3], alone["huge"])
-        # the C++ handlers (early_exit = false) give the same bits as the PTX loop
+        # the early_exit = false form of the loop gives the same bits, and so do the scalar C++ functions
+        # (dex::m_sin / m_cos, which the eval_diff kernel runs for the value)
         y3, _ = dexb200.eval_tree_array(tree, X, ops, eval_context=dexb200.EvalContext(early_exit=False))
         assert np.array_equal(y3, y)
+        y4, _, _ = dexb200.eval_diff_tree_array(tree, X, ops, 1)
+        assert np.array_equal(y4, y)
         # Inf -> NaN, flagged incomplete; the other samples of the warp are unaffected
         mix2 = mix.copy()
         mix2[5::97] = np.inf
