@@ -774,7 +774,7 @@ __global__ void __launch_bounds__(DEX_GRAD_THREADS, DEX_GRAD_MIN_CTAS) grad_kern
                 if (pass == 0) {
                     T* o = a.out + (size_t)t * a.ldo + sbase;
                     if (out_vec)
-                        *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(&av[u * C]);
+                        __stcs(reinterpret_cast<uint4*>(o), *reinterpret_cast<const uint4*>(&av[u * C]));
                     else {
 #pragma unroll
                         for (int k = 0; k < C; ++k) if (sbase + k < a.N) o[k] = av[u * C + k];
@@ -798,8 +798,8 @@ __global__ void __launch_bounds__(DEX_GRAD_THREADS, DEX_GRAD_MIN_CTAS) grad_kern
 #pragma unroll
                             for (int g = 0; g < GC; ++g) flat[k * GC + g] = ad[g][u * C + k];
 #pragma unroll
-                        for (int q = 0; q < C * GC; q += C)
-                            *reinterpret_cast<uint4*>(gout + q) = *reinterpret_cast<const uint4*>(flat + q);
+                        for (int q = 0; q < C * GC; q += C)      // streaming: 1.5 GB per C3 launch, never re-read
+                            __stcs(reinterpret_cast<uint4*>(gout + q), *reinterpret_cast<const uint4*>(flat + q));
                     } else {
 #pragma unroll
                         for (int k = 0; k < C; ++k)
