@@ -30,6 +30,28 @@ def test_library_exports_every_declared_symbol():
     assert D.lib().dex_abi_version() == 1
 
 
+def test_enum_values_agree_between_the_header_and_its_bindings():
+    """include/dexb200.h is the contract: the ctypes binding and the Julia extension restate its enum
+    values by hand."""
+    hdr = open(os.path.join(ROOT, "include", "dexb200.h")).read() + open(os.path.join(ROOT, "include", "dex_wire.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    enums = {k: int(v) for k, v in re.findall(r"\b(DEX_[A-Z0-9_]+)\s*=\s*(-?\d+)", hdr)}
+    py = {"DEX_EVAL_EARLY_EXIT": D.EVAL_EARLY_EXIT, "DEX_EVAL_SKIP_INCOMPLETE": D.EVAL_SKIP_INCOMPLETE,
+          "DEX_PACK_FUSED": D.PACK_FUSED, "DEX_PACK_BUMPER": D.PACK_BUMPER, "DEX_GRAD_CONSTANTS": D.GRAD_CONSTANTS,
+          "DEX_GRAD_FEATURES": D.GRAD_FEATURES, "DEX_GRAD_BOTH": D.GRAD_BOTH, "DEX_F32": D.F32, "DEX_F64": D.F64,
+          "DEX_OK": D.OK}
+    for k, v in py.items():
+        assert enums[k] == v, k
+    jl = open(os.path.join(ROOT, "ext", "DynamicExpressionsB200Ext.jl")).read()
+    consts = {}
+    for names, values in re.findall(r"^const (DEX_[A-Z0-9_, ]+?) = ((?:Cint\(-?\d+\)(?:, )?)+)", jl, flags=re.M):
+        for k, v in zip(names.split(", "), re.findall(r"-?\d+", values)):
+            consts[k] = int(v)
+    assert len(consts) >= 9, consts
+    for k, v in consts.items():
+        assert enums.get(k) == v, f"{k} = {v} in the Julia extension, {enums.get(k)} in the header"
+
+
 def test_opcode_lookup_matches_def_file():
     l = D.lib()
     for (name, deg), code in dexb200.OPCODE_TABLE.items():
