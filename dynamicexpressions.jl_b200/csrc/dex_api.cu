@@ -1136,6 +1136,77 @@ int dex_shard_eval_host(dex_ctx* const* ctxs, const dex_population* const* pops,
     return DEX_OK;
 }
 
+// ok[t] = AND over the R shards of flags[r * P + t]
+__global__ void and_flags_kernel(const uint8_t* __restrict__ flags, int R, int64_t P, uint8_t* __restrict__ ok) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= P) return;
+    uint8_t k = 1;
+    for (int r = 0; r < R; ++r) k &= flags[(size_t)r * (size_t)P + (size_t)t];
+    ok[t] = k;
+}
+
+// Sample-sharded evaluation with the result gathered on ONE device of the same process (SURVEY.md
+// §8b `dex_shard_eval` + `dex_gather` as one call): device d evaluates ITS column block (X_devs[d],
+// resident on device d) and its interpreter kernel stores straight into the root device's
+// (n_trees x nsamples) matrix through peer memory — the gather is the kernel's own streaming stores
+// over NVLink, overlapped with the arithmetic, no staging and no collective.  Flags are AND-reduced on
+// the root.  Asynchronous: everything is ordered behind the work already enqueued on ctxs[root]'s
+// stream, and the results are complete in that stream's order (dex_ctx_synchronize(ctxs[root])).
+int dex_shard_eval(dex_ctx* const* ctxs, const dex_population* const* pops, int32_t n_devices,
+                   const void* const* X_devs, int32_t nfeatures, int64_t nsamples, int64_t ldx,
+                   void* out_root_dev, int64_t ldo, uint8_t* ok_root_dev, int32_t root, int eval_flags) {
+    if (!ctxs || !pops || !X_devs || n_devices < 1 || root < 0 || root >= n_devices) return DEX_ERR_INVALID;
+    for (int d = 0; d < n_devices; ++d)
+        if (!ctxs[d] || !pops[d]) return DEX_ERR_INVALID;
+    dex_ctx* cr = ctxs[root];
+    const int64_t P = pops[0]->h.n_trees;
+    const size_t es = pops[0]->h.dtype == DEX_F32 ? 4 : 8;
+    for (int d = 1; d < n_devices; ++d)
+        if (pops[d]->h.n_trees != P || pops[d]->h.dtype != pops[0]->h.dtype)
+            return set_err(cr, DEX_ERR_INVALID, "the per-device populations differ (pack the same trees on every device)");
+    if (ldo < nsamples) return set_err(cr, DEX_ERR_INVALID, "ldo < nsamples");
+    if (P == 0) return DEX_OK;
+    if (!ok_root_dev || (!out_root_dev && nsamples > 0)) return set_err(cr, DEX_ERR_INVALID, "null out / ok");
+    int rc = ensure_device(cr);
+    if (rc) return rc;
+    // the shards' flags land side by side in the root's staging buffer
+    if ((rc = ensure_dev_io(cr, (size_t)n_devices * (size_t)P))) return rc;
+    uint8_t* flags = static_cast<uint8_t*>(cr->dev_io);
+    // peers run behind whatever the root stream holds so far (its output buffer may still be read)
+    CU(cr, cudaEventRecord(cr->ev[0], cr->stream));
+    for (int d = 0; d < n_devices; ++d) {
+        dex_ctx* c = ctxs[d];
+        if ((rc = ensure_device(c))) return rc;      // makes c->device current
+        if (c->device != cr->device) {
+            int can = 0;
+            CU(c, cudaDeviceCanAccessPeer(&can, c->device, cr->device));
+            if (!can)
+                return set_err(cr, DEX_ERR_UNSUPPORTED, "device " + std::to_string(c->device) + " cannot access device " +
+                                                             std::to_string(cr->device) + " (no peer path)");
+            cudaError_t e = cudaDeviceEnablePeerAccess(cr->device, 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+            else if (e != cudaSuccess) return cuda_err(c, e, "cudaDeviceEnablePeerAccess");
+        }
+        if (c != cr) CU(c, cudaStreamWaitEvent(c->stream, cr->ev[0], 0));
+        const int64_t s = nsamples * d / n_devices, e = nsamples * (d + 1) / n_devices;
+        rc = dex_eval(c, pops[d], X_devs[d], nfeatures, e - s, ldx,
+                      out_root_dev ? static_cast<char*>(out_root_dev) + (size_t)s * es : nullptr, ldo,
+                      flags + (size_t)d * (size_t)P, eval_flags & ~DEX_EVAL_SKIP_INCOMPLETE);
+        if (rc != DEX_OK) {
+            if (c != cr) set_err(cr, rc, std::string("device ") + std::to_string(d) + ": " + c->last_error);
+            return rc;
+        }
+    }
+    if ((rc = ensure_device(cr))) return rc;
+    for (int d = 0; d < n_devices; ++d)
+        if (ctxs[d] != cr && ctxs[d]->ev_done_valid) CU(cr, cudaStreamWaitEvent(cr->stream, ctxs[d]->ev_done, 0));
+    and_flags_kernel<<<(unsigned)((P + 255) / 256), 256, 0, cr->stream>>>(flags, n_devices, P, ok_root_dev);
+    cr->launches += 1;
+    cudaError_t le = cudaGetLastError();
+    if (le != cudaSuccess) return cuda_err(cr, le, "flag reduction");
+    return finish_call(cr, DEX_OK);
+}
+
 // plain copies on the context's stream, for hosts that have no CUDA binding of their own (the
 // Julia extension holds device buffers as raw pointers from dex_device_alloc)
 int dex_copy_to_device(dex_ctx* ctx, void* dst_dev, const void* src_host, int64_t bytes) {

@@ -62,6 +62,7 @@ ABI = {
     "dex_eval_loss_grad": (C.c_int, [_P, _P, _P, _I32, _I64, _I64, _P, _P, C.c_int, _P, _P, _P, _U8P]),
     "dex_eval_host": (C.c_int, [_P, _P, _P, _I32, _I64, _I64, _P, _I64, _U8P, C.c_int]),
     "dex_shard_eval_host": (C.c_int, [_P, _P, _I32, _P, _I32, _I64, _I64, _P, _I64, _U8P, C.c_int]),
+    "dex_shard_eval": (C.c_int, [_P, _P, _I32, _P, _I32, _I64, _I64, _P, _I64, _U8P, _I32, C.c_int]),
     "dex_copy_to_device": (C.c_int, [_P, _P, _P, _I64]),
     "dex_copy_to_host": (C.c_int, [_P, _P, _P, _I64]),
     "dex_host_alloc": (C.c_int, [C.POINTER(_P), _I64]),
@@ -569,3 +570,28 @@ def shard_eval_host(pops, X_host, out_host, ok_host, *, early_exit=True):
     pops[0].ctx.check(lib().dex_shard_eval_host(ctxs, hs, n, _ptr(X_host), F, N, F, _ptr(out_host), N, _ptr(ok_host),
                                                 EVAL_EARLY_EXIT if early_exit else 0))
     return out_host, ok_host
+
+
+def shard_eval(pops, X_blocks, out_root, ok_root, *, root=0, early_exit=True):
+    """``dex_shard_eval``: one process, one :class:`Population` (same trees) per device.  ``X_blocks[d]`` is
+    device d's column block of X as a CUDA tensor of shape (F, n_d) with column-major memory (``Xt.T`` of a
+    contiguous (n_d, F) tensor); the (P, N) result and the flags are CUDA tensors on ``pops[root]``'s
+    device, written by every device through peer memory.  Asynchronous in the root context's stream."""
+    n = len(pops)
+    F = X_blocks[0].shape[0]
+    N = sum(int(x.shape[1]) for x in X_blocks)
+    for d, x in enumerate(X_blocks):
+        s, e = N * d // n, N * (d + 1) // n
+        assert x.is_cuda and x.device.index == pops[d].ctx.device and x.shape == (F, e - s)
+        assert x.shape[1] <= 1 or (x.stride(0) == 1 and x.stride(1) >= F), "column-major (F, n) blocks"
+    ldx = max([int(x.stride(1)) for x in X_blocks if x.shape[1] > 1] + [F])
+    assert all(x.shape[1] <= 1 or x.stride(1) == ldx for x in X_blocks)
+    assert out_root.is_cuda and out_root.device.index == pops[root].ctx.device and out_root.stride(1) == 1
+    ctxs = (_P * n)(*[p.ctx.h for p in pops])
+    hs = (_P * n)(*[p.h for p in pops])
+    xs = (_P * n)(*[_ptr(x) for x in X_blocks])
+    for p in pops:
+        p.ctx.use_current_stream()
+    pops[root].ctx.check(lib().dex_shard_eval(ctxs, hs, n, xs, F, N, ldx, _ptr(out_root), out_root.stride(0), _ptr(ok_root),
+                                              root, EVAL_EARLY_EXIT if early_exit else 0))
+    return out_root, ok_root

@@ -239,6 +239,18 @@ int dex_shard_eval_host(dex_ctx* const* ctxs, const dex_population* const* pops,
                         const void* X_host, int32_t nfeatures, int64_t nsamples, int64_t ldx, void* out_host,
                         int64_t ldo, uint8_t* ok_host, int eval_flags);
 
+/* ... and with the result left on ONE device (SURVEY.md §8b `dex_shard_eval` + `dex_gather` in one
+ * call).  X_devs[d]: device d's column block [N d / R, N (d+1) / R) of X, resident on device d,
+ * column-major with leading dimension ldx.  out_root_dev / ok_root_dev live on the device of
+ * ctxs[root]: every device's interpreter kernel stores its block of the (n_trees x nsamples) result
+ * straight into that matrix through peer memory (NVLink), so the gather overlaps the arithmetic and
+ * nothing is staged; ok_root_dev[t] = complete on every shard.  Asynchronous: ordered behind the work
+ * already enqueued on ctxs[root]'s stream, complete in that stream's order.  The multi-PROCESS form
+ * of the same scheme uses dex_ipc_export / dex_ipc_open below.                                   */
+int dex_shard_eval(dex_ctx* const* ctxs, const dex_population* const* pops, int32_t n_devices,
+                   const void* const* X_devs, int32_t nfeatures, int64_t nsamples, int64_t ldx,
+                   void* out_root_dev, int64_t ldo, uint8_t* ok_root_dev, int32_t root, int eval_flags);
+
 /* plain copies on the context's stream for hosts without a CUDA binding of their own (a Julia
  * extension holding dex_device_alloc'ed buffers as raw pointers): to_device is asynchronous (the
  * source must stay valid until the next synchronising call), to_host returns when the bytes

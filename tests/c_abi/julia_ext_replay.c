@@ -14,6 +14,7 @@
  *   7. eval_loss_and_grad(...)                                  -> dex_eval_loss_grad
  *   8. set_constants!                                           -> dex_population_set_constants
  *   9. two contexts on the device, dex_shard_eval_host (the single-process multi-device entry point)
+ *  10. the same with the result gathered on the root device through peer stores: dex_shard_eval
  * Expected values are the closed forms of the reference's own tests / docs (cited below).
  * Exit code 0 = all checks pass; 3 = no CUDA device (every compute call must fail with
  * DEX_ERR_CUDA: no CPU fallback); 1 = failure.                                                   */
@@ -266,6 +267,27 @@ int main(void) {
     CHECK(dex_shard_eval_host(ctxs, pops, 2, XS, F, NS, F, OS, NS, oks, DEX_EVAL_EARLY_EXIT));
     CHECK(dex_eval_host(ctx, pop, XS, F, NS, F, OR, NS, okr, DEX_EVAL_EARLY_EXIT));
     EXPECT(memcmp(OS, OR, sizeof OS) == 0 && memcmp(oks, okr, P) == 0, "sharded == unsharded, bit for bit");
+
+    /* ---- 10. ... with the result gathered on the root DEVICE: dex_shard_eval (every context's kernel
+     *          stores its column block straight into the root's matrix) ------------------------------ */
+    {
+        const int64_t n0 = NS / 2, n1 = NS - n0;           /* blocks [0, NS/2) and [NS/2, NS) */
+        void *dX0 = NULL, *dX1 = NULL, *dOR = NULL, *dKR = NULL;
+        CHECK(dex_device_alloc(ctx, &dX0, (int64_t)(F * n0 * sizeof(double))));
+        CHECK(dex_device_alloc(ctx2, &dX1, (int64_t)(F * n1 * sizeof(double))));
+        CHECK(dex_device_alloc(ctx, &dOR, (int64_t)sizeof OS));
+        CHECK(dex_device_alloc(ctx, &dKR, P));
+        CHECK(dex_copy_to_device(ctx, dX0, XS, (int64_t)(F * n0 * sizeof(double))));
+        CHECK(dex_copy_to_device(ctx2, dX1, XS + F * n0, (int64_t)(F * n1 * sizeof(double))));
+        CHECK(dex_ctx_synchronize(ctx2));
+        const void* xdevs[2] = {dX0, dX1};
+        CHECK(dex_shard_eval(ctxs, pops, 2, xdevs, F, NS, F, dOR, NS, (uint8_t*)dKR, 0, DEX_EVAL_EARLY_EXIT));
+        memset(OS, 0, sizeof OS);
+        CHECK(dex_copy_to_host(ctx, OS, dOR, (int64_t)sizeof OS));      /* root stream order: complete */
+        CHECK(dex_copy_to_host(ctx, oks, dKR, P));
+        EXPECT(memcmp(OS, OR, sizeof OS) == 0 && memcmp(oks, okr, P) == 0, "device-side sharded gather == unsharded");
+        dex_device_free(ctx, dX0); dex_device_free(ctx2, dX1); dex_device_free(ctx, dOR); dex_device_free(ctx, dKR);
+    }
 
     printf("julia_ext_replay: all checks passed (launches=%lld)\n", (long long)dex_ctx_launch_count(ctx));
     dex_device_free(ctx, dX); dex_device_free(ctx, dO); dex_device_free(ctx, dG); dex_device_free(ctx, dK);

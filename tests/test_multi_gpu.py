@@ -103,3 +103,31 @@ def test_single_process_shard_eval_over_two_devices():
     pops[0].eval_host(Xh, ref, rok)
     good = rok.astype(bool)     # rows of incomplete trees are unspecified (early exit)
     assert good.sum() > 50 and (ok == rok).all() and np.array_equal(out[good], ref[good])
+
+
+def test_single_process_shard_eval_gathers_on_the_root_device():
+    """dex_shard_eval: every device's kernel stores its column block straight into the root device's
+    matrix through peer memory; flags are AND-reduced on the root; asynchronous in the root stream."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    import dexb200
+    from dexb200 import device as D, treegen
+    ops = dexb200.OperatorEnum(treegen.OPSET_A)
+    nodes, offsets = treegen.gen_population(300, 7, 2, 4, 5, seed=4)
+    N = 70_000 + 5
+    Xh = np.random.default_rng(3).standard_normal((N, 5)).astype(np.float32)
+    pops = [D.Population(None, ops, np.float32, wire=(nodes, offsets), ctx=D.Context.get(d)) for d in (0, 1)]
+    for root in (0, 1):
+        blocks = []
+        for d in (0, 1):
+            s, e = N * d // 2, N * (d + 1) // 2
+            blocks.append(torch.from_numpy(Xh[s:e]).to(f"cuda:{d}").T)       # (F, n_d), column-major memory
+        out = torch.full((300, N), -3.0, device=f"cuda:{root}")
+        ok = torch.full((300,), 7, dtype=torch.uint8, device=f"cuda:{root}")
+        D.shard_eval(pops, blocks, out, ok, root=root)
+        pops[root].ctx.synchronize()
+        ref, rok = pops[root].eval(torch.from_numpy(Xh).to(f"cuda:{root}").T)
+        torch.cuda.synchronize(root)
+        good = rok.bool()
+        assert int(good.sum()) > 50 and torch.equal(ok, rok)
+        assert torch.equal(out[good], ref[good])
