@@ -206,6 +206,23 @@ function eval_tree_array(trees::AbstractVector{<:AbstractExpressionNode{T}}, X::
                      ctx, pop.handle, cX, F, N, F, out, N, ok, eval_flags(eval_context)))
     return out, ok .!= 0
 end
+"""The same over several devices of this process: device `devices[d]` evaluates the d-th contiguous
+column block of `X` against its own packed copy of the trees and its rows land in place in the result
+(`dex_shard_eval_host`: every device is enqueued before any is waited for)."""
+function eval_tree_array(trees::AbstractVector{<:AbstractExpressionNode{T}}, X::B200Matrix{T}, operators::OperatorEnum,
+                         devices::AbstractVector{<:Integer}; eval_context::Union{EvalContext,Nothing}=nothing) where {T}
+    ctxs = Ptr{Cvoid}[context(d) for d in devices]
+    pops = [population(trees, operators, c; pack_flags=pack_flags(eval_context)) for c in ctxs]
+    handles = Ptr{Cvoid}[p.handle for p in pops]
+    cX = X.data isa Matrix{T} ? X.data : Matrix{T}(X.data)
+    F, N = size(cX)
+    out = Matrix{T}(undef, N, length(trees))
+    ok = Vector{UInt8}(undef, length(trees))
+    GC.@preserve pops check(ctxs[1], ccall((:dex_shard_eval_host, LIB), Cint,
+                     (Ptr{Ptr{Cvoid}}, Ptr{Ptr{Cvoid}}, Int32, Ptr{T}, Int32, Int64, Int64, Ptr{T}, Int64, Ptr{UInt8}, Cint),
+                     ctxs, handles, length(devices), cX, F, N, F, out, N, ok, eval_flags(eval_context)))
+    return out, ok .!= 0
+end
 # the reference's single-tree signature (src/Evaluate.jl:279-285)
 function eval_tree_array(tree::AbstractExpressionNode{T}, X::B200Matrix{T}, operators::OperatorEnum;
                          eval_context::Union{EvalContext,Nothing}=nothing, kws...) where {T}
