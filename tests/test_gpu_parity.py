@@ -667,6 +667,7 @@ def test_native_float32_handlers_are_accurate_to_a_few_ulp():
     loop and, for the operators it does not implement, the C++ handlers.)"""
     rng = np.random.default_rng(99)
     n = 4096
+    no_exit = dexb200.EvalContext(early_exit=False)
     pos = np.exp(rng.uniform(-80.0, 80.0, n)).astype(np.float32)            # wide-range positive
     sgn = (rng.standard_normal(n) * 10.0).astype(np.float32)
     small = rng.uniform(-80.0, 80.0, n).astype(np.float32)
@@ -685,6 +686,12 @@ def test_native_float32_handlers_are_accurate_to_a_few_ulp():
             want = f(x.astype(np.float64))
             assert ok, (name, form)
             np.testing.assert_allclose(y, want, rtol=4e-7, atol=1e-37, err_msg=f"{name}/{form}")
+            # the early_exit = false form of the loop (or the C++ handler it hands over to) and the
+            # Float32 value of the eval_diff kernel's scalar C++ functions: within 2 ulp of the same
+            y2, ok2 = dexb200.eval_tree_array(tree, X, ops, eval_context=no_exit)
+            assert ok2 and np.allclose(y2, y, rtol=2.5e-7, atol=1e-37), (name, form)
+            if name not in ("log", "safe_log"):      # log: polynomial (PTX) vs library (C++), both a few ulp
+                assert np.array_equal(y2, y), (name, form)
     a = (rng.standard_normal(n) * 100).astype(np.float32)
     b = np.where(rng.random(n) < 0.5, -1, 1).astype(np.float32) * np.exp(rng.uniform(-20, 20, n)).astype(np.float32)
     binary = {"+": np.add, "-": np.subtract, "*": np.multiply, "/": np.divide, "max": np.maximum, "min": np.minimum}
@@ -700,6 +707,8 @@ def test_native_float32_handlers_are_accurate_to_a_few_ulp():
             rhs = np.full(n, 2.5) if form == "RC" else b.astype(np.float64)
             assert ok, (name, form)
             np.testing.assert_allclose(y, f(lhs, rhs), rtol=2e-7, atol=1e-37, err_msg=f"{name}/{form}")
+            y2, ok2 = dexb200.eval_tree_array(tree, X, ops, eval_context=no_exit)
+            assert ok2 and np.array_equal(y2, y), (name, form)
 
 
 @pytest.mark.parametrize("name", ["sin", "cos"])
