@@ -1,3 +1,5 @@
+"""Launches one configuration a few times so that ncu can capture its kernel (profiles/run_profile.sh):
+    python benchmarks/profile_target.py C3 | C6"""
 import sys, os
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))

@@ -9,7 +9,7 @@ WHAT=${2:-eval}
 mkdir -p gpurun_out
 if [ "$WHAT" = "grad" ]; then
     ncu --set full --clock-control none --import-source on -k regex:grad_kernel -s 2 -c 1 \
-        -f -o gpurun_out/prof_grad_${TAG} python benchmarks/debug/run_c3.py C3 > gpurun_out/ncu_grad_${TAG}.log 2>&1
+        -f -o gpurun_out/prof_grad_${TAG} python benchmarks/profile_target.py C3 > gpurun_out/ncu_grad_${TAG}.log 2>&1
     exit 0
 fi
 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv \
