@@ -2,7 +2,7 @@
     python benchmarks/profile_target.py C3 | C6"""
 import sys, os
 import numpy as np, torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import dexb200
 from dexb200 import device as D, treegen
 which = sys.argv[1] if len(sys.argv) > 1 else "C3"
