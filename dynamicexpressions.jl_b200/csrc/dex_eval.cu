@@ -517,28 +517,30 @@ __global__ void __launch_bounds__(DEX_MAX_THREADS, (U == 1 && sizeof(T) == 4) ? 
                         T la[K], lb[K], lz[K], lr[K];
 #pragma unroll
                         for (int k = 0; k < K; ++k) { la[k] = va.v[k]; lb[k] = vb.v[k]; lz[k] = acc.v[k]; }
-#pragma unroll(FAST ? 1 : K)
-                        for (int k = 0; k < K; ++k) {
-                            const T x = la[k], y = lb[k], z = lz[k];
-                            T v;
-                            switch (opc) {
-#define U_CASE(SYM, VEXPR, GEXPR) case DEX_OP_##SYM: v = (VEXPR); break;
-                                DEX_UNARY_OPS(U_CASE)
+                        // the opcode dispatch runs ONCE per instruction; each case is a rolled loop over
+                        // the samples (the reference's fused unary kernels substitute Inf where the inner
+                        // value is invalid — `guard`, only observable when early_exit is off)
+#define GEN_LOOP(EXPR)                                                              \
+    _Pragma("unroll 1") for (int k = 0; k < K; ++k) {                               \
+        const T x = la[k], y = lb[k], z = lz[k];                                    \
+        T v = (EXPR);                                                               \
+        if (guard && !t_finite(x)) v = t_inf<T>();                                  \
+        lr[k] = v;                                                                  \
+        (void)y; (void)z;                                                           \
+    }
+                        switch (opc) {
+#define U_CASE(SYM, VEXPR, GEXPR) case DEX_OP_##SYM: GEN_LOOP(VEXPR) break;
+                            DEX_UNARY_OPS(U_CASE)
 #undef U_CASE
-#define B_CASE(SYM, VEXPR, G0, G1) case DEX_OP_##SYM: v = (VEXPR); break;
-                                DEX_BINARY_OPS(B_CASE)
+#define B_CASE(SYM, VEXPR, G0, G1) case DEX_OP_##SYM: GEN_LOOP(VEXPR) break;
+                            DEX_BINARY_OPS(B_CASE)
 #undef B_CASE
-#define T_CASE(SYM, VEXPR, G0, G1, G2) case DEX_OP_##SYM: v = (VEXPR); break;
-                                DEX_TERNARY_OPS(T_CASE)
+#define T_CASE(SYM, VEXPR, G0, G1, G2) case DEX_OP_##SYM: GEN_LOOP(VEXPR) break;
+                            DEX_TERNARY_OPS(T_CASE)
 #undef T_CASE
-                                default: v = t_nan<T>(); break;
-                            }
-                            // the reference's fused unary kernels substitute Inf where the inner
-                            // value is invalid; only observable when early_exit is off
-                            if (guard && !t_finite(x)) v = t_inf<T>();
-                            lr[k] = v;
-                            (void)y; (void)z;
+                            default: GEN_LOOP(t_nan<T>()) break;
                         }
+#undef GEN_LOOP
 #pragma unroll
                         for (int k = 0; k < K; ++k) r.v[k] = lr[k];
                     }
