@@ -132,8 +132,18 @@ __device__ __forceinline__ float m_cos(float x) {
     if (fabsf(x) > 105615.0f) return large_sincosf<1>(x);
     return fast_sincosf<1>(x);
 }
+#ifndef DEX_F64_SINCOS_INLINE
+#define DEX_F64_SINCOS_INLINE 1
+#endif
+#if DEX_F64_SINCOS_INLINE
+// inline: the K samples of a thread are independent, and the library sequences are long chains of
+// dependent DFMAs — interleaved they hide each other's latency, behind a call they run one by one
+__device__ __forceinline__ double m_sin(double x) { return sin(x); }
+__device__ __forceinline__ double m_cos(double x) { return cos(x); }
+#else
 __device__ __forceinline__ double m_sin(double x) { return slow_sin(x); }
 __device__ __forceinline__ double m_cos(double x) { return slow_cos(x); }
+#endif
 
 template <typename T> __device__ __forceinline__ T t_nan();
 template <> __device__ __forceinline__ float t_nan<float>() { return CUDART_NAN_F; }
