@@ -871,6 +871,53 @@ def test_early_exit_leaves_the_other_trees_alone(dtype):
     assert np.array_equal(full[ok], out[ok])
 
 
+def test_contexts_on_several_host_threads_are_independent():
+    """One context per host thread, like the reference's task-local state (SURVEY §8b "Threading"): packing,
+    evaluation and gradients from four threads at once (ctypes releases the GIL inside the library) give
+    the single-threaded answers."""
+    import threading
+    import torch
+    ops = dexb200.OperatorEnum(treegen.OPSET_A)
+    X = np.random.default_rng(12).standard_normal((5, 3000)).astype(np.float32)
+    pops = [treegen.gen_population(120, 6, 2, 4, 5, seed=70 + i) for i in range(4)]
+    want = []
+    for nodes, offsets in pops:
+        pop = D.Population(None, ops, np.float32, wire=(nodes, offsets))
+        o, k = pop.eval(X)
+        _, g, off, gk = pop.eval_grad(X, D.GRAD_FEATURES)
+        want.append((o.cpu().numpy(), k.cpu().numpy(), g.cpu().numpy(), gk.cpu().numpy()))
+    errors = []
+
+    def work(i):
+        try:
+            torch.cuda.set_device(0)
+            ctx = D.Context(0)
+            stream = torch.cuda.Stream()
+            with torch.cuda.stream(stream):
+                for rep in range(6):
+                    nodes, offsets = pops[i]
+                    pop = D.Population(None, ops, np.float32, wire=(nodes, offsets), ctx=ctx)      # re-packed every time
+                    o, k = pop.eval(X)
+                    _, g, off, gk = pop.eval_grad(X, D.GRAD_FEATURES)
+                    stream.synchronize()
+                    o, k, g, gk = o.cpu().numpy(), k.cpu().numpy(), g.cpu().numpy(), gk.cpu().numpy()
+                    good = want[i][1].astype(bool)
+                    ggood = want[i][3].astype(bool)
+                    assert (k == want[i][1]).all() and (gk == want[i][3]).all()
+                    assert np.array_equal(o[good], want[i][0][good])
+                    G = g.reshape(120, -1)
+                    assert np.array_equal(G[ggood], want[i][2].reshape(120, -1)[ggood])
+        except BaseException as e:     # noqa: BLE001 - reported by the main thread
+            errors.append((i, repr(e)))
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errors, errors
+
+
 def test_set_constants_equals_repack(oracle):
     ops = dexb200.OperatorEnum(treegen.OPSET_A)
     nodes, offsets = treegen.gen_population(80, 6, 2, 4, 3, seed=41)
