@@ -15,6 +15,17 @@
 
 #include "../../include/dexb200.h"
 #include "dex_kernels.h"
+// NVTX ranges around the entry points (the reference has no tracing of its own; a profiler that is
+// attached — ncu --nvtx, Nsight Systems — sees `dexb200::<entry point>`; without one a range costs a
+// few nanoseconds).  Header-only: nvtx3 loads the tool's injection library lazily, nothing to link.
+#include <nvtx3/nvToolsExt.h>
+namespace {
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+}  // namespace
+#define DEX_RANGE(name) NvtxRange nvtx_range_("dexb200::" name)
 #include "dex_tape.h"
 
 using namespace dex;
@@ -624,6 +635,7 @@ int dex_optable_destroy(dex_optable* t) {
 int dex_population_pack(dex_ctx* ctx, const dex_optable* ops, const dex_node* nodes,
                         const int64_t* offsets, int64_t n_trees, int dtype, int pack_flags,
                         dex_population** out) {
+    DEX_RANGE("dex_population_pack");
     if (!ctx || !out) return DEX_ERR_INVALID;
     *out = nullptr;
     if (!ops || !offsets || n_trees < 0 || (n_trees > 0 && !nodes)) return set_err(ctx, DEX_ERR_INVALID, "null argument");
@@ -741,6 +753,7 @@ int dex_population_get_constants(dex_ctx* ctx, const dex_population* pop, void* 
 
 int dex_population_set_constants(dex_ctx* ctx, dex_population* pop, const void* values_host,
                                  int64_t n_values) {
+    DEX_RANGE("dex_population_set_constants");
     if (!ctx || !pop || (!values_host && n_values > 0)) return DEX_ERR_INVALID;
     if (n_values != pop->h.n_constants) return set_err(ctx, DEX_ERR_INVALID, "constant count mismatch");
     const size_t es = pop->h.dtype == DEX_F32 ? 4 : 8;
@@ -778,6 +791,7 @@ int dex_population_set_constants(dex_ctx* ctx, dex_population* pop, const void* 
 int dex_eval(dex_ctx* ctx, const dex_population* pop, const void* X_dev, int32_t nfeatures,
              int64_t nsamples, int64_t ldx, void* out_dev, int64_t ldo, uint8_t* ok_dev,
              int eval_flags) {
+    DEX_RANGE("dex_eval");
     int rc = ensure_device(ctx);
     if (rc) return rc;
     if ((rc = check_eval_args(ctx, pop, X_dev, nfeatures, nsamples, ldx, out_dev, ldo, ok_dev))) return rc;
@@ -791,6 +805,7 @@ int dex_eval_parametric(dex_ctx* ctx, const dex_population* pop, const void* X_d
                         int32_t nfeatures, int64_t nsamples, int64_t ldx, const void* params_dev,
                         int32_t n_params, int32_t n_classes, const int32_t* classes_dev,
                         void* out_dev, int64_t ldo, uint8_t* ok_dev, int eval_flags) {
+    DEX_RANGE("dex_eval_parametric");
     int rc = ensure_device(ctx);
     if (rc) return rc;
     if ((rc = check_eval_args(ctx, pop, X_dev, nfeatures, nsamples, ldx, out_dev, ldo, ok_dev))) return rc;
@@ -809,6 +824,7 @@ int dex_eval_parametric(dex_ctx* ctx, const dex_population* pop, const void* X_d
 int dex_eval_loss(dex_ctx* ctx, const dex_population* pop, const void* X_dev, int32_t nfeatures,
                   int64_t nsamples, int64_t ldx, const void* y_dev, const void* weights_dev,
                   double* loss_dev, uint8_t* ok_dev, int eval_flags) {
+    DEX_RANGE("dex_eval_loss");
     int rc = ensure_device(ctx);
     if (rc) return rc;
     if ((rc = check_eval_args(ctx, pop, X_dev, nfeatures, nsamples, ldx, nullptr, 0, ok_dev))) return rc;
@@ -974,6 +990,7 @@ static int run_grad(dex_ctx* ctx, const dex_population* cpop, const void* X, int
 int dex_eval_loss_grad(dex_ctx* ctx, const dex_population* pop, const void* X_dev, int32_t nfeatures,
                        int64_t nsamples, int64_t ldx, const void* y_dev, const void* weights_dev, int mode,
                        double* loss_dev, double* grad_dev, const int64_t* grad_offsets_host, uint8_t* ok_dev) {
+    DEX_RANGE("dex_eval_loss_grad");
     int rc = ensure_device(ctx);
     if (rc) return rc;
     if ((rc = check_eval_args(ctx, pop, X_dev, nfeatures, nsamples, ldx, nullptr, 0, ok_dev))) return rc;
@@ -989,6 +1006,7 @@ int dex_eval_loss_grad(dex_ctx* ctx, const dex_population* pop, const void* X_de
 int dex_eval_grad(dex_ctx* ctx, const dex_population* pop, const void* X_dev, int32_t nfeatures,
                   int64_t nsamples, int64_t ldx, int mode, void* out_dev, int64_t ldo,
                   void* grad_dev, const int64_t* grad_offsets_host, uint8_t* ok_dev) {
+    DEX_RANGE("dex_eval_grad");
     int rc = ensure_device(ctx);
     if (rc) return rc;
     if ((rc = check_eval_args(ctx, pop, X_dev, nfeatures, nsamples, ldx, out_dev, ldo, ok_dev))) return rc;
@@ -1003,6 +1021,7 @@ int dex_eval_grad_parametric(dex_ctx* ctx, const dex_population* pop, const void
                              int64_t nsamples, int64_t ldx, const void* params_dev, int32_t n_params,
                              int32_t n_classes, const int32_t* classes_dev, int mode, void* out_dev,
                              int64_t ldo, void* grad_dev, const int64_t* grad_offsets_host, uint8_t* ok_dev) {
+    DEX_RANGE("dex_eval_grad_parametric");
     int rc = ensure_device(ctx);
     if (rc) return rc;
     if ((rc = check_eval_args(ctx, pop, X_dev, nfeatures, nsamples, ldx, out_dev, ldo, ok_dev))) return rc;
@@ -1019,6 +1038,7 @@ int dex_eval_grad_parametric(dex_ctx* ctx, const dex_population* pop, const void
 int dex_eval_diff(dex_ctx* ctx, const dex_population* pop, const void* X_dev, int32_t nfeatures,
                   int64_t nsamples, int64_t ldx, int32_t direction, void* out_dev, void* dout_dev,
                   int64_t ldo, uint8_t* ok_dev) {
+    DEX_RANGE("dex_eval_diff");
     int rc = ensure_device(ctx);
     if (rc) return rc;
     if ((rc = check_eval_args(ctx, pop, X_dev, nfeatures, nsamples, ldx, out_dev, ldo, ok_dev))) return rc;
@@ -1086,6 +1106,7 @@ static int host_eval_wait(dex_ctx* ctx) {
 int dex_eval_host(dex_ctx* ctx, const dex_population* pop, const void* X_host, int32_t nfeatures,
                   int64_t nsamples, int64_t ldx, void* out_host, int64_t ldo, uint8_t* ok_host,
                   int eval_flags) {
+    DEX_RANGE("dex_eval_host");
     int rc = host_eval_enqueue(ctx, pop, X_host, nfeatures, nsamples, ldx, out_host, ldo, ok_host, eval_flags);
     if (rc) return rc;
     return host_eval_wait(ctx);
@@ -1099,6 +1120,7 @@ int dex_eval_host(dex_ctx* ctx, const dex_population* pop, const void* X_host, i
 int dex_shard_eval_host(dex_ctx* const* ctxs, const dex_population* const* pops, int32_t n_devices,
                         const void* X_host, int32_t nfeatures, int64_t nsamples, int64_t ldx, void* out_host,
                         int64_t ldo, uint8_t* ok_host, int eval_flags) {
+    DEX_RANGE("dex_shard_eval_host");
     if (!ctxs || !pops || n_devices < 1) return DEX_ERR_INVALID;
     for (int d = 0; d < n_devices; ++d)
         if (!ctxs[d] || !pops[d]) return DEX_ERR_INVALID;
@@ -1155,6 +1177,7 @@ __global__ void and_flags_kernel(const uint8_t* __restrict__ flags, int R, int64
 int dex_shard_eval(dex_ctx* const* ctxs, const dex_population* const* pops, int32_t n_devices,
                    const void* const* X_devs, int32_t nfeatures, int64_t nsamples, int64_t ldx,
                    void* out_root_dev, int64_t ldo, uint8_t* ok_root_dev, int32_t root, int eval_flags) {
+    DEX_RANGE("dex_shard_eval");
     if (!ctxs || !pops || !X_devs || n_devices < 1 || root < 0 || root >= n_devices) return DEX_ERR_INVALID;
     for (int d = 0; d < n_devices; ++d)
         if (!ctxs[d] || !pops[d]) return DEX_ERR_INVALID;
