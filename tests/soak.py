@@ -49,11 +49,15 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--rounds", type=int, default=40)
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--grad", action="store_true", help="also compare gradients (small rounds only)")
     args = ap.parse_args()
     import dexb200
     from dexb200 import treegen
     from oracle import oracle
-    from tests.test_gpu_parity import _check_population
+    from dexb200 import device as D
+    from tests.parity_util import check_trees
+    from tests.test_gpu_parity import _check_population, _flags_agree, _grad_verdict
+    from tests.test_gpu_parity_full import _grad_yardsticks
     oracle.lib()
     rng = np.random.default_rng(args.seed)
     suspects = []
@@ -72,7 +76,32 @@ def main():
             suspects.append(r)
             print("SUSPECT", label, "\n   ", str(e)[:400], flush=True)
             continue
-        print(f"ok   {label}: {int(ok.sum())}/{P} complete, {len(errs)} compared, {time.time() - t0:.1f} s", flush=True)
+        # gradients of the same population (a mode per round; sizes capped: the oracle materialises (G x N) per tree)
+        gnote = ""
+        if args.grad and P * N <= 400_000:
+            mode = [D.GRAD_FEATURES, D.GRAD_CONSTANTS, D.GRAD_BOTH][r % 3]
+            omode = [oracle.GRAD_FEATURES, oracle.GRAD_CONSTANTS, oracle.GRAD_BOTH][r % 3]
+            try:
+                pop = D.Population(None, ops, dtype, wire=(nodes, offsets))
+                out, grad, off, gok = pop.eval_grad(X, mode)
+                out, grad, gok = out.cpu().numpy(), grad.cpu().numpy(), gok.cpu().numpy().astype(bool)
+                ref, rgrads, rok = oracle.eval_grad_population(nodes, offsets, ops.opcodes, X, omode)
+                _, _, rok_e = oracle.eval_grad_population(nodes, offsets, ops.opcodes, X, omode | oracle.GRAD_ELEMENTWISE)
+                _flags_agree(gok, rok, rok_e, "grad")
+                yards = _grad_yardsticks(oracle, nodes, offsets, ops, X, omode)
+                verdicts, ids = [], []
+                for t in np.nonzero(rok)[0]:
+                    G = rgrads[t].shape[0]
+                    g = grad[off[t]:off[t + 1]].reshape(N, G).T if G else np.zeros((0, N), dtype)
+                    verdicts.append(_grad_verdict(dtype, out[t], g, ref[t], rgrads[t], [(y[t], yg[t]) for y, yg in yards]))
+                    ids.append(int(t))
+                check_trees("", dtype, verdicts, min_strict=0.0, ids=ids)
+                gnote = f"; gradients (mode {r % 3}) of {len(ids)} trees agree"
+            except AssertionError as e:
+                suspects.append(r)
+                print("SUSPECT (gradient)", label, "\n   ", str(e)[:400], flush=True)
+                continue
+        print(f"ok   {label}: {int(ok.sum())}/{P} complete, {len(errs)} compared{gnote}, {time.time() - t0:.1f} s", flush=True)
     print(f"{args.rounds - len(suspects)} of {args.rounds} rounds agree; to triage: {suspects}")
     return 1 if suspects else 0
 
