@@ -34,6 +34,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <map>
+#include <mutex>
 #include <utility>
 
 // samples per thread = DEX_EVAL_U chunks of 16 bytes (8 floats / 4 doubles for U = 2)
@@ -847,11 +848,16 @@ __global__ void fold_kernel(Instr* tape, const Instr* ctape, const int64_t* seg,
     if (t < n_trees) fold_ok[t] = fold_tree<T, GRAD>(tape, ctape, seg, seg_off, t) ? 1 : 0;
 }
 
+// The attribute belongs to the (device, function), not to the calling thread: the record of what
+// has been granted is process-wide and the limit is only ever raised — a thread that needs less
+// must not lower it under a launch that another thread has sized for more.
 cudaError_t ensure_dynamic_smem(const void* kernel, size_t bytes) {
-    static thread_local std::map<std::pair<int, const void*>, size_t> granted;
+    static std::mutex m;
+    static std::map<std::pair<int, const void*>, size_t> granted;
     int dev = 0;
     cudaError_t err = cudaGetDevice(&dev);
     if (err != cudaSuccess) return err;
+    std::lock_guard<std::mutex> lk(m);
     size_t& have = granted[std::make_pair(dev, kernel)];
     if (bytes <= have) return cudaSuccess;
     err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);

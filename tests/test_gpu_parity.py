@@ -878,10 +878,13 @@ def test_contexts_on_several_host_threads_are_independent():
     import threading
     import torch
     ops = dexb200.OperatorEnum(treegen.OPSET_A)
-    X = np.random.default_rng(12).standard_normal((5, 3000)).astype(np.float32)
-    pops = [treegen.gen_population(120, 6, 2, 4, 5, seed=70 + i) for i in range(4)]
+    # a different number of features per thread: the launches need different amounts of dynamic shared
+    # memory, and that limit is an attribute of the (device, kernel), shared by all threads
+    Fs = (2, 5, 8, 11)
+    Xs = [np.random.default_rng(12 + i).standard_normal((F, 3000)).astype(np.float32) for i, F in enumerate(Fs)]
+    pops = [treegen.gen_population(120, 6, 2, 4, F, seed=70 + i) for i, F in enumerate(Fs)]
     want = []
-    for nodes, offsets in pops:
+    for (nodes, offsets), X in zip(pops, Xs):
         pop = D.Population(None, ops, np.float32, wire=(nodes, offsets))
         o, k = pop.eval(X)
         _, g, off, gk = pop.eval_grad(X, D.GRAD_FEATURES)
@@ -894,6 +897,7 @@ def test_contexts_on_several_host_threads_are_independent():
             ctx = D.Context(0)
             stream = torch.cuda.Stream()
             with torch.cuda.stream(stream):
+                X = Xs[i]
                 for rep in range(6):
                     nodes, offsets = pops[i]
                     pop = D.Population(None, ops, np.float32, wire=(nodes, offsets), ctx=ctx)      # re-packed every time
