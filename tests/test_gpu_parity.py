@@ -922,6 +922,39 @@ def test_contexts_on_several_host_threads_are_independent():
     assert not errors, errors
 
 
+def test_pack_evaluate_destroy_cycles_do_not_leak():
+    """Callers whose trees change every generation pack and destroy a population per step; contexts come
+    and go with their threads.  Device memory must come back (the population pool recycles blocks)."""
+    import gc
+    import torch
+    ops = dexb200.OperatorEnum(treegen.OPSET_A)
+    X = torch.randn((1000, 5), device="cuda")
+
+    def cycle(ctx, n, seed0):
+        for i in range(n):
+            nodes, offsets = treegen.gen_population(50 + 37 * (i % 5), 5 + i % 3, 2, 4, 5, seed=seed0 + i)
+            pop = D.Population(None, ops, np.float32, wire=(nodes, offsets), ctx=ctx)
+            pop.eval(X.T)
+            if i % 7 == 0:
+                pop.eval_grad(X.T, D.GRAD_BOTH)
+            del pop
+    ctx = D.Context(0)
+    cycle(ctx, 40, 0)                     # fills the pools / scratch buffers once
+    torch.cuda.synchronize()
+    gc.collect()
+    free0, _ = torch.cuda.mem_get_info()
+    cycle(ctx, 300, 1000)
+    for k in range(10):                   # short-lived contexts
+        c = D.Context(0)
+        cycle(c, 3, 5000 + 10 * k)
+        c.synchronize()
+        del c
+    torch.cuda.synchronize()
+    gc.collect()
+    free1, _ = torch.cuda.mem_get_info()
+    assert free0 - free1 < 64 << 20, f"device memory shrank by {(free0 - free1) >> 20} MiB over 330 pack/destroy cycles"
+
+
 def test_set_constants_equals_repack(oracle):
     ops = dexb200.OperatorEnum(treegen.OPSET_A)
     nodes, offsets = treegen.gen_population(80, 6, 2, 4, 3, seed=41)
