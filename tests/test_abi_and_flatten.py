@@ -52,6 +52,21 @@ def test_enum_values_agree_between_the_header_and_its_bindings():
         assert enums.get(k) == v, f"{k} = {v} in the Julia extension, {enums.get(k)} in the header"
 
 
+def test_safe_pow_is_the_power_operator(oracle):
+    """`safe_pow(x, y) = x < 0 && y != round(y) ? NaN : x^y` of the reference's tests (test/test_parse.jl:66,
+    test/test_symbolic_utils.jl:9-10) is what the table's `^` computes: C pow returns NaN exactly where
+    Julia's `^` throws."""
+    assert dexb200.opcode_of("safe_pow", 2) == dexb200.opcode_of("^", 2)
+    ops = dexb200.OperatorEnum({2: ("safe_pow", "+")})
+    N_ = dexb200.Node
+    tree = N_(1, N_(feature=1, T=np.float64), N_(feature=2, T=np.float64))
+    X = np.array([[-2.0, -2.0, 2.0, 0.0], [2.0, 0.5, 0.5, 3.0]])
+    y, _ = oracle.eval_tree_array(dexb200.to_wire(tree), ops.opcodes, X, 0)      # early_exit off: every value
+    assert np.isnan(y[1]) and y[0] == 4.0 and y[2] == 2.0 ** 0.5 and y[3] == 0.0
+    _, ok = oracle.eval_tree_array(dexb200.to_wire(tree), ops.opcodes, X)
+    assert not ok
+
+
 def test_opcode_lookup_matches_def_file():
     l = D.lib()
     for (name, deg), code in dexb200.OPCODE_TABLE.items():
