@@ -47,6 +47,9 @@
 #ifndef DEX_MIN_CTAS
 #define DEX_MIN_CTAS 3
 #endif
+#ifndef DEX_PTX_INTERP_F64
+#define DEX_PTX_INTERP_F64 1
+#endif
 #ifndef DEX_PACKED_FP32
 #define DEX_PACKED_FP32 1
 #endif
@@ -591,6 +594,28 @@ __global__ void __launch_bounds__(DEX_MAX_THREADS, (U == 1 && sizeof(T) == 4) ? 
                         : "l"(ip), "r"(n), "r"(my_s), "r"(tile_b), "r"(cs_b), "l"(__cvta_generic_to_global(k_inv_pio4))
                         : "memory");
                 }
+                if (pc < n) {   // handed over: ins0 is already two instructions ahead
+                    step(__ldg(ip + pc));
+                    ++pc;
+                    ins0 = __ldg(ip + pc);
+                }
+            }
+        } else if constexpr (DEX_PTX_INTERP_F64 && sizeof(T) == 8 && U == 2 && FAST) {
+            // Float64: the same loop with scalar double arithmetic (gen_interp_f64_ptx.py): loads, + - * /
+            // max min and the cheap unary handlers are native, the transcendental ones are handed to
+            // `step` (the library's double-precision sequences)
+            const uint32_t my_s = (uint32_t)__cvta_generic_to_shared(my);
+            const uint32_t tile_b = (uint32_t)TILE * 8u, cs_b = (uint32_t)CS * 8u;
+            int pc = 0;
+            double* av = reinterpret_cast<double*>(acc.v);
+            double* nfv = reinterpret_cast<double*>(nf);
+            while (pc < n) {
+                asm volatile(
+#include "dex_interp_f64.inc"
+                    : "+r"(pc), "+d"(av[0]), "+d"(av[1]), "+d"(av[2]), "+d"(av[3]), "+d"(nfv[0]), "+d"(nfv[1]),
+                      "+r"(ins0.x), "+r"(ins0.y), "+r"(ins0.z), "+r"(ins0.w)
+                    : "l"(ip), "r"(n), "r"(my_s), "r"(tile_b), "r"(cs_b)
+                    : "memory");
                 if (pc < n) {   // handed over: ins0 is already two instructions ahead
                     step(__ldg(ip + pc));
                     ++pc;
