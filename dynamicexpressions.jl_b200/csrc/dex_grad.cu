@@ -392,9 +392,13 @@ __device__ __forceinline__ void combine_un(T (&ad)[GC][VK<T, U>::K], const T (&p
 #include DEX_GRAD_INC
 // runs the generated loop for (GC, U, NT) when it exists; otherwise leaves pc untouched and the
 // C++ `step` executes the whole tape
-template <int GC, int U, int NT, typename... A>
+template <typename T, int GC, int U, int NT, typename... A>
 __device__ __forceinline__ void ptx_loop(A&&... a) {
-    if constexpr (GradLoopF32<GC, U, NT>::exists) GradLoopF32<GC, U, NT>::run(static_cast<A&&>(a)...);
+    if constexpr (sizeof(T) == 4) {
+        if constexpr (GradLoopF32<GC, U, NT>::exists) GradLoopF32<GC, U, NT>::run(static_cast<A&&>(a)...);
+    } else {
+        if constexpr (GradLoopF64<GC, U, NT>::exists) GradLoopF64<GC, U, NT>::run(static_cast<A&&>(a)...);
+    }
 }
 #endif
 
@@ -686,7 +690,9 @@ __global__ void __launch_bounds__(DEX_GRAD_THREADS, DEX_GRAD_MIN_CTAS) grad_kern
             // registers): the Float32 256- and 128-thread launches run the instruction loop as one inline-PTX
             // block with jump-table dispatch (gen_grad_ptx.py), which returns at the end of the tape
             // or at the first instruction it does not implement natively; `step` executes that one.
-            constexpr bool HAS_PTX = DEX_GRAD_PTX && sizeof(T) == 4 && !DIFF;
+            // (Float64: the same generated structure with one double per 64-bit register; + - * / neg
+            // square cube inv sqrt native, the rest handed to `step`)
+            constexpr bool HAS_PTX = DEX_GRAD_PTX && !DIFF;
             if (pass > 0) ins = __ldg(ip);
             int pc = 0;
             while (pc < n) {
@@ -695,13 +701,13 @@ __global__ void __launch_bounds__(DEX_GRAD_THREADS, DEX_GRAD_MIN_CTAS) grad_kern
                     // the loops are generated per CTA size (row strides are immediates)
                     if (nthr == 256 || nthr == 128) {
                         const uint32_t my_s = (uint32_t)__cvta_generic_to_shared(my);
-                        float nfa[2] = {nf, 0.f};
+                        T nfa[2] = {nf, T(0)};
                         if (nthr == 256)
-                            ptx_loop<GC, U, 256>(pc, av, ad, nfa, ins, ip, n, my_s, S, S * GC, foff - S, coff, ordp,
-                                                 mode != DEX_GRAD_FEATURES ? 1 : 0);
+                            ptx_loop<T, GC, U, 256>(pc, av, ad, nfa, ins, ip, n, my_s, S, S * GC, foff - S, coff, ordp,
+                                                    mode != DEX_GRAD_FEATURES ? 1 : 0);
                         else
-                            ptx_loop<GC, U, 128>(pc, av, ad, nfa, ins, ip, n, my_s, S, S * GC, foff - S, coff, ordp,
-                                                 mode != DEX_GRAD_FEATURES ? 1 : 0);
+                            ptx_loop<T, GC, U, 128>(pc, av, ad, nfa, ins, ip, n, my_s, S, S * GC, foff - S, coff, ordp,
+                                                    mode != DEX_GRAD_FEATURES ? 1 : 0);
                         nf = nfa[0] + nfa[1];
                         if (pc < n) ins = __ldg(ip + pc);   // early exit: `ins` is two instructions ahead
                     }
