@@ -390,7 +390,8 @@ int run_eval(dex_ctx* ctx, const dex_population* cpop, const void* X, int32_t F,
     int threads;
     size_t smem;
     const int32_t front_rows = h.max_stack + h.n_param_rows;
-    const int64_t n_tiles = eval_num_tiles(h.dtype, F, front_rows, N, &threads, &smem);
+    const bool wide_ok = (eval_flags & DEX_EVAL_EARLY_EXIT) && !params;   // as launch_eval decides
+    const int64_t n_tiles = eval_num_tiles(h.dtype, F, front_rows, N, &threads, &smem, wide_ok);
     if (n_tiles_out) *n_tiles_out = n_tiles;
     if (smem > 227 * 1024)
         return set_err(ctx, DEX_ERR_UNSUPPORTED,
@@ -418,15 +419,26 @@ int run_eval(dex_ctx* ctx, const dex_population* cpop, const void* X, int32_t F,
     a.n_chunks = (int32_t)n_chunks;
     a.max_stack = h.max_stack;
     a.n_param_rows = h.n_param_rows;
-    if ((rc = ensure_xt(ctx, eval_xt_bytes(h.dtype, F, front_rows, N)))) return rc;
+    if ((rc = ensure_xt(ctx, eval_xt_bytes(h.dtype, F, front_rows, N, wide_ok)))) return rc;
     a.X = X; a.F = F; a.N = N; a.ldx = ldx; a.xt = ctx->xt;
     a.out = out; a.ldo = ldo; a.ok = ok;
     a.early_exit = (eval_flags & DEX_EVAL_EARLY_EXIT) ? 1 : 0;
     a.params = params; a.n_params = n_params; a.n_classes = n_classes; a.classes = classes;
     a.y = y; a.w = w; a.loss_partial = loss_partial;
-    // per-tree CTA barrier of the store path: -3 % on C6, +4 % on C2, +3 % on C4 — off (the fused
-    // loss, whose epilogue is longer, always re-aligns: DEX_LOSS_SYNC in dex_eval.cu)
-    a.sync_tree = getenv("DEXB200_SYNC_TREE") ? 1 : 0;
+    // CTA barrier every sync_tree-th tree (a power of two, 0 = never): off.  With the single-chain loss
+    // epilogue of earlier versions the warps of a CTA drifted apart without one (+7 %); with four
+    // accumulation chains the barrier only costs: C6-loss every tree 40.96 ms, every 2nd 40.30, 4th 39.75,
+    // 8th 39.65, 32nd 39.22, never 39.13.  Store path (C2 / C4 shard / C6): never 0.2888 / 14.79 / 37.81,
+    // every 8th 0.2887 / 14.86 / 38.25, every 4th 0.353 / 14.96 / 38.64.
+    {
+        auto pow2 = [](const char* env, int dflt) {
+            if (!env) return dflt;
+            int v = atoi(env), p = 0;
+            while (v > 1) { v >>= 1; ++p; }
+            return atoi(env) <= 0 ? 0 : 1 << p;
+        };
+        a.sync_tree = y ? pow2(getenv("DEXB200_LOSS_SYNC"), 0) : pow2(getenv("DEXB200_SYNC_TREE"), 0);
+    }
     int launches = 0;
     if (!out_host) {
         cudaError_t e = launch_eval(a, ctx->stream, ctx->sm_count, &launches);
@@ -832,7 +844,8 @@ int dex_eval_loss(dex_ctx* ctx, const dex_population* pop, const void* X_dev, in
     if (pop->h.max_parameter >= 0) return set_err(ctx, DEX_ERR_INVALID, "population has parameter leaves");
     if (pop->h.n_trees == 0) return DEX_OK;
     int threads; size_t smem;
-    const int64_t n_tiles = eval_num_tiles(pop->h.dtype, nfeatures, pop->h.folded->max_stack + pop->h.n_param_rows, std::max<int64_t>(nsamples, 1), &threads, &smem);
+    const int64_t n_tiles = eval_num_tiles(pop->h.dtype, nfeatures, pop->h.folded->max_stack + pop->h.n_param_rows, std::max<int64_t>(nsamples, 1), &threads, &smem,
+                                           (eval_flags & DEX_EVAL_EARLY_EXIT) != 0);
     // scratch: [sum of weights (256 B slot)] [partial sums: one per (tile, warp slot, tree); warps a
     // smaller CTA does not have leave their zero]
     constexpr int64_t kWarpSlots = 8;   // DEX_MAX_THREADS / 32 (dex_eval.cu)

@@ -56,8 +56,15 @@
 #ifndef DEX_MAX_THREADS
 #define DEX_MAX_THREADS 256
 #endif
-#ifndef DEX_LOSS_SYNC
-#define DEX_LOSS_SYNC 1
+// residual of the fused loss: the exact difference of the two values in double (default), or the
+// difference rounded to T first (what a caller computing `pred .- y` in T would square)
+#ifndef DEX_LOSS_RESIDUAL_IN_T
+#define DEX_LOSS_RESIDUAL_IN_T 0
+#endif
+#if DEX_LOSS_RESIDUAL_IN_T
+#define DEX_LOSS_RESIDUAL(v, y) ((double)((v) - (y)))
+#else
+#define DEX_LOSS_RESIDUAL(v, y) ((double)(v) - (double)(y))
 #endif
 #ifndef DEX_SYNC_TREE
 #define DEX_SYNC_TREE 0
@@ -200,6 +207,10 @@ template <typename T> struct KArgs {
     // eight warps then share tape lines in L1 and handler code in the instruction cache (C6: -3 %);
     // with long tapes or the parametric gather the barrier costs more than it saves (C4: +3 %)
     int32_t sync_tree;
+    // wide inputs (GX kernels): rows [0, smem_rows) live in shared memory (the stack rows and the
+    // first smem_rows - max_stack features), the remaining feature rows are read from the
+    // feature-major global copy through L1 — a third CTA fits per SM
+    int32_t smem_rows;
 };
 
 // A row vector of one thread: U chunks of C elements.
@@ -252,7 +263,7 @@ __device__ __forceinline__ void guard_inf(Vec<T, U>& r, const Vec<T, U>& x) {
 
 // NT: CTA size fixed at compile time (the full-size 256-thread launch: row and chunk strides
 // become immediates of the shared-memory accesses) or 0 = read blockDim.x.
-template <typename T, int U, bool FAST, bool PARAM, bool LOSS, int NT = 0>
+template <typename T, int U, bool FAST, bool PARAM, bool LOSS, int NT = 0, bool GX = false>
 __global__ void __launch_bounds__(DEX_MAX_THREADS, (U == 1 && sizeof(T) == 4) ? 4 : DEX_MIN_CTAS) eval_kernel(const KArgs<T> a) {
     using V = Vec<T, U>;
     constexpr int C = V::C;
@@ -275,13 +286,14 @@ __global__ void __launch_bounds__(DEX_MAX_THREADS, (U == 1 && sizeof(T) == 4) ? 
         T* xs = rows + (size_t)(a.max_stack + a.n_param_rows) * TILE;
         const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&stage_bar);
         const uint32_t row_bytes = (uint32_t)TILE * (uint32_t)sizeof(T);
+        const int FS = GX ? a.smem_rows - a.max_stack - a.n_param_rows : a.F;   // features staged
         if (tid == 0) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar),
-                         "r"(row_bytes * (uint32_t)a.F)
+                         "r"(row_bytes * (uint32_t)FS)
                          : "memory");
-            for (int f = 0; f < a.F; ++f) {
+            for (int f = 0; f < FS; ++f) {
                 const uint32_t dst = (uint32_t)__cvta_generic_to_shared(xs + (size_t)f * TILE);
                 const T* src = a.X + (size_t)f * a.ldx + s0;
                 asm volatile(
@@ -291,7 +303,7 @@ __global__ void __launch_bounds__(DEX_MAX_THREADS, (U == 1 && sizeof(T) == 4) ? 
             }
         }
         __syncthreads();  // the barrier is initialised before anybody polls it
-        if (a.F > 0) {
+        if (FS > 0) {
             uint32_t done = 0;
             while (!done) {
                 asm volatile(
@@ -328,6 +340,9 @@ __global__ void __launch_bounds__(DEX_MAX_THREADS, (U == 1 && sizeof(T) == 4) ? 
     __syncthreads();
 
     T* my = rows + tid * C;  // this thread's first chunk inside row 0
+    // GX: this thread's first chunk of "row 0" in the global copy (feature f is row
+    // max_stack + n_param_rows + f; the base is moved back by that many rows)
+    const T* xg = GX ? a.X + s0 + tid * C - (int64_t)(a.max_stack + a.n_param_rows) * a.ldx : nullptr;
     const int t0 = a.chunk_start[blockIdx.y], t1 = a.chunk_start[blockIdx.y + 1];
     const bool early = FAST ? true : (a.early_exit != 0);
     const bool full_tile_samples = s0 + TILE <= a.N;
@@ -340,7 +355,9 @@ __global__ void __launch_bounds__(DEX_MAX_THREADS, (U == 1 && sizeof(T) == 4) ? 
     int64_t off = a.tape_off[t0], off_next = a.tape_off[t0 + 1];
     uint4 ins0 = __ldg(a.tape + off);   // instruction at the current pc of the PTX loop
     for (int t = t0; t < t1; ++t) {
-        if (DEX_SYNC_TREE || (!PARAM && !LOSS && a.sync_tree)) __syncthreads();
+        // every sync_tree-th tree (a power of two; 0 = never) the warps of the CTA are re-aligned: they
+        // share tape lines in L1 and handler code in the instruction cache
+        if (DEX_SYNC_TREE || (!PARAM && a.sync_tree && (t & (a.sync_tree - 1)) == 0)) __syncthreads();
         const int n = (int)(off_next - off);
         const uint4* ip = a.tape + off;
         const int64_t off_next2 = a.tape_off[t + 2];   // slack behind the table: dex_api.cu upload()
@@ -366,6 +383,10 @@ __global__ void __launch_bounds__(DEX_MAX_THREADS, (U == 1 && sizeof(T) == 4) ? 
             const uint32_t w0 = ins.x;
             const T* ra = my + (size_t)row_a(ins.y) * TILE;
             const T* rb = my + (size_t)row_b(ins.y) * TILE;
+            if constexpr (GX) {
+                if ((int)row_a(ins.y) >= a.smem_rows) ra = xg + (int64_t)row_a(ins.y) * a.ldx;
+                if ((int)row_b(ins.y) >= a.smem_rows) rb = xg + (int64_t)row_b(ins.y) * a.ldx;
+            }
             const T c = const_of<T>(ins);
             V cv;  // the inline constant broadcast over the K samples
 #pragma unroll
@@ -569,7 +590,16 @@ __global__ void __launch_bounds__(DEX_MAX_THREADS, (U == 1 && sizeof(T) == 4) ? 
             float* av = reinterpret_cast<float*>(acc.v);
             float* nfv = reinterpret_cast<float*>(nf);
             while (pc < n) {
-                if constexpr (U == 2 && FAST) {
+                if constexpr (U == 2 && FAST && GX) {
+                    asm volatile(
+#include "dex_interp_f32_gx.inc"
+                        : "+r"(pc), "+f"(av[0]), "+f"(av[1]), "+f"(av[2]), "+f"(av[3]), "+f"(av[4]), "+f"(av[5]),
+                          "+f"(av[6]), "+f"(av[7]), "+f"(nfv[0]), "+f"(nfv[1]), "+r"(ins0.x), "+r"(ins0.y),
+                          "+r"(ins0.z), "+r"(ins0.w)
+                        : "l"(ip), "r"(n), "r"(my_s), "r"(tile_b), "r"(cs_b), "l"(__cvta_generic_to_global(k_inv_pio4)),
+                          "r"((uint32_t)a.smem_rows), "l"(__cvta_generic_to_global(xg)), "r"((uint32_t)a.ldx * 4u)
+                        : "memory");
+                } else if constexpr (U == 2 && FAST) {
                     asm volatile(
 #include "dex_interp_f32.inc"
                         : "+r"(pc), "+f"(av[0]), "+f"(av[1]), "+f"(av[2]), "+f"(av[3]), "+f"(av[4]), "+f"(av[5]),
@@ -645,6 +675,8 @@ __global__ void __launch_bounds__(DEX_MAX_THREADS, (U == 1 && sizeof(T) == 4) ? 
             }
         }
 
+        const bool bad = (nf[0] != nf[0]) || (nf[1] != nf[1]);
+        const bool warp_bad = __any_sync(0xffffffffu, bad);
         // ---- result row segment ----------------------------------------------------
         if (!LOSS) {
             T* o = a.out + (size_t)t * a.ldo + s0 + (size_t)tid * C;
@@ -659,45 +691,39 @@ __global__ void __launch_bounds__(DEX_MAX_THREADS, (U == 1 && sizeof(T) == 4) ? 
                     if (s0 + s < a.N) a.out[(size_t)t * a.ldo + s0 + s] = acc.v[k];
                 }
             }
+        } else if (FAST && warp_bad) {
+            // an incomplete tree has no loss (its row is unspecified under early exit): NaN, no epilogue
+            if ((tid & 31) == 0)
+                a.loss_partial[((size_t)blockIdx.x * (DEX_MAX_THREADS / 32) + (tid >> 5)) * a.n_trees + t] =
+                    __longlong_as_double(0x7ff8000000000000LL);
         } else {
             // fused loss: sum_j w_j (v_j - y_j)^2 over this warp's samples, in double (the caller's
             // yardstick is the float64 reduction of the float32 values).  One partial per (tile, warp,
             // tree) goes straight to global memory — no shared memory, no barrier; the second-stage
             // kernel adds the partials in a fixed order (deterministic).
-            double ls = 0.0;
-            if (a.w) {
+            // Four independent accumulation chains per thread (a single chain of K dependent DFMAs
+            // is pure latency in front of the warp reduction and the barrier).
+            double lp[4] = {0.0, 0.0, 0.0, 0.0};
+            if (a.w || !full_tile_samples) {   // w_j given, or 1 with 0 on the padded tail of the last tile
 #pragma unroll
                 for (int k = 0; k < K; ++k) {
-                    const double d = (double)acc.v[k] - (double)yv[k];
-                    ls = fma((double)wv[k] * d, d, ls);
+                    const double d = DEX_LOSS_RESIDUAL(acc.v[k], yv[k]);
+                    lp[k & 3] = fma((double)wv[k] * d, d, lp[k & 3]);
                 }
-            } else {   // w_j = 1 (0 on the padded tail of the last tile)
+            } else {
 #pragma unroll
                 for (int k = 0; k < K; ++k) {
-                    const double d = (double)acc.v[k] - (double)yv[k];
-                    ls = fma(d, d, ls);
-                }
-                if (!full_tile_samples) {
-                    ls = 0.0;
-#pragma unroll
-                    for (int k = 0; k < K; ++k) {
-                        const double d = (double)acc.v[k] - (double)yv[k];
-                        ls = fma((double)wv[k] * d, d, ls);
-                    }
+                    const double d = DEX_LOSS_RESIDUAL(acc.v[k], yv[k]);
+                    lp[k & 3] = fma(d, d, lp[k & 3]);
                 }
             }
+            double ls = (lp[0] + lp[1]) + (lp[2] + lp[3]);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) ls += __shfl_xor_sync(0xffffffffu, ls, o);
             if ((tid & 31) == 0)
                 a.loss_partial[((size_t)blockIdx.x * (DEX_MAX_THREADS / 32) + (tid >> 5)) * a.n_trees + t] = ls;
-#if DEX_LOSS_SYNC
-            // keeps the warps of the CTA on the same tree: they share tape lines in L1 and handler
-            // code in the instruction cache (measured: without it the fused loss is 7 % slower)
-            __syncthreads();
-#endif
         }
-        const bool bad = (nf[0] != nf[0]) || (nf[1] != nf[1]);
-        if (__any_sync(0xffffffffu, bad) && (tid & 31) == 0) a.ok[t] = 0;
+        if (warp_bad && (tid & 31) == 0) a.ok[t] = 0;
         off = off_next;
         off_next = off_next2;
     }
@@ -756,9 +782,20 @@ cudaError_t launch_typed(const EvalArgs& e, cudaStream_t stream, int threads, si
     a.F = e.F; a.max_stack = e.max_stack; a.n_param_rows = e.n_param_rows; a.early_exit = e.early_exit;
     a.n_params = e.n_params; a.n_classes = e.n_classes;
     a.sync_tree = e.sync_tree;
+    a.smem_rows = e.smem_rows;
     dim3 grid((unsigned)n_tiles, (unsigned)e.n_chunks);
     const bool param = e.params != nullptr, loss = e.y != nullptr, fast = e.early_exit != 0;
     void (*kern)(const KArgs<T>);
+    if constexpr (sizeof(T) == 4 && U == 2) {
+        if (e.smem_rows > 0) {   // eval_num_tiles has checked: Float32, early exit, 256 threads, no parameter rows
+            kern = loss ? eval_kernel<T, U, true, false, true, DEX_MAX_THREADS, true>
+                        : eval_kernel<T, U, true, false, false, DEX_MAX_THREADS, true>;
+            cudaError_t err = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem);
+            if (err != cudaSuccess) return err;
+            kern<<<grid, threads, smem, stream>>>(a);
+            return cudaGetLastError();
+        }
+    }
     if (fast && threads == DEX_MAX_THREADS && sizeof(T) == 4) {
         constexpr int NT = sizeof(T) == 4 ? DEX_MAX_THREADS : 0;
         kern = loss ? (param ? eval_kernel<T, U, true, true, true, NT> : eval_kernel<T, U, true, false, true, NT>)
@@ -797,26 +834,40 @@ static int eval_pick_u(int dtype, size_t rows) {
     return (dtype == DEX_F32 && rows >= U1_ROWS) ? 1 : EVAL_U;
 }
 
-size_t eval_xt_bytes(int dtype, int32_t F, int32_t max_stack, int64_t N) {
+size_t eval_xt_bytes(int dtype, int32_t F, int32_t max_stack, int64_t N, bool wide_ok) {
     int threads;
     size_t smem;
-    const int64_t n_tiles = eval_num_tiles(dtype, F, max_stack, N, &threads, &smem);
+    const int64_t n_tiles = eval_num_tiles(dtype, F, max_stack, N, &threads, &smem, wide_ok);
     const int u = eval_pick_u(dtype, (size_t)F + (size_t)max_stack);
     const int64_t tile = (int64_t)threads * (dtype == DEX_F32 ? 4 : 2) * u;
     return (size_t)std::max<int64_t>(n_tiles * tile, 1) * (size_t)std::max(F, 1) * (dtype == DEX_F32 ? 4 : 8);
 }
 
+// Wide inputs (Float32, early exit, no parameter rows: `wide_ok`).  The rows of a 2 048-sample tile
+// cost 8 KB of shared memory each; beyond 9 rows only two CTAs fit where the registers allow three,
+// beyond 14 the block has to shrink.  The GX kernels keep GX_SMEM_ROWS rows in shared memory (the
+// stack and the first features) and read the other feature rows from the feature-major global copy
+// through L1 (C4 shard, 10 features + 4 stack rows: 16.5 -> 14.7 ms; the number of rows kept made no
+// measurable difference between 4 and 9).  3 x (8 x 8 KB + 1 KB reserved) = 195 KB of the SM's 228 KB.
+constexpr int GX_SMEM_ROWS = 8;
+
 int64_t eval_num_tiles(int dtype, int32_t F, int32_t max_stack, int64_t N, int* threads_out,
-                       size_t* smem_out) {
+                       size_t* smem_out, bool wide_ok, int* smem_rows_out) {
     const size_t es = dtype == DEX_F32 ? 4 : 8;
-    const size_t rows = (size_t)F + (size_t)max_stack;
-    const int K = (dtype == DEX_F32 ? 4 : 2) * eval_pick_u(dtype, rows);
+    const size_t all_rows = (size_t)F + (size_t)max_stack;
+    const int K = (dtype == DEX_F32 ? 4 : 2) * eval_pick_u(dtype, all_rows);
+    static const bool gx_off = getenv("DEXB200_NO_GX") != nullptr;
+    int gx_rows = std::max(GX_SMEM_ROWS, max_stack);
+    if (const char* env = getenv("DEXB200_GX_ROWS")) gx_rows = std::max(max_stack, std::min(atoi(env), 9));   // tuning knob
+    bool gx = wide_ok && !gx_off && dtype == DEX_F32 && K == 8 && all_rows > 9 && (int64_t)all_rows > gx_rows && max_stack <= 14 &&
+              N >= (int64_t)DEX_MAX_THREADS * K && N < ((int64_t)1 << 30) - DEX_MAX_THREADS * K;
     int threads = 256;
     bool forced = false;
     if (const char* env = getenv("DEXB200_THREADS")) {   // tuning knob for experiments
         const int v = atoi(env);
-        if (v >= 32 && v <= DEX_MAX_THREADS && v % 32 == 0) { threads = v; forced = true; }
+        if (v >= 32 && v <= DEX_MAX_THREADS && v % 32 == 0) { threads = v; forced = true; gx = gx && v == DEX_MAX_THREADS; }
     }
+    const size_t rows = gx ? (size_t)gx_rows : all_rows;
     // keep >= 2 CTAs resident per SM when possible; shrink the block if the rows do not fit
     const size_t budget = forced ? SMEM_LIMIT : SMEM_LIMIT / 2;
     while (threads > 32 && rows * (size_t)threads * K * es > budget) threads >>= 1;
@@ -827,6 +878,7 @@ int64_t eval_num_tiles(int dtype, int32_t F, int32_t max_stack, int64_t N, int* 
     if (smem == 0) smem = 16;
     if (threads_out) *threads_out = threads;
     if (smem_out) *smem_out = smem;
+    if (smem_rows_out) *smem_rows_out = gx ? gx_rows : 0;
     const int64_t tile = (int64_t)threads * K;
     return (N + tile - 1) / tile;
 }
@@ -835,7 +887,9 @@ cudaError_t launch_eval(const EvalArgs& e, cudaStream_t stream, int sm_count, in
     (void)sm_count;
     int threads;
     size_t smem;
-    const int64_t n_tiles = eval_num_tiles(e.dtype, e.F, e.max_stack + e.n_param_rows, e.N, &threads, &smem);
+    int smem_rows = 0;
+    const bool wide_ok = e.early_exit != 0 && e.params == nullptr;
+    const int64_t n_tiles = eval_num_tiles(e.dtype, e.F, e.max_stack + e.n_param_rows, e.N, &threads, &smem, wide_ok, &smem_rows);
     if (smem > SMEM_LIMIT) return cudaErrorInvalidConfiguration;
     if (e.n_trees == 0 || e.N == 0) return cudaSuccess;
     const int u = eval_pick_u(e.dtype, (size_t)e.F + (size_t)e.max_stack + (size_t)e.n_param_rows);
@@ -859,6 +913,7 @@ cudaError_t launch_eval(const EvalArgs& e, cudaStream_t stream, int sm_count, in
     EvalArgs k = e;   // the interpreter reads the staged copy
     k.X = e.xt;
     k.ldx = Npad;
+    k.smem_rows = smem_rows;   // > 0: the wide-input kernel (eval_num_tiles)
     err = e.dtype == DEX_F64 ? launch_typed<double, EVAL_U>(k, stream, threads, smem, n_tiles)
           : u == 1           ? launch_typed<float, 1>(k, stream, threads, smem, n_tiles)
                              : launch_typed<float, EVAL_U>(k, stream, threads, smem, n_tiles);

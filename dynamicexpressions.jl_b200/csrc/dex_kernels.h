@@ -52,15 +52,19 @@ struct EvalArgs {
     int32_t skip_prepass;       // the transposed copy of X and ok[] are already prepared (slice > 0)
     // launch shape chosen by the launcher
     int32_t threads;
+    // chosen by launch_eval: rows kept in shared memory by the wide-input kernel (0 = all of them)
+    int32_t smem_rows;
 };
 
 // Chooses the block size / shared memory, presets ok[], launches.  Returns cudaError_t.
 cudaError_t launch_eval(const EvalArgs& a, cudaStream_t stream, int sm_count, int* launches);
-size_t eval_xt_bytes(int dtype, int32_t F, int32_t max_stack, int64_t N);
+size_t eval_xt_bytes(int dtype, int32_t F, int32_t max_stack, int64_t N, bool wide_ok);
 // number of sample tiles launch_eval will use for (dtype, F, max_stack, N)
 // `max_stack` here = stack rows + parameter rows (every row in front of the features)
+// `wide_ok`: the launch may take the wide-input kernel (Float32, early exit, no parameter rows), which keeps
+// only *smem_rows_out rows in shared memory (0 = every row is in shared memory)
 int64_t eval_num_tiles(int dtype, int32_t F, int32_t max_stack, int64_t N, int* threads_out,
-                       size_t* smem_out);
+                       size_t* smem_out, bool wide_ok, int* smem_rows_out = nullptr);
 
 struct GradArgs {
     int dtype;

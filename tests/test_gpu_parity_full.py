@@ -77,6 +77,52 @@ def test_config4_shard_shape(oracle):
     assert len(errs) > 100
 
 
+_WIDE_CHILD = """
+import sys, numpy as np
+import dexb200
+from dexb200 import device as D, treegen
+F, N, out = int(sys.argv[1]), int(sys.argv[2]), sys.argv[3]
+ops = dexb200.OperatorEnum(treegen.OPSET_A)
+nodes, offsets = treegen.gen_population(200, 9, 2, 4, F, seed=8)
+X = np.random.default_rng(11).standard_normal((F, N)).astype(np.float32)
+pop = D.Population(None, ops, np.float32, wire=(nodes, offsets))
+o, ok = pop.eval(X)
+np.savez(out, o=o.cpu().numpy(), ok=ok.cpu().numpy())
+"""
+
+
+@pytest.mark.parametrize("F,N", [(12, 5000), (24, 3 * 2048), (60, 4099)])
+def test_wide_inputs_read_feature_rows_through_l1(F, N, oracle, tmp_path):
+    """More than 9 rows per 2 048-sample tile: the wide-input kernel keeps 8 rows in shared memory and
+    reads the other feature rows from the feature-major global copy (dex_eval.cu eval_num_tiles, GX).
+    Values vs the oracle, bit-equality with the all-shared-memory kernel (a child process with
+    DEXB200_NO_GX=1), fused loss vs the materialised rows."""
+    import os
+    import subprocess
+    import sys
+    ops = dexb200.OperatorEnum(treegen.OPSET_A)
+    nodes, offsets = treegen.gen_population(200, 9, 2, 4, F, seed=8)
+    X = np.random.default_rng(11).standard_normal((F, N)).astype(np.float32)
+    errs, ok = _check_population(oracle, nodes, offsets, ops, X, np.float32, label=f"wide input F={F} N={N}",
+                                 min_strict=0.7)
+    assert ok.sum() > 40
+    pop = D.Population(None, ops, np.float32, wire=(nodes, offsets))
+    out, dok = pop.eval(X)
+    out, dok = out.cpu().numpy(), dok.cpu().numpy().astype(bool)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, DEXB200_NO_GX="1", PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    dst = str(tmp_path / "nogx.npz")
+    subprocess.run([sys.executable, "-c", _WIDE_CHILD, str(F), str(N), dst], check=True, env=env, cwd=root)
+    ref = np.load(dst)
+    assert (ref["ok"].astype(bool) == dok).all()
+    assert np.array_equal(ref["o"][dok].view(np.uint32), out[dok].view(np.uint32))
+    y = np.random.default_rng(13).standard_normal(N).astype(np.float32)
+    loss, lok = pop.eval_loss(X, y)
+    assert (lok.cpu().numpy().astype(bool) == dok).all()
+    want = ((out.astype(np.float64) - y.astype(np.float64)[None]) ** 2).mean(axis=1)
+    np.testing.assert_allclose(loss.cpu().numpy()[dok], want[dok], rtol=1e-10)
+
+
 def test_config5_parametric_at_full_sample_count(oracle):
     """configs[4]: ParametricExpression, 3 parameters x 10 classes, 2^18 samples; every 4th tree."""
     ops = dexb200.OperatorEnum(treegen.OPSET_A)
