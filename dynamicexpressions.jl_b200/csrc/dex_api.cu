@@ -390,8 +390,8 @@ int run_eval(dex_ctx* ctx, const dex_population* cpop, const void* X, int32_t F,
     int threads;
     size_t smem;
     const int32_t front_rows = h.max_stack + h.n_param_rows;
-    const bool wide_ok = (eval_flags & DEX_EVAL_EARLY_EXIT) && !params;   // as launch_eval decides
-    const int64_t n_tiles = eval_num_tiles(h.dtype, F, front_rows, N, &threads, &smem, wide_ok);
+    const int wide = eval_wide_mode((eval_flags & DEX_EVAL_EARLY_EXIT) != 0, params != nullptr, y != nullptr);   // as launch_eval decides
+    const int64_t n_tiles = eval_num_tiles(h.dtype, F, front_rows, N, &threads, &smem, wide);
     if (n_tiles_out) *n_tiles_out = n_tiles;
     if (smem > 227 * 1024)
         return set_err(ctx, DEX_ERR_UNSUPPORTED,
@@ -419,7 +419,7 @@ int run_eval(dex_ctx* ctx, const dex_population* cpop, const void* X, int32_t F,
     a.n_chunks = (int32_t)n_chunks;
     a.max_stack = h.max_stack;
     a.n_param_rows = h.n_param_rows;
-    if ((rc = ensure_xt(ctx, eval_xt_bytes(h.dtype, F, front_rows, N, wide_ok)))) return rc;
+    if ((rc = ensure_xt(ctx, eval_xt_bytes(h.dtype, F, front_rows, N, wide)))) return rc;
     a.X = X; a.F = F; a.N = N; a.ldx = ldx; a.xt = ctx->xt;
     a.out = out; a.ldo = ldo; a.ok = ok;
     a.early_exit = (eval_flags & DEX_EVAL_EARLY_EXIT) ? 1 : 0;
@@ -845,7 +845,7 @@ int dex_eval_loss(dex_ctx* ctx, const dex_population* pop, const void* X_dev, in
     if (pop->h.n_trees == 0) return DEX_OK;
     int threads; size_t smem;
     const int64_t n_tiles = eval_num_tiles(pop->h.dtype, nfeatures, pop->h.folded->max_stack + pop->h.n_param_rows, std::max<int64_t>(nsamples, 1), &threads, &smem,
-                                           (eval_flags & DEX_EVAL_EARLY_EXIT) != 0);
+                                           eval_wide_mode((eval_flags & DEX_EVAL_EARLY_EXIT) != 0, false, true));
     // scratch: [sum of weights (256 B slot)] [partial sums: one per (tile, warp slot, tree); warps a
     // smaller CTA does not have leave their zero]
     constexpr int64_t kWarpSlots = 8;   // DEX_MAX_THREADS / 32 (dex_eval.cu)

@@ -58,6 +58,11 @@
 #endif
 // residual of the fused loss: the exact difference of the two values in double (default), or the
 // difference rounded to T first (what a caller computing `pred .- y` in T would square)
+// resident CTAs per SM the wide-input evaluation kernel is compiled for: 4 (64 registers, 20 bytes of
+// spills) beats 3 on wide inputs (C4 shard 14.8 -> 13.7 ms); its fused-loss form spills more and stays at 3
+#ifndef DEX_GX_MIN_CTAS
+#define DEX_GX_MIN_CTAS 4
+#endif
 #ifndef DEX_LOSS_RESIDUAL_IN_T
 #define DEX_LOSS_RESIDUAL_IN_T 0
 #endif
@@ -264,7 +269,7 @@ __device__ __forceinline__ void guard_inf(Vec<T, U>& r, const Vec<T, U>& x) {
 // NT: CTA size fixed at compile time (the full-size 256-thread launch: row and chunk strides
 // become immediates of the shared-memory accesses) or 0 = read blockDim.x.
 template <typename T, int U, bool FAST, bool PARAM, bool LOSS, int NT = 0, bool GX = false>
-__global__ void __launch_bounds__(DEX_MAX_THREADS, (U == 1 && sizeof(T) == 4) ? 4 : DEX_MIN_CTAS) eval_kernel(const KArgs<T> a) {
+__global__ void __launch_bounds__(DEX_MAX_THREADS, (U == 1 && sizeof(T) == 4) ? 4 : ((GX && !LOSS) ? DEX_GX_MIN_CTAS : DEX_MIN_CTAS)) eval_kernel(const KArgs<T> a) {
     using V = Vec<T, U>;
     constexpr int C = V::C;
     constexpr int K = V::K;
@@ -834,32 +839,37 @@ static int eval_pick_u(int dtype, size_t rows) {
     return (dtype == DEX_F32 && rows >= U1_ROWS) ? 1 : EVAL_U;
 }
 
-size_t eval_xt_bytes(int dtype, int32_t F, int32_t max_stack, int64_t N, bool wide_ok) {
+size_t eval_xt_bytes(int dtype, int32_t F, int32_t max_stack, int64_t N, int wide) {
     int threads;
     size_t smem;
-    const int64_t n_tiles = eval_num_tiles(dtype, F, max_stack, N, &threads, &smem, wide_ok);
+    const int64_t n_tiles = eval_num_tiles(dtype, F, max_stack, N, &threads, &smem, wide);
     const int u = eval_pick_u(dtype, (size_t)F + (size_t)max_stack);
     const int64_t tile = (int64_t)threads * (dtype == DEX_F32 ? 4 : 2) * u;
     return (size_t)std::max<int64_t>(n_tiles * tile, 1) * (size_t)std::max(F, 1) * (dtype == DEX_F32 ? 4 : 8);
 }
 
-// Wide inputs (Float32, early exit, no parameter rows: `wide_ok`).  The rows of a 2 048-sample tile
-// cost 8 KB of shared memory each; beyond 9 rows only two CTAs fit where the registers allow three,
-// beyond 14 the block has to shrink.  The GX kernels keep GX_SMEM_ROWS rows in shared memory (the
-// stack and the first features) and read the other feature rows from the feature-major global copy
-// through L1 (C4 shard, 10 features + 4 stack rows: 16.5 -> 14.7 ms; the number of rows kept made no
-// measurable difference between 4 and 9).  3 x (8 x 8 KB + 1 KB reserved) = 195 KB of the SM's 228 KB.
-constexpr int GX_SMEM_ROWS = 8;
+// Wide inputs (Float32, early exit, no parameter rows: `wide` = EVAL_WIDE_STORE / EVAL_WIDE_LOSS).  The rows
+// of a 2 048-sample tile cost 8 KB of shared memory each; beyond 9 rows only two CTAs fit where the
+// registers allow three, beyond 14 the block has to shrink.  The GX kernels keep only the first rows in
+// shared memory (the stack, and a few features in the loss form) and read the other feature rows from
+// the feature-major global copy through L1.  Measured on the C4 shard (10 features + 4 stack rows):
+// all rows in shared memory, 2 CTAs/SM 16.5 ms; 8 rows, 3 CTAs 14.7 ms (4..9 rows: 14.7-15.0);
+// 4 rows, 4 CTAs of 64 registers 13.7 ms.  Narrow inputs do not gain (C2 0.288 -> 0.314 ms, C6 37.9 ->
+// 39.9 ms: the predicated second load form costs ~5 instructions per row operand).
+constexpr int GX_SMEM_ROWS_STORE = 4;   // 4 x (4 x 8 KB + 1 KB reserved) = 132 KB of the SM's 228 KB
+constexpr int GX_SMEM_ROWS_LOSS = 8;    // 3 x (8 x 8 KB + 1 KB reserved) = 195 KB
 
 int64_t eval_num_tiles(int dtype, int32_t F, int32_t max_stack, int64_t N, int* threads_out,
-                       size_t* smem_out, bool wide_ok, int* smem_rows_out) {
+                       size_t* smem_out, int wide, int* smem_rows_out) {
     const size_t es = dtype == DEX_F32 ? 4 : 8;
     const size_t all_rows = (size_t)F + (size_t)max_stack;
     const int K = (dtype == DEX_F32 ? 4 : 2) * eval_pick_u(dtype, all_rows);
     static const bool gx_off = getenv("DEXB200_NO_GX") != nullptr;
-    int gx_rows = std::max(GX_SMEM_ROWS, max_stack);
+    const bool wide_ok = wide != EVAL_WIDE_NO;
+    int gx_rows = std::max(wide == EVAL_WIDE_LOSS ? GX_SMEM_ROWS_LOSS : GX_SMEM_ROWS_STORE, max_stack);
     if (const char* env = getenv("DEXB200_GX_ROWS")) gx_rows = std::max(max_stack, std::min(atoi(env), 9));   // tuning knob
-    bool gx = wide_ok && !gx_off && dtype == DEX_F32 && K == 8 && all_rows > 9 && (int64_t)all_rows > gx_rows && max_stack <= 14 &&
+    static const bool gx_force = getenv("DEXB200_GX_FORCE") != nullptr;   // experiments: narrow inputs too
+    bool gx = wide_ok && !gx_off && dtype == DEX_F32 && K == 8 && (all_rows > 9 || gx_force) && (int64_t)all_rows > gx_rows && max_stack <= 14 &&
               N >= (int64_t)DEX_MAX_THREADS * K && N < ((int64_t)1 << 30) - DEX_MAX_THREADS * K;
     int threads = 256;
     bool forced = false;
@@ -888,8 +898,8 @@ cudaError_t launch_eval(const EvalArgs& e, cudaStream_t stream, int sm_count, in
     int threads;
     size_t smem;
     int smem_rows = 0;
-    const bool wide_ok = e.early_exit != 0 && e.params == nullptr;
-    const int64_t n_tiles = eval_num_tiles(e.dtype, e.F, e.max_stack + e.n_param_rows, e.N, &threads, &smem, wide_ok, &smem_rows);
+    const int wide = eval_wide_mode(e.early_exit != 0, e.params != nullptr, e.y != nullptr);
+    const int64_t n_tiles = eval_num_tiles(e.dtype, e.F, e.max_stack + e.n_param_rows, e.N, &threads, &smem, wide, &smem_rows);
     if (smem > SMEM_LIMIT) return cudaErrorInvalidConfiguration;
     if (e.n_trees == 0 || e.N == 0) return cudaSuccess;
     const int u = eval_pick_u(e.dtype, (size_t)e.F + (size_t)e.max_stack + (size_t)e.n_param_rows);

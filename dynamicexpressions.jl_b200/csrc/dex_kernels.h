@@ -58,13 +58,19 @@ struct EvalArgs {
 
 // Chooses the block size / shared memory, presets ok[], launches.  Returns cudaError_t.
 cudaError_t launch_eval(const EvalArgs& a, cudaStream_t stream, int sm_count, int* launches);
-size_t eval_xt_bytes(int dtype, int32_t F, int32_t max_stack, int64_t N, bool wide_ok);
+// which wide-input kernel a launch may take (dex_eval.cu eval_num_tiles): none (Float64, early_exit = false,
+// parameter rows), the store form or the fused-loss form
+enum { EVAL_WIDE_NO = 0, EVAL_WIDE_STORE = 1, EVAL_WIDE_LOSS = 2 };
+inline int eval_wide_mode(bool early_exit, bool has_params, bool loss) {
+    return (!early_exit || has_params) ? EVAL_WIDE_NO : loss ? EVAL_WIDE_LOSS : EVAL_WIDE_STORE;
+}
+size_t eval_xt_bytes(int dtype, int32_t F, int32_t max_stack, int64_t N, int wide);
 // number of sample tiles launch_eval will use for (dtype, F, max_stack, N)
 // `max_stack` here = stack rows + parameter rows (every row in front of the features)
-// `wide_ok`: the launch may take the wide-input kernel (Float32, early exit, no parameter rows), which keeps
-// only *smem_rows_out rows in shared memory (0 = every row is in shared memory)
+// `wide`: the wide-input kernel the launch may take (it keeps only *smem_rows_out rows in shared memory;
+// 0 = every row is in shared memory)
 int64_t eval_num_tiles(int dtype, int32_t F, int32_t max_stack, int64_t N, int* threads_out,
-                       size_t* smem_out, bool wide_ok, int* smem_rows_out = nullptr);
+                       size_t* smem_out, int wide, int* smem_rows_out = nullptr);
 
 struct GradArgs {
     int dtype;
