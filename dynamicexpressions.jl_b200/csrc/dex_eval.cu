@@ -273,6 +273,7 @@ __global__ void __launch_bounds__(DEX_MAX_THREADS, (U == 1 && sizeof(T) == 4) ? 
     using V = Vec<T, U>;
     constexpr int C = V::C;
     constexpr int K = V::K;
+    static_assert(!GX || (NT == 256 && sizeof(T) == 4 && U == 2), "the GX loop hard-codes the chunk stride of 256 threads");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* rows = reinterpret_cast<T*>(smem_raw);
     const int tid = threadIdx.x;
@@ -680,8 +681,6 @@ __global__ void __launch_bounds__(DEX_MAX_THREADS, (U == 1 && sizeof(T) == 4) ? 
             }
         }
 
-        const bool bad = (nf[0] != nf[0]) || (nf[1] != nf[1]);
-        const bool warp_bad = __any_sync(0xffffffffu, bad);
         // ---- result row segment ----------------------------------------------------
         if (!LOSS) {
             T* o = a.out + (size_t)t * a.ldo + s0 + (size_t)tid * C;
@@ -696,6 +695,11 @@ __global__ void __launch_bounds__(DEX_MAX_THREADS, (U == 1 && sizeof(T) == 4) ? 
                     if (s0 + s < a.N) a.out[(size_t)t * a.ldo + s0 + s] = acc.v[k];
                 }
             }
+        }
+        const bool bad = (nf[0] != nf[0]) || (nf[1] != nf[1]);
+        const bool warp_bad = __any_sync(0xffffffffu, bad);
+        if (!LOSS) {
+            // stored above
         } else if (FAST && warp_bad) {
             // an incomplete tree has no loss (its row is unspecified under early exit): NaN, no epilogue
             if ((tid & 31) == 0)
@@ -848,15 +852,19 @@ size_t eval_xt_bytes(int dtype, int32_t F, int32_t max_stack, int64_t N, int wid
     return (size_t)std::max<int64_t>(n_tiles * tile, 1) * (size_t)std::max(F, 1) * (dtype == DEX_F32 ? 4 : 8);
 }
 
-// Wide inputs (Float32, early exit, no parameter rows: `wide` = EVAL_WIDE_STORE / EVAL_WIDE_LOSS).  The rows
-// of a 2 048-sample tile cost 8 KB of shared memory each; beyond 9 rows only two CTAs fit where the
-// registers allow three, beyond 14 the block has to shrink.  The GX kernels keep only the first rows in
-// shared memory (the stack, and a few features in the loss form) and read the other feature rows from
-// the feature-major global copy through L1.  Measured on the C4 shard (10 features + 4 stack rows):
-// all rows in shared memory, 2 CTAs/SM 16.5 ms; 8 rows, 3 CTAs 14.7 ms (4..9 rows: 14.7-15.0);
-// 4 rows, 4 CTAs of 64 registers 13.7 ms.  Narrow inputs do not gain (C2 0.288 -> 0.314 ms, C6 37.9 ->
-// 39.9 ms: the predicated second load form costs ~5 instructions per row operand).
-constexpr int GX_SMEM_ROWS_STORE = 4;   // 4 x (4 x 8 KB + 1 KB reserved) = 132 KB of the SM's 228 KB
+// The GX kernels (Float32, early exit, no parameter rows: `wide` = EVAL_WIDE_STORE / EVAL_WIDE_LOSS) keep
+// only the first rows in shared memory (the stack and a few features) and read the other feature rows from
+// the feature-major global copy through L1.  A row of a 2 048-sample tile costs 8 KB of shared memory: with
+// more than 9 rows only two CTAs used to fit where the registers allow three, beyond 14 the block had to
+// shrink.  With the shared memory out of the way the store form is compiled for FOUR resident CTAs (64
+// registers, 8 bytes of spills) and serves every input, narrow ones included:
+//   C4 shard (10 features + 4 stack rows): all rows in shared memory, 2 CTAs/SM 16.5 ms -> 12.97 ms
+//     (4 rows kept; 6 rows 13.09; 8 rows = 3 CTAs 13.6)
+//   C2 (5 features + 3 stack rows, 3 CTAs/SM before) 0.2778 -> 0.2578 ms in bench.py (3..6 rows kept:
+//     within 1 %);  C6 37.85 -> 37.16 ms with 6 rows kept (3..4 rows: 37.7)
+// The fused-loss form needs more registers (four CTAs: 72 bytes of spills, 46 ms against 38.5 on C6-loss):
+// it stays at three CTAs and is used for wide inputs only.
+constexpr int GX_SMEM_ROWS_STORE = 6;   // 4 x (6 x 8 KB + 1 KB reserved) = 196 KB of the SM's 228 KB
 constexpr int GX_SMEM_ROWS_LOSS = 8;    // 3 x (8 x 8 KB + 1 KB reserved) = 195 KB
 
 int64_t eval_num_tiles(int dtype, int32_t F, int32_t max_stack, int64_t N, int* threads_out,
@@ -868,9 +876,10 @@ int64_t eval_num_tiles(int dtype, int32_t F, int32_t max_stack, int64_t N, int* 
     const bool wide_ok = wide != EVAL_WIDE_NO;
     int gx_rows = std::max(wide == EVAL_WIDE_LOSS ? GX_SMEM_ROWS_LOSS : GX_SMEM_ROWS_STORE, max_stack);
     if (const char* env = getenv("DEXB200_GX_ROWS")) gx_rows = std::max(max_stack, std::min(atoi(env), 9));   // tuning knob
-    static const bool gx_force = getenv("DEXB200_GX_FORCE") != nullptr;   // experiments: narrow inputs too
-    bool gx = wide_ok && !gx_off && dtype == DEX_F32 && K == 8 && (all_rows > 9 || gx_force) && (int64_t)all_rows > gx_rows && max_stack <= 14 &&
+    bool gx = wide_ok && !gx_off && dtype == DEX_F32 && K == 8 && all_rows > 0 && max_stack <= 14 &&
+              (wide == EVAL_WIDE_STORE || (all_rows > 9 && (int64_t)all_rows > gx_rows)) &&
               N >= (int64_t)DEX_MAX_THREADS * K && N < ((int64_t)1 << 30) - DEX_MAX_THREADS * K;
+    gx_rows = (int)std::min<size_t>((size_t)gx_rows, all_rows);
     int threads = 256;
     bool forced = false;
     if (const char* env = getenv("DEXB200_THREADS")) {   // tuning knob for experiments

@@ -1,5 +1,5 @@
 #!/bin/bash
-# Runs on the GPU box (under gpurun).  Usage: bash profiles/run_profile.sh <tag> [eval|grad]
+# Runs on the GPU box (under gpurun).  Usage: bash profiles/run_profile.sh <tag> [eval|grad|c4]
 #   eval (default): launch list of the bench command, one full ncu capture of the eval kernel, then
 #                   the bench line itself (never under a profiler) and the reference arm
 #   grad:           one full ncu capture of the gradient kernel on C3
@@ -10,6 +10,11 @@ mkdir -p gpurun_out
 if [ "$WHAT" = "grad" ]; then
     ncu --set full --clock-control none --import-source on -k regex:grad_kernel -s 2 -c 1 \
         -f -o gpurun_out/prof_grad_${TAG} python benchmarks/profile_target.py C3 > gpurun_out/ncu_grad_${TAG}.log 2>&1
+    exit 0
+fi
+if [ "$WHAT" = "c4" ]; then   # the wide-input kernel on one C4 shard (10 features, depth-12 trees, 2^17 samples)
+    ncu --set full --clock-control none --import-source on -k regex:eval_kernel -s 1 -c 1 \
+        -f -o gpurun_out/prof_c4_${TAG} python benchmarks/profile_target.py C4 > gpurun_out/ncu_c4_${TAG}.log 2>&1
     exit 0
 fi
 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv \
