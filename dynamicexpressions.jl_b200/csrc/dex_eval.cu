@@ -269,7 +269,7 @@ __device__ __forceinline__ void guard_inf(Vec<T, U>& r, const Vec<T, U>& x) {
 // NT: CTA size fixed at compile time (the full-size 256-thread launch: row and chunk strides
 // become immediates of the shared-memory accesses) or 0 = read blockDim.x.
 template <typename T, int U, bool FAST, bool PARAM, bool LOSS, int NT = 0, bool GX = false>
-__global__ void __launch_bounds__(DEX_MAX_THREADS, (U == 1 && sizeof(T) == 4) ? 4 : ((GX && !LOSS) ? DEX_GX_MIN_CTAS : DEX_MIN_CTAS)) eval_kernel(const KArgs<T> a) {
+__global__ void __launch_bounds__(DEX_MAX_THREADS, (U == 1 && sizeof(T) == 4) ? 4 : ((GX && !LOSS && !PARAM) ? DEX_GX_MIN_CTAS : DEX_MIN_CTAS)) eval_kernel(const KArgs<T> a) {
     using V = Vec<T, U>;
     constexpr int C = V::C;
     constexpr int K = V::K;
@@ -797,8 +797,9 @@ cudaError_t launch_typed(const EvalArgs& e, cudaStream_t stream, int threads, si
     void (*kern)(const KArgs<T>);
     if constexpr (sizeof(T) == 4 && U == 2) {
         if (e.smem_rows > 0) {   // eval_num_tiles has checked: Float32, early exit, 256 threads, no parameter rows
-            kern = loss ? eval_kernel<T, U, true, false, true, DEX_MAX_THREADS, true>
-                        : eval_kernel<T, U, true, false, false, DEX_MAX_THREADS, true>;
+            kern = param  ? eval_kernel<T, U, true, true, false, DEX_MAX_THREADS, true>
+                   : loss ? eval_kernel<T, U, true, false, true, DEX_MAX_THREADS, true>
+                          : eval_kernel<T, U, true, false, false, DEX_MAX_THREADS, true>;
             cudaError_t err = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem);
             if (err != cudaSuccess) return err;
             kern<<<grid, threads, smem, stream>>>(a);
@@ -863,7 +864,9 @@ size_t eval_xt_bytes(int dtype, int32_t F, int32_t max_stack, int64_t N, int wid
 //   C2 (5 features + 3 stack rows, 3 CTAs/SM before) 0.2778 -> 0.2578 ms in bench.py (3..6 rows kept:
 //     within 1 %);  C6 37.85 -> 37.16 ms with 6 rows kept (3..4 rows: 37.7)
 // The fused-loss form needs more registers (four CTAs: 72 bytes of spills, 46 ms against 38.5 on C6-loss):
-// it stays at three CTAs and is used for wide inputs only.
+// it stays at three CTAs and is used for wide inputs only.  The parametric form (its class indices take
+// eight more registers) is compiled for three CTAs as well; with the stack and parameter rows only in
+// shared memory three fit where C5's 11 rows allowed two.
 constexpr int GX_SMEM_ROWS_STORE = 6;   // 4 x (6 x 8 KB + 1 KB reserved) = 196 KB of the SM's 228 KB
 constexpr int GX_SMEM_ROWS_LOSS = 8;    // 3 x (8 x 8 KB + 1 KB reserved) = 195 KB
 
@@ -877,7 +880,7 @@ int64_t eval_num_tiles(int dtype, int32_t F, int32_t max_stack, int64_t N, int* 
     int gx_rows = std::max(wide == EVAL_WIDE_LOSS ? GX_SMEM_ROWS_LOSS : GX_SMEM_ROWS_STORE, max_stack);
     if (const char* env = getenv("DEXB200_GX_ROWS")) gx_rows = std::max(max_stack, std::min(atoi(env), 9));   // tuning knob
     bool gx = wide_ok && !gx_off && dtype == DEX_F32 && K == 8 && all_rows > 0 && max_stack <= 14 &&
-              (wide == EVAL_WIDE_STORE || (all_rows > 9 && (int64_t)all_rows > gx_rows)) &&
+              (wide != EVAL_WIDE_LOSS || (all_rows > 9 && (int64_t)all_rows > gx_rows)) &&
               N >= (int64_t)DEX_MAX_THREADS * K && N < ((int64_t)1 << 30) - DEX_MAX_THREADS * K;
     gx_rows = (int)std::min<size_t>((size_t)gx_rows, all_rows);
     int threads = 256;

@@ -58,11 +58,12 @@ struct EvalArgs {
 
 // Chooses the block size / shared memory, presets ok[], launches.  Returns cudaError_t.
 cudaError_t launch_eval(const EvalArgs& a, cudaStream_t stream, int sm_count, int* launches);
-// which wide-input kernel a launch may take (dex_eval.cu eval_num_tiles): none (Float64, early_exit = false,
-// parameter rows), the store form or the fused-loss form
-enum { EVAL_WIDE_NO = 0, EVAL_WIDE_STORE = 1, EVAL_WIDE_LOSS = 2 };
+// which GX kernel a launch may take (dex_eval.cu eval_num_tiles): none (Float64, early_exit = false), the
+// store form, the fused-loss form or the parametric form
+enum { EVAL_WIDE_NO = 0, EVAL_WIDE_STORE = 1, EVAL_WIDE_LOSS = 2, EVAL_WIDE_PARAM = 3 };
 inline int eval_wide_mode(bool early_exit, bool has_params, bool loss) {
-    return (!early_exit || has_params) ? EVAL_WIDE_NO : loss ? EVAL_WIDE_LOSS : EVAL_WIDE_STORE;
+    if (!early_exit || (has_params && loss)) return EVAL_WIDE_NO;
+    return has_params ? EVAL_WIDE_PARAM : loss ? EVAL_WIDE_LOSS : EVAL_WIDE_STORE;
 }
 size_t eval_xt_bytes(int dtype, int32_t F, int32_t max_stack, int64_t N, int wide);
 // number of sample tiles launch_eval will use for (dtype, F, max_stack, N)
