@@ -51,7 +51,7 @@ if kind != "eval":
 scale = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1}
 rd = float(d["dram__bytes_read.sum"][1]) * scale[d["dram__bytes_read.sum"][0]]
 wr = float(d["dram__bytes_write.sum"][1]) * scale[d["dram__bytes_write.sum"][0]]
-json.dump({"kernel": "dex::eval_kernel<float, 2, true, false, false>",
+json.dump({"kernel": "dex::eval_kernel<float, 2, true, false, false, 256, true>",
            "source": f"ncu --set full, {rep} (one launch of bench.py configs[1])",
            "dram_bytes_read": rd, "dram_bytes_write": wr, "dram_bytes_per_launch": rd + wr},
           open("profiles/eval_kernel_traffic.json", "w"), indent=1)
