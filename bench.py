@@ -692,7 +692,7 @@ def main():
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "read_only_frac": (achieved * (NFEATURES * 4) / BYTES_PER_UNIT) / peak,
-                         "kernel": "dex::eval_kernel<float, 2, FAST, !PARAM, !LOSS, 256, GX> (64 registers, 4 CTAs per SM, feature rows beyond six through L1)",
+                         "kernel": "dex::eval_kernel<float, 2, true, false, false, 256, true> (GX form: 64 registers, 4 CTAs per SM, feature rows beyond six read through L1)",
                          "note": "an ALGORITHMIC-bytes ratio: X is L2-resident, real DRAM traffic (`traffic`) is the "
                                  "result writes only; the kernel is issue-bound (issue_roofline)"},
             "e2e": {"value": e2e_value, "unit": UNIT,
