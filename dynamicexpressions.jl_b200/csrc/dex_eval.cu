@@ -613,6 +613,15 @@ __global__ void __launch_bounds__(DEX_MAX_THREADS, (U == 1 && sizeof(T) == 4) ? 
                           "+r"(ins0.z), "+r"(ins0.w)
                         : "l"(ip), "r"(n), "r"(my_s), "r"(tile_b), "r"(cs_b), "l"(__cvta_generic_to_global(k_inv_pio4))
                         : "memory");
+                } else if constexpr (U == 2 && GX) {
+                    asm volatile(
+#include "dex_interp_f32_noexit_gx.inc"
+                        : "+r"(pc), "+f"(av[0]), "+f"(av[1]), "+f"(av[2]), "+f"(av[3]), "+f"(av[4]), "+f"(av[5]),
+                          "+f"(av[6]), "+f"(av[7]), "+f"(nfv[0]), "+f"(nfv[1]), "+r"(ins0.x), "+r"(ins0.y),
+                          "+r"(ins0.z), "+r"(ins0.w)
+                        : "l"(ip), "r"(n), "r"(my_s), "r"(tile_b), "r"(cs_b), "l"(__cvta_generic_to_global(k_inv_pio4)),
+                          "r"((uint32_t)a.smem_rows), "l"(__cvta_generic_to_global(xg)), "r"((uint32_t)a.ldx * 4u)
+                        : "memory");
                 } else if constexpr (U == 2) {
                     // early_exit = false: checks only where ALWAYS is set, GUARD substitution, no skipping
                     asm volatile(
@@ -797,7 +806,8 @@ cudaError_t launch_typed(const EvalArgs& e, cudaStream_t stream, int threads, si
     void (*kern)(const KArgs<T>);
     if constexpr (sizeof(T) == 4 && U == 2) {
         if (e.smem_rows > 0) {   // eval_num_tiles has checked: Float32, early exit, 256 threads, no parameter rows
-            kern = param  ? eval_kernel<T, U, true, true, false, DEX_MAX_THREADS, true>
+            kern = !fast  ? eval_kernel<T, U, false, false, false, DEX_MAX_THREADS, true>
+                   : param ? eval_kernel<T, U, true, true, false, DEX_MAX_THREADS, true>
                    : loss ? eval_kernel<T, U, true, false, true, DEX_MAX_THREADS, true>
                           : eval_kernel<T, U, true, false, false, DEX_MAX_THREADS, true>;
             cudaError_t err = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem);

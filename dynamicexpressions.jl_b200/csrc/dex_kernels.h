@@ -62,7 +62,8 @@ cudaError_t launch_eval(const EvalArgs& a, cudaStream_t stream, int sm_count, in
 // store form, the fused-loss form or the parametric form
 enum { EVAL_WIDE_NO = 0, EVAL_WIDE_STORE = 1, EVAL_WIDE_LOSS = 2, EVAL_WIDE_PARAM = 3 };
 inline int eval_wide_mode(bool early_exit, bool has_params, bool loss) {
-    if (!early_exit || (has_params && loss)) return EVAL_WIDE_NO;
+    if (!early_exit) return (has_params || loss) ? EVAL_WIDE_NO : EVAL_WIDE_STORE;
+    if (has_params && loss) return EVAL_WIDE_NO;
     return has_params ? EVAL_WIDE_PARAM : loss ? EVAL_WIDE_LOSS : EVAL_WIDE_STORE;
 }
 size_t eval_xt_bytes(int dtype, int32_t F, int32_t max_stack, int64_t N, int wide);

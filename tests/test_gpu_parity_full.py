@@ -106,6 +106,8 @@ def test_wide_inputs_read_feature_rows_through_l1(F, N, oracle, tmp_path):
     errs, ok = _check_population(oracle, nodes, offsets, ops, X, np.float32, label=f"wide input F={F} N={N}",
                                  min_strict=0.7)
     assert ok.sum() > 40
+    _check_population(oracle, nodes, offsets, ops, X, np.float32, ctx={"early_exit": False},
+                      label=f"wide input F={F} N={N} early_exit=false", min_strict=0.7)
     pop = D.Population(None, ops, np.float32, wire=(nodes, offsets))
     out, dok = pop.eval(X)
     out, dok = out.cpu().numpy(), dok.cpu().numpy().astype(bool)
