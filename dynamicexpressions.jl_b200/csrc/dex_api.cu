@@ -625,6 +625,23 @@ const char* dex_last_error(const dex_ctx* ctx) { return ctx ? ctx->last_error.c_
 
 int64_t dex_ctx_launch_count(const dex_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+int dex_eval_launch_info(const dex_population* pop, int32_t nfeatures, int64_t nsamples, int eval_flags,
+                         int loss, int parametric, int32_t* threads, int64_t* smem_bytes, int64_t* n_tiles,
+                         int32_t* smem_rows) {
+    if (!pop || nfeatures < 0 || nsamples < 0) return DEX_ERR_INVALID;
+    const PackedPopulation& h = *pop->h.folded;
+    int th = 0, rows = 0;
+    size_t smem = 0;
+    const int wide = eval_wide_mode((eval_flags & DEX_EVAL_EARLY_EXIT) != 0, parametric != 0, loss != 0);
+    const int64_t tiles = eval_num_tiles(h.dtype, nfeatures, h.max_stack + h.n_param_rows,
+                                         std::max<int64_t>(nsamples, 1), &th, &smem, wide, &rows);
+    if (threads) *threads = th;
+    if (smem_bytes) *smem_bytes = (int64_t)smem;
+    if (n_tiles) *n_tiles = tiles;
+    if (smem_rows) *smem_rows = rows;
+    return DEX_OK;
+}
+
 // ---- operators -------------------------------------------------------------------------
 int dex_optable_create(const int32_t* opcodes, const int32_t* degree_offsets, int max_degree,
                        dex_optable** out) {

@@ -73,6 +73,8 @@ ABI = {
     "dex_ipc_open": (C.c_int, [_P, _P, C.POINTER(_P)]),
     "dex_ipc_close": (C.c_int, [_P, _P]),
     "dex_ctx_launch_count": (_I64, [_P]),
+    "dex_eval_launch_info": (C.c_int, [_P, C.c_int32, _I64, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32),
+                                       C.POINTER(_I64), C.POINTER(_I64), C.POINTER(C.c_int32)]),
     "dex_population_copy_tape": (_I64, [_P, _P, _I64, _P]),
     "dex_population_copy_folded": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "dex_handler_name": (C.c_char_p, [C.c_int]),
@@ -335,6 +337,19 @@ class Population:
         lib().dex_population_get_info(self.h, C.byref(info))
         self.info = {k: getattr(info, k) for k, _ in _Info._fields_}
         self.n_nodes = self.info["n_nodes"]
+
+    def launch_info(self, nfeatures, nsamples, *, early_exit=True, loss=False, parametric=False):
+        """Launch geometry ``dex_eval`` / ``dex_eval_loss`` / ``dex_eval_parametric`` would choose (no device
+        needed): threads per CTA, shared memory per CTA, sample tiles, rows kept in shared memory
+        (0 = all; otherwise the remaining feature rows are read through L1 — dex_eval.cu eval_num_tiles)."""
+        th, rows = C.c_int32(), C.c_int32()
+        smem, tiles = _I64(), _I64()
+        rc = lib().dex_eval_launch_info(self.h, int(nfeatures), int(nsamples), EVAL_EARLY_EXIT if early_exit else 0,
+                                        int(bool(loss)), int(bool(parametric)), C.byref(th), C.byref(smem),
+                                        C.byref(tiles), C.byref(rows))
+        if rc != OK:
+            raise ValueError("dex_eval_launch_info: invalid arguments")
+        return {"threads": th.value, "smem_bytes": smem.value, "n_tiles": tiles.value, "smem_rows": rows.value}
 
     def __del__(self):
         try:

@@ -288,6 +288,14 @@ int dex_ipc_close(dex_ctx* ctx, void* p);
 /* ---- introspection (tests, benchmarks) -------------------------------------------------- */
 /* kernels launched through this context so far */
 int64_t dex_ctx_launch_count(const dex_ctx* ctx);
+/* launch geometry dex_eval / dex_eval_loss choose for a population (no device needed): threads per CTA,
+ * dynamic shared memory per CTA in bytes, sample tiles, and how many rows of a tile live in shared memory
+ * (0 = all of them; > 0 = the wide-input layout: the remaining feature rows are read from the global copy
+ * through L1).  eval_flags as for dex_eval; `loss` != 0 describes dex_eval_loss; `parametric` != 0
+ * dex_eval_parametric.  Returns DEX_OK or DEX_ERR_INVALID. */
+int dex_eval_launch_info(const dex_population* pop, int32_t nfeatures, int64_t nsamples, int eval_flags,
+                         int loss, int parametric, int32_t* threads, int64_t* smem_bytes, int64_t* n_tiles,
+                         int32_t* smem_rows);
 /* name of an interpreter handler id ("ADD_AR", "COS_R", ...; csrc/dex_tape.h), NULL if none */
 const char* dex_handler_name(int handler);
 /* copies the host image of the evaluation tape (16-byte instructions, csrc/dex_tape.h);

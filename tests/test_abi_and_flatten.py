@@ -98,6 +98,36 @@ def test_compute_without_gpu_fails_loudly():
     assert rc == -3 and b"no CPU fallback" in D.lib().dex_last_error(ctx.h)
 
 
+def test_launch_geometry_of_narrow_wide_and_short_inputs():
+    """Host logic of dex_eval.cu eval_num_tiles through dex_eval_launch_info (no device): Float32 early-exit
+    launches of at least one 2 048-sample tile keep at most six rows of a tile in shared memory (four CTAs of
+    48 KB per SM; the other feature rows are read through L1), the fused loss takes that layout for wide inputs
+    only, Float64 and inputs shorter than a tile keep every row in shared memory."""
+    N = dexb200.Node
+    ctx = D.host_context()
+    ops = dexb200.OperatorEnum({1: ("cos",), 2: ("+", "*")})
+    x = [N(feature=i + 1) for i in range(3)]
+    tree = N(2, N(1, N(1, x[0], x[1])), N(1, x[2], N(val=2.0)))        # needs a couple of stack rows
+    pop = D.Population([tree], ops, np.float32, ctx=ctx)
+    for F, N_ in ((5, 1 << 16), (10, 1 << 17), (60, 4099), (100, 1 << 20)):
+        li = pop.launch_info(F, N_)
+        assert li["threads"] == 256 and li["n_tiles"] == -(-N_ // 2048)
+        assert 0 < li["smem_rows"] <= 6 and li["smem_bytes"] == li["smem_rows"] * 2048 * 4
+        assert 4 * (li["smem_bytes"] + 1024) <= 228 * 1024             # four CTAs resident
+        assert pop.launch_info(F, N_, early_exit=False)["smem_rows"] == li["smem_rows"]
+    # the fused loss: all rows in shared memory for narrow inputs, eight for wide ones
+    narrow, wide = pop.launch_info(5, 1 << 16, loss=True), pop.launch_info(24, 1 << 16, loss=True)
+    assert narrow["smem_rows"] == 0 and wide["smem_rows"] == 8 and wide["threads"] == 256
+    assert 3 * (wide["smem_bytes"] + 1024) <= 228 * 1024
+    # shorter than one tile: the block shrinks, every row in shared memory
+    short = pop.launch_info(5, 100)
+    assert short["smem_rows"] == 0 and short["threads"] < 256 and short["n_tiles"] == 1
+    # Float64 keeps the all-shared-memory layout
+    pop64 = D.Population([tree], ops, np.float64, ctx=ctx)
+    assert pop64.launch_info(5, 1 << 16)["smem_rows"] == 0
+    assert D.lib().dex_eval_launch_info(None, 1, 1, 1, 0, 0, None, None, None, None) != D.OK
+
+
 def test_pack_validation_errors():
     ctx = D.host_context()
     ops = dexb200.OperatorEnum({1: ("cos",), 2: ("+",)})
